@@ -168,6 +168,20 @@ int lscpm_trace_host(LscpmScene* scene, const LscpmBatchDesc* batches, int32_t n
                      const LscpmSpectraDesc* spectra, uint64_t photon_begin, uint64_t photon_count,
                      uint64_t seed, int64_t* tallies_host);
 
+/* ---- resident batch plans --------------------------------------------------------------------- */
+/* The drivers trace thousands of time points (reference miniplant/full_simulation.py:106 applies one
+ * simulation per DataFrame row).  A plan lowers and uploads the batch descriptors and spectra once, so
+ * that repeated launches (more photons, other seeds, other photon ranges) start from inputs already
+ * resident in device memory.  lscpm_trace == plan_create + trace_plan + plan_destroy. */
+typedef struct LscpmPlan LscpmPlan;
+int lscpm_plan_create(LscpmScene* scene, const LscpmBatchDesc* batches, int32_t n_batches,
+                      const LscpmSpectraDesc* spectra, LscpmPlan** out);
+int lscpm_plan_destroy(LscpmPlan* plan);
+int lscpm_trace_plan(LscpmPlan* plan, uint64_t photon_begin, uint64_t photon_count, uint64_t seed,
+                     int64_t* tallies_dev, void* stream);
+/* Number of kernel launches the library has issued on the calling process so far (all entry points). */
+uint64_t lscpm_launch_count(void);
+
 /* ---- deterministic per-ray entry points (parity check #1, and pvtrace next_hit) -------------- */
 /*
  * For n rays given in WORLD coordinates (pos[3n], dir[3n], unit directions): the next interface

@@ -1,0 +1,1005 @@
+// lscpm.cu — kernels and C-ABI of liblscpm.so (see include/lscpm.h for the contract and the reference
+// interfaces each entry point replaces).  sm_100a only; no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/lscpm.h"
+#include "lscpm_device.cuh"
+
+using namespace lscpm;
+
+// =================================================================================================
+// kernels
+// =================================================================================================
+constexpr int TRACE_THREADS = 128;
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+struct TraceArgs {
+    const DevBatch* batches;
+    const float* spec_x;
+    const float* spec_cdf;
+    unsigned long long photon_begin;    // first photon index of every batch in this launch
+    unsigned long long photon_count;    // photons per batch in this launch
+    unsigned long long chunks_per_batch;
+    unsigned long long n_chunks;
+    unsigned int chunk;                  // photons per work item
+    uint2 key;
+    unsigned long long* work_counter;
+    unsigned long long* tallies;         // [n_batches][n_bins + LSCPM_N_COUNTERS]
+};
+
+// K2: persistent photon kernel.  Every lane carries one photon in registers and steps it until it
+// terminates; dead lanes are refilled at the top of the loop from the warp's current work item
+// (ballot + popc ranks), work items are claimed with one atomic per warp.  The photon's result depends only
+// on (seed, batch id, photon index) so the scheduling does not influence the tallies.
+__global__ void __launch_bounds__(TRACE_THREADS)
+trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceArgs A) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lane_lt = (1u << lane) - 1u;
+    const int stride = S.n_bins + LSCPM_N_COUNTERS;
+
+    unsigned long long cur = 0, end = 0;   // warp-uniform: photons [cur, end) of batch `cbatch` are unclaimed
+    int cbatch = 0;
+    bool more = true;                       // work items may remain in the global queue
+
+    Photon p;
+    Rng rng;
+    int batch = 0;
+    bool alive = false;
+    unsigned n_events = 0, n_emit = 0;
+
+    for (;;) {
+        // ---- refill dead lanes ------------------------------------------------------------------
+        bool want = !alive;
+        bool fresh = false;
+        unsigned long long g = 0;
+        while (true) {
+            const unsigned pending = __ballot_sync(FULL_MASK, want);
+            if (!pending) break;
+            if (cur >= end) {
+                if (!more) break;
+                unsigned long long id = 0;
+                if (lane == 0) id = atomicAdd(A.work_counter, 1ULL);
+                id = __shfl_sync(FULL_MASK, id, 0);
+                if (id >= A.n_chunks) { more = false; break; }
+                cbatch = (int)(id / A.chunks_per_batch);
+                cur = (id % A.chunks_per_batch) * (unsigned long long)A.chunk;
+                end = min(cur + (unsigned long long)A.chunk, A.photon_count);
+            }
+            const unsigned long long avail = end - cur;
+            const unsigned rank = __popc(pending & lane_lt);
+            if (want && rank < avail) {
+                g = A.photon_begin + cur + rank;
+                batch = cbatch;
+                want = false;
+                fresh = true;
+            }
+            cur += min((unsigned long long)__popc(pending), avail);
+        }
+        int bin = -1;
+        if (fresh) {
+            const DevBatch& B = A.batches[batch];
+            rng.key = A.key; rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32); rng.batch = B.batch_id; rng.calls = 0;
+            const RayStart r = generate_ray(S, B, A.spec_x, A.spec_cdf, rng);
+            p.dx = r.dx; p.dy = r.dy; p.dz = r.dz; p.wl = r.wl;
+            refresh_alphas(S, p);
+            StepOut so;
+            bin = photon_start(S, p, r.ox, r.oy, r.oz, B.anchor_on_top && r.dz < 0.f, r.ax, r.ay, rng, so);
+            n_events = p.n_surface; n_emit = 0;
+            alive = true;
+        } else if (alive) {
+            StepOut so;
+            bin = photon_step(S, p, rng, so);
+            if (so.event != EV_KILL) ++n_events;
+            if (so.event == EV_EMIT) ++n_emit;
+        }
+        if (alive && bin >= 0) {
+            unsigned long long* row = A.tallies + (size_t)batch * stride;
+            atomicAdd(row + bin, 1ULL);
+            atomicAdd(row + S.n_bins, (unsigned long long)n_events);
+            if (n_emit) atomicAdd(row + S.n_bins + 1, (unsigned long long)n_emit);
+            alive = false;
+        }
+        if (!__any_sync(FULL_MASK, alive) && !more && cur >= end) break;
+    }
+}
+
+// K1 (debug/emit): the rays a batch generates, in plate-local coordinates
+__global__ void emit_kernel(const __grid_constant__ DevScene S, const DevBatch* batch, const float* spec_x,
+                            const float* spec_cdf, unsigned long long photon_begin, long long n, uint2 key,
+                            float* out /* [n][7]: origin, direction, wavelength */) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long g = photon_begin + (unsigned long long)i;
+    Rng rng; rng.key = key; rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32); rng.batch = batch->batch_id; rng.calls = 0;
+    const RayStart r = generate_ray(S, *batch, spec_x, spec_cdf, rng);
+    float* o = out + 7 * i;
+    o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; o[3] = r.dx; o[4] = r.dy; o[5] = r.dz; o[6] = r.wl;
+}
+
+// K5: deterministic per-ray probe — next interface and both outgoing directions
+struct ProbeIn { float xr, y, z, dx, dy, dz; int kc, medium; };
+struct ProbeOut {
+    float t, n1, n2, R, cosi;
+    float nx, ny, nz, rx, ry, rz, tx, ty, tz;
+    int kind, face, ch, container, adj, found;
+};
+
+__global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* in, ProbeOut* out, long long n) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const ProbeIn q = in[i];
+    ProbeOut o;
+    memset(&o, 0, sizeof(o));
+    Photon p;
+    p.xr = q.xr; p.y = q.y; p.z = q.z; p.dx = q.dx; p.dy = q.dy; p.dz = q.dz; p.kc = q.kc; p.medium = q.medium;
+    p.wl = 555.f; p.a_plate = p.a_outer = p.a_inner = 0.f; p.steps = 0; p.n_surface = 0; p.emitted = 0;
+    float nx, ny, nz;
+    if (q.medium == MED_AIR) {
+        float t; int face;
+        const float xa = abs_x(S, p);
+        if (!box_enter(S, xa, p.y, p.z, p.dx, p.dy, p.dz, t, face)) { out[i] = o; return; }
+        o.found = 1; o.t = t; o.kind = SURF_BOX; o.face = face; o.container = MED_AIR; o.adj = MED_PLATE; o.ch = 0;
+        o.n1 = S.med[MED_AIR].n; o.n2 = S.med[MED_PLATE].n;
+        box_normal(face, nx, ny, nz);
+    } else {
+        const Hit h = find_hit(S, p);
+        o.found = 1; o.t = h.t; o.kind = h.kind; o.face = h.face; o.ch = h.ch; o.container = h.container; o.adj = h.adj;
+        o.n1 = h.n1; o.n2 = h.n2;
+        if (h.kind == SURF_BOX || h.kind == SURF_CAP) box_normal(h.face, nx, ny, nz);
+        else {
+            const int surf_ch = (p.medium == MED_PLATE) ? h.ch : p.kc;
+            float xr = fmaf(p.dx, h.t, p.xr) - (float)(surf_ch - p.kc) * S.pitch;
+            const float oz = fmaf(p.dz, h.t, p.z) - S.zc;
+            const float inv = rsqrtf(xr * xr + oz * oz);
+            nx = xr * inv; ny = 0.f; nz = oz * inv;
+        }
+    }
+    const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, o.n1, o.n2);
+    o.R = I.R; o.cosi = I.cosi; o.nx = I.nx; o.ny = I.ny; o.nz = I.nz;
+    Photon r = p; reflect_dir(r, I);
+    o.rx = r.dx; o.ry = r.dy; o.rz = r.dz;
+    if (I.R < 1.f) { Photon t = p; refract_dir(t, I, o.n1, o.n2); o.tx = t.dx; o.ty = t.dy; o.tz = t.dz; }
+    out[i] = o;
+}
+
+// follow with per-step recording (one thread per ray; used for photon paths and per-photon bins)
+struct FollowIn { float ox, oy, oz, dx, dy, dz, wl; };
+struct FollowStep { float x, y, z, dx, dy, dz, wl; int event, medium, ch, kind, face; };
+
+__global__ void follow_kernel(const __grid_constant__ DevScene S, const FollowIn* in, long long n, uint32_t batch_id,
+                              unsigned long long photon_begin, uint2 key, int max_steps, int* n_steps,
+                              FollowStep* steps, int* final_bin) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FollowIn q = in[i];
+    const unsigned long long g = photon_begin + (unsigned long long)i;
+    Rng rng; rng.key = key; rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32); rng.batch = batch_id; rng.calls = 0;
+    Photon p;
+    p.dx = q.dx; p.dy = q.dy; p.dz = q.dz; p.wl = q.wl;
+    p.kc = 0; p.xr = 0.f; p.y = 0.f; p.z = 0.f; p.medium = MED_AIR;
+    refresh_alphas(S, p);
+    int k = 0;
+    auto rec = [&](const StepOut& so) {
+        if (k < max_steps) {
+            FollowStep& s = steps[(size_t)i * max_steps + k];
+            s.x = abs_x(S, p); s.y = p.y; s.z = p.z; s.dx = p.dx; s.dy = p.dy; s.dz = p.dz; s.wl = p.wl;
+            s.event = so.event; s.medium = so.medium; s.ch = so.ch; s.kind = so.kind; s.face = so.face;
+        }
+        ++k;
+    };
+    StepOut so;
+    int bin = photon_start(S, p, q.ox, q.oy, q.oz, false, 0.f, 0.f, rng, so);
+    if (so.event != EV_GENERATE) rec(so);
+    while (bin < 0) {
+        bin = photon_step(S, p, rng, so);
+        rec(so);
+    }
+    n_steps[i] = k;
+    final_bin[i] = bin;
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+namespace {
+
+thread_local std::string g_error;
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const std::string& msg) { g_error = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(LSCPM_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CUDA_TRY(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) return cuda_fail(e__, #expr); } while (0)
+
+struct Vec3 { double x, y, z; };
+inline Vec3 mul_rt(const double* pose, Vec3 v) {   // R^T v for a row-major 4x4 pose
+    return {pose[0] * v.x + pose[4] * v.y + pose[8] * v.z, pose[1] * v.x + pose[5] * v.y + pose[9] * v.z,
+            pose[2] * v.x + pose[6] * v.y + pose[10] * v.z};
+}
+
+// bin layout shared with lscpm_b200/tally.py and oracle/
+struct BinLayout {
+    int n_bins = 0;
+    std::vector<int> exit_base, abs_base;
+};
+int n_components_of(const LscpmSceneDesc* d, int node) {
+    const int m = d->node_material[node];
+    return d->mat_comp_begin[m + 1] - d->mat_comp_begin[m];
+}
+BinLayout bin_layout(const LscpmSceneDesc* d) {
+    BinLayout L;
+    L.exit_base.assign(d->n_nodes, -1);
+    L.abs_base.assign(d->n_nodes, -1);
+    int next = 3;
+    for (int i = 1; i < d->n_nodes; ++i) { L.exit_base[i] = next; next += 6; }
+    for (int i = 0; i < d->n_nodes; ++i) { L.abs_base[i] = next; next += n_components_of(d, i); }
+    L.n_bins = next;
+    return L;
+}
+std::string bin_name(const LscpmSceneDesc* d, int bin) {
+    static const char* box_faces[6] = {"-x", "+x", "-y", "+y", "-z", "+z"};
+    static const char* cyl_faces[3] = {"side", "-cap", "+cap"};
+    if (bin == 0) return "kill";
+    if (bin == 1) return "exit/miss";
+    if (bin == 2) return "exit/entry_reflect";
+    const BinLayout L = bin_layout(d);
+    if (bin < 0 || bin >= L.n_bins) return "";
+    const int first_abs = L.abs_base[0];
+    if (bin < first_abs) {
+        const int node = 1 + (bin - 3) / 6, face = (bin - 3) % 6;
+        std::string f;
+        const int geom = d->node_geom[node];
+        if (geom == LSCPM_GEOM_BOX) f = box_faces[face];
+        else if (geom == LSCPM_GEOM_CYLINDER && face < 3) f = cyl_faces[face];
+        else if (geom == LSCPM_GEOM_SPHERE && face == 0) f = "surface";
+        else f = "unused" + std::to_string(face);
+        return std::string("exit/") + d->node_name[node] + "/" + f;
+    }
+    for (int i = d->n_nodes - 1; i >= 0; --i) {
+        if (bin >= L.abs_base[i] && bin < L.abs_base[i] + n_components_of(d, i)) {
+            const int c = bin - L.abs_base[i];
+            const int comp = d->mat_comp_begin[d->node_material[i]] + c;
+            const char* prefix = d->comp_kind[comp] == LSCPM_COMP_REACTOR ? "react/" : "absorb/";
+            return std::string(prefix) + d->node_name[i] + "/" + std::to_string(c);
+        }
+    }
+    return "";
+}
+
+int validate_desc(const LscpmSceneDesc* d) {
+    if (!d) return fail(LSCPM_EINVAL, "scene description is NULL");
+    if (d->n_nodes < 1 || !d->node_geom || !d->node_parent || !d->node_material || !d->node_size || !d->node_pose ||
+        !d->node_name)
+        return fail(LSCPM_EINVAL, "scene description has no nodes or NULL node arrays");
+    if (d->n_materials < 1 || !d->mat_refractive_index || !d->mat_comp_begin)
+        return fail(LSCPM_EINVAL, "scene description has no materials");
+    for (int i = 0; i < d->n_nodes; ++i) {
+        if (d->node_material[i] < 0 || d->node_material[i] >= d->n_materials)
+            return fail(LSCPM_EINVAL, "node material index out of range");
+        if (d->node_parent[i] >= i) return fail(LSCPM_EINVAL, "nodes must be in pre-order (parent before child)");
+        if (!d->node_name[i]) return fail(LSCPM_EINVAL, "node name is NULL");
+    }
+    if (d->mat_comp_begin[d->n_materials] != d->n_components) return fail(LSCPM_EINVAL, "component CSR does not match n_components");
+    for (int c = 0; c < d->n_components; ++c) {
+        if (d->comp_abs_table[c] >= d->n_tables || d->comp_ems_table[c] >= d->n_tables)
+            return fail(LSCPM_EINVAL, "component table index out of range");
+        if (d->comp_kind[c] == LSCPM_COMP_LUMINOPHORE && d->comp_ems_table[c] < 0)
+            return fail(LSCPM_EINVAL, "luminophore without an emission table");
+    }
+    for (int t = 0; t < d->n_tables; ++t) {
+        const int lo = d->table_begin[t], hi = d->table_begin[t + 1];
+        if (hi - lo < 2) return fail(LSCPM_EINVAL, "spectrum table needs at least two knots");
+        for (int i = lo + 1; i < hi; ++i)
+            if (!(d->table_x[i] > d->table_x[i - 1])) return fail(LSCPM_EINVAL, "spectrum table abscissae must increase");
+        for (int i = lo; i < hi; ++i)
+            if (!(d->table_y[i] >= 0.0)) return fail(LSCPM_EINVAL, "spectrum table ordinates must be non-negative");
+    }
+    return LSCPM_OK;
+}
+
+void trapezoid_cdf(const double* x, const double* y, int n, std::vector<double>& cdf) {
+    cdf.assign(n, 0.0);
+    for (int i = 1; i < n; ++i) cdf[i] = cdf[i - 1] + 0.5 * (y[i] + y[i - 1]) * (x[i] - x[i - 1]);
+    double peak = 0.0;
+    for (int i = 0; i < n; ++i) peak = std::max(peak, cdf[i]);
+    if (peak > 0) for (int i = 0; i < n; ++i) cdf[i] /= peak;
+}
+
+bool same_material(const LscpmSceneDesc* d, int ma, int mb) {
+    if (ma == mb) return true;
+    if (d->mat_refractive_index[ma] != d->mat_refractive_index[mb]) return false;
+    const int na = d->mat_comp_begin[ma + 1] - d->mat_comp_begin[ma], nb = d->mat_comp_begin[mb + 1] - d->mat_comp_begin[mb];
+    if (na != nb) return false;
+    for (int c = 0; c < na; ++c) {
+        const int a = d->mat_comp_begin[ma] + c, b = d->mat_comp_begin[mb] + c;
+        if (d->comp_kind[a] != d->comp_kind[b] || d->comp_coefficient[a] != d->comp_coefficient[b] ||
+            d->comp_abs_table[a] != d->comp_abs_table[b] || d->comp_ems_table[a] != d->comp_ems_table[b] ||
+            d->comp_quantum_yield[a] != d->comp_quantum_yield[b])
+            return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+struct LscpmScene {
+    int device = 0;
+    DevScene dev{};
+    // host copies needed to lower batches and to map results back to nodes / the world frame
+    double plate_pose[16]{};
+    double world_centre[3]{}, world_radius = 0;
+    double hx = 0, hy = 0, hz = 0, cx0 = 0, pitch = 1, zc = 0, r_o = 0, r_i = 0;
+    int n_ch = 0, has_inner = 0;
+    int node_plate = 1;
+    std::vector<int> node_outer, node_inner;
+    BinLayout layout;
+    std::vector<std::string> bin_names;
+    // device allocations
+    float *d_tab_x = nullptr, *d_tab_y = nullptr, *d_tab_cdf = nullptr;
+    int *d_tab_begin = nullptr, *d_abs_outer = nullptr, *d_abs_inner = nullptr;
+    unsigned long long* d_counters = nullptr;   // ring of work counters
+    std::atomic<unsigned> next_counter{0};
+    int n_sm = 0, blocks_per_sm = 0;
+};
+constexpr int COUNTER_RING = 256;
+
+struct LscpmPlan {
+    LscpmScene* scene = nullptr;
+    int n_batches = 0;
+    DevBatch* d_batches = nullptr;
+    float *d_spec_x = nullptr, *d_spec_cdf = nullptr;
+};
+
+namespace {
+
+int lower_medium(const LscpmSceneDesc* d, int material, DevMedium& m) {
+    m.n = (float)d->mat_refractive_index[material];
+    const int c0 = d->mat_comp_begin[material];
+    m.n_comp = d->mat_comp_begin[material + 1] - c0;
+    if (m.n_comp > MAX_COMP) return fail(LSCPM_EUNSUPPORTED, "more than 4 components in one material");
+    for (int c = 0; c < m.n_comp; ++c) {
+        DevComponent& dc = m.comp[c];
+        dc.kind = d->comp_kind[c0 + c];
+        dc.abs_table = d->comp_abs_table[c0 + c];
+        dc.ems_table = d->comp_ems_table[c0 + c];
+        dc.coef = (float)d->comp_coefficient[c0 + c];
+        dc.qy = (float)d->comp_quantum_yield[c0 + c];
+        if (dc.kind != LSCPM_COMP_ABSORBER && dc.kind != LSCPM_COMP_LUMINOPHORE && dc.kind != LSCPM_COMP_REACTOR)
+            return fail(LSCPM_EINVAL, "unknown component kind");
+    }
+    return LSCPM_OK;
+}
+
+// Recognise world > plate box > equally spaced y-parallel capillaries [> coaxial inner cylinder] and express it
+// in the plate-local frame.  Everything is done in double; the kernels get the rounded floats.
+int lower_scene(const LscpmSceneDesc* d, LscpmScene* s) {
+    const double tol = 1e-9;
+    if (d->n_nodes < 2) return fail(LSCPM_EUNSUPPORTED, "scene has no plate");
+    if (d->node_geom[0] != LSCPM_GEOM_SPHERE) return fail(LSCPM_EUNSUPPORTED, "world node must be a sphere");
+    if (n_components_of(d, 0) != 0) return fail(LSCPM_EUNSUPPORTED, "an absorbing world medium is not supported");
+    int plate = -1;
+    for (int i = 1; i < d->n_nodes; ++i)
+        if (d->node_parent[i] == 0) {
+            if (plate >= 0) return fail(LSCPM_EUNSUPPORTED, "more than one object directly inside the world");
+            plate = i;
+        }
+    if (plate < 0 || d->node_geom[plate] != LSCPM_GEOM_BOX) return fail(LSCPM_EUNSUPPORTED, "the object inside the world must be a box (the plate)");
+    s->node_plate = plate;
+    s->world_radius = d->node_size[0];
+    s->world_centre[0] = d->node_pose[3]; s->world_centre[1] = d->node_pose[7]; s->world_centre[2] = d->node_pose[11];
+    const double* P = d->node_pose + 16 * plate;
+    memcpy(s->plate_pose, P, sizeof(double) * 16);
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+            double dot = 0;
+            for (int k = 0; k < 3; ++k) dot += P[4 * k + r] * P[4 * k + c];
+            if (std::fabs(dot - (r == c ? 1.0 : 0.0)) > 1e-9) return fail(LSCPM_EUNSUPPORTED, "plate pose is not rigid");
+        }
+    s->hx = 0.5 * d->node_size[3 * plate]; s->hy = 0.5 * d->node_size[3 * plate + 1]; s->hz = 0.5 * d->node_size[3 * plate + 2];
+
+    struct Channel { double x, z; int outer, inner; };
+    std::vector<Channel> ch;
+    for (int i = 1; i < d->n_nodes; ++i) {
+        if (i == plate || d->node_parent[i] != plate) continue;
+        if (d->node_geom[i] != LSCPM_GEOM_CYLINDER)
+            return fail(LSCPM_EUNSUPPORTED, std::string("node '") + d->node_name[i] +
+                        "' is not a capillary cylinder (photovoltaic boxes are not supported by this build)");
+        const double* C = d->node_pose + 16 * i;
+        const Vec3 axis = mul_rt(P, {C[2], C[6], C[10]});                      // capillary z axis in plate coordinates
+        const Vec3 centre = mul_rt(P, {C[3] - P[3], C[7] - P[7], C[11] - P[11]});
+        if (std::fabs(std::fabs(axis.y) - 1.0) > tol || std::fabs(axis.x) > tol || std::fabs(axis.z) > tol)
+            return fail(LSCPM_EUNSUPPORTED, "capillaries must run along the plate's y axis");
+        if (std::fabs(centre.y) > tol || std::fabs(d->node_size[3 * i] - 2 * s->hy) > tol)
+            return fail(LSCPM_EUNSUPPORTED, "capillaries must span the plate exactly (end caps on the +-y faces)");
+        Channel c{centre.x, centre.z, i, -1};
+        for (int j = i + 1; j < d->n_nodes; ++j) {
+            if (d->node_parent[j] != i) continue;
+            if (c.inner >= 0 || d->node_geom[j] != LSCPM_GEOM_CYLINDER)
+                return fail(LSCPM_EUNSUPPORTED, "a capillary may hold exactly one coaxial inner cylinder");
+            const double* I = d->node_pose + 16 * j;
+            for (int k = 0; k < 12; ++k)
+                if (std::fabs(I[k] - C[k]) > tol) return fail(LSCPM_EUNSUPPORTED, "inner cylinder must be coaxial with its capillary");
+            if (std::fabs(d->node_size[3 * j] - d->node_size[3 * i]) > tol) return fail(LSCPM_EUNSUPPORTED, "inner cylinder must have the capillary's length");
+            for (int q = j + 1; q < d->n_nodes; ++q)
+                if (d->node_parent[q] == j) return fail(LSCPM_EUNSUPPORTED, "nesting deeper than capillary > inner cylinder");
+            c.inner = j;
+        }
+        ch.push_back(c);
+    }
+    for (int i = 1; i < d->n_nodes; ++i) {
+        const int par = d->node_parent[i];
+        if (i == plate || par == plate) continue;
+        if (par <= 0 || d->node_parent[par] != plate) return fail(LSCPM_EUNSUPPORTED, "unexpected node outside the plate hierarchy");
+    }
+    std::sort(ch.begin(), ch.end(), [](const Channel& a, const Channel& b) { return a.x < b.x; });
+    s->n_ch = (int)ch.size();
+    s->has_inner = 0;
+    if (!ch.empty()) {
+        const int o0 = ch[0].outer;
+        s->r_o = d->node_size[3 * o0 + 1];
+        s->has_inner = ch[0].inner >= 0;
+        s->r_i = s->has_inner ? d->node_size[3 * ch[0].inner + 1] : 0.0;
+        s->cx0 = ch[0].x; s->zc = ch[0].z;
+        s->pitch = ch.size() > 1 ? (ch.back().x - ch[0].x) / (double)(ch.size() - 1) : 1.0;
+        for (size_t k = 0; k < ch.size(); ++k) {
+            const Channel& c = ch[k];
+            if (std::fabs(c.x - (s->cx0 + k * s->pitch)) > tol || std::fabs(c.z - s->zc) > tol)
+                return fail(LSCPM_EUNSUPPORTED, "capillaries must be equally spaced in x at a common height");
+            if (std::fabs(d->node_size[3 * c.outer + 1] - s->r_o) > tol || !same_material(d, d->node_material[c.outer], d->node_material[o0]))
+                return fail(LSCPM_EUNSUPPORTED, "capillaries must share radius and material");
+            if ((c.inner >= 0) != (s->has_inner != 0)) return fail(LSCPM_EUNSUPPORTED, "either all or no capillaries have an inner cylinder");
+            if (c.inner >= 0 && (std::fabs(d->node_size[3 * c.inner + 1] - s->r_i) > tol ||
+                                 !same_material(d, d->node_material[c.inner], d->node_material[ch[0].inner])))
+                return fail(LSCPM_EUNSUPPORTED, "inner cylinders must share radius and material");
+            s->node_outer.push_back(c.outer);
+            s->node_inner.push_back(c.inner);
+        }
+        if (s->has_inner && !(s->r_i < s->r_o)) return fail(LSCPM_EUNSUPPORTED, "inner radius must be smaller than the capillary radius");
+        if (ch.size() > 1 && !(s->pitch > 2 * s->r_o)) return fail(LSCPM_EUNSUPPORTED, "capillaries overlap");
+        if (!(std::fabs(s->zc) + s->r_o < s->hz) || !(std::fabs(ch[0].x) + s->r_o < s->hx) || !(std::fabs(ch.back().x) + s->r_o < s->hx))
+            return fail(LSCPM_EUNSUPPORTED, "capillaries must lie strictly inside the plate");
+    }
+
+    DevScene& D = s->dev;
+    memset(&D, 0, sizeof(D));
+    D.hx = (float)s->hx; D.hy = (float)s->hy; D.hz = (float)s->hz;
+    D.cx0 = (float)s->cx0; D.pitch = (float)s->pitch; D.zc = (float)s->zc; D.inv_pitch = (float)(1.0 / s->pitch);
+    D.n_ch = s->n_ch; D.has_inner = s->has_inner;
+    D.r_o = (float)s->r_o; D.r_i = (float)s->r_i; D.r_o2 = (float)(s->r_o * s->r_o); D.r_i2 = (float)(s->r_i * s->r_i);
+    D.med[MED_AIR].n = (float)d->mat_refractive_index[d->node_material[0]];
+    D.med[MED_AIR].n_comp = 0;
+    int rc = lower_medium(d, d->node_material[plate], D.med[MED_PLATE]);
+    if (rc) return rc;
+    if (!ch.empty()) {
+        if ((rc = lower_medium(d, d->node_material[ch[0].outer], D.med[MED_OUTER]))) return rc;
+        if (s->has_inner && (rc = lower_medium(d, d->node_material[ch[0].inner], D.med[MED_INNER]))) return rc;
+    }
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) D.w2l[3 * r + c] = (float)P[4 * c + r];   // R^T
+    s->layout = bin_layout(d);
+    D.n_bins = s->layout.n_bins;
+    D.exit_base_plate = s->layout.exit_base[plate];
+    D.abs_base_plate = s->layout.abs_base[plate];
+    s->bin_names.resize(D.n_bins);
+    for (int b = 0; b < D.n_bins; ++b) s->bin_names[b] = bin_name(d, b);
+    return LSCPM_OK;
+}
+
+template <typename T>
+int upload(const std::vector<T>& host, T** dev) {
+    *dev = nullptr;
+    const size_t bytes = std::max<size_t>(host.size(), 1) * sizeof(T);
+    CUDA_TRY(cudaMalloc((void**)dev, bytes));
+    if (!host.empty()) CUDA_TRY(cudaMemcpy(*dev, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return LSCPM_OK;
+}
+
+// world -> plate-local helpers (double)
+inline void world_point_to_plate(const double* P, const double* w, double* out) {
+    const Vec3 v = mul_rt(P, {w[0] - P[3], w[1] - P[7], w[2] - P[11]});
+    out[0] = v.x; out[1] = v.y; out[2] = v.z;
+}
+inline void world_vec_to_plate(const double* P, const double* w, double* out) {
+    const Vec3 v = mul_rt(P, {w[0], w[1], w[2]});
+    out[0] = v.x; out[1] = v.y; out[2] = v.z;
+}
+inline void plate_vec_to_world(const double* P, const double* l, double* out) {
+    for (int r = 0; r < 3; ++r) out[r] = P[4 * r] * l[0] + P[4 * r + 1] * l[1] + P[4 * r + 2] * l[2];
+}
+inline void plate_point_to_world(const double* P, const double* l, double* out) {
+    plate_vec_to_world(P, l, out);
+    out[0] += P[3]; out[1] += P[7]; out[2] += P[11];
+}
+
+int lower_batch(const LscpmScene* s, const LscpmBatchDesc* b, const std::vector<int>& spec_begin, DevBatch& o) {
+    memset(&o, 0, sizeof(o));
+    if (b->light_kind != LSCPM_LIGHT_DIRECT && b->light_kind != LSCPM_LIGHT_DIFFUSE) return fail(LSCPM_EINVAL, "unknown light kind");
+    o.light_kind = b->light_kind;
+    o.batch_id = b->batch_id;
+    o.wavelength = (float)b->wavelength_nm;
+    if (b->spectrum >= 0) {
+        if (b->spectrum + 1 >= (int)spec_begin.size()) return fail(LSCPM_EINVAL, "batch spectrum index out of range");
+        o.spec_begin = spec_begin[b->spectrum];
+        o.spec_n = spec_begin[b->spectrum + 1] - spec_begin[b->spectrum];
+    } else {
+        o.spec_begin = -1; o.spec_n = 0;
+        if (!(b->wavelength_nm > 0)) return fail(LSCPM_EINVAL, "constant wavelength must be positive");
+    }
+    if (!(b->mask_half[0] >= 0) || !(b->mask_half[1] >= 0) || !(b->back_off >= 0)) return fail(LSCPM_EINVAL, "negative mask extent or back-off");
+    o.mask_half[0] = (float)b->mask_half[0]; o.mask_half[1] = (float)b->mask_half[1];
+    const double* P = s->plate_pose;
+    double A[12];
+    for (int c = 0; c < 4; ++c) {
+        const double col[3] = {b->mask_pose[c], b->mask_pose[4 + c], b->mask_pose[8 + c]};
+        double out[3];
+        if (c < 3) world_vec_to_plate(P, col, out); else world_point_to_plate(P, col, out);
+        for (int r = 0; r < 3; ++r) A[4 * r + c] = out[r];
+    }
+    for (int k = 0; k < 12; ++k) o.A[k] = (float)A[k];
+    if (b->light_kind == LSCPM_LIGHT_DIRECT) {
+        const double n2 = b->direction[0] * b->direction[0] + b->direction[1] * b->direction[1] + b->direction[2] * b->direction[2];
+        if (std::fabs(n2 - 1.0) > 1e-9) return fail(LSCPM_EINVAL, "beam direction must be a unit vector");
+        double dl[3];
+        world_vec_to_plate(P, b->direction, dl);
+        for (int k = 0; k < 3; ++k) o.dir[k] = (float)dl[k];
+    }
+    o.back_off = (float)b->back_off;
+    const double tilt = b->tilt_deg * M_PI / 180.0;
+    o.cos_tilt = (float)std::cos(tilt); o.sin_tilt = (float)std::sin(tilt);
+    // anchors on the top face?  (standard LSC-PM lights: reference utils.py:87-99 puts them exactly there)
+    const double tol = 1e-9;
+    const bool flat = std::fabs(A[8]) < tol && std::fabs(A[9]) < tol && std::fabs(A[11] - s->hz) < tol;
+    const double ex = std::fabs(A[0]) * b->mask_half[0] + std::fabs(A[1]) * b->mask_half[1] + std::fabs(A[3]);
+    const double ey = std::fabs(A[4]) * b->mask_half[0] + std::fabs(A[5]) * b->mask_half[1] + std::fabs(A[7]);
+    o.anchor_on_top = flat && ex <= s->hx + tol && ey <= s->hy + tol && b->back_off > 1e-6;
+    return LSCPM_OK;
+}
+
+int pick_counter(LscpmScene* s, cudaStream_t stream, unsigned long long** out) {
+    const unsigned slot = s->next_counter.fetch_add(1) % COUNTER_RING;
+    *out = s->d_counters + slot;
+    CUDA_TRY(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), stream));
+    return LSCPM_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+extern "C" {
+
+int lscpm_abi_version(void) { return LSCPM_ABI_VERSION; }
+const char* lscpm_last_error(void) { return g_error.c_str(); }
+uint64_t lscpm_launch_count(void) { return g_launches.load(); }
+
+int lscpm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int lscpm_desc_n_bins(const LscpmSceneDesc* desc) {
+    const int rc = validate_desc(desc);
+    if (rc) return rc;
+    return bin_layout(desc).n_bins;
+}
+
+int lscpm_desc_bin_name(const LscpmSceneDesc* desc, int bin, char* buf, int buf_len) {
+    const int rc = validate_desc(desc);
+    if (rc) return rc;
+    const std::string name = bin_name(desc, bin);
+    if (name.empty()) return fail(LSCPM_EINVAL, "bin index out of range");
+    if (buf && buf_len > 0) { strncpy(buf, name.c_str(), (size_t)buf_len - 1); buf[buf_len - 1] = 0; }
+    return (int)name.size();
+}
+
+int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out) {
+    if (!out) return fail(LSCPM_EINVAL, "out pointer is NULL");
+    *out = nullptr;
+    int rc = validate_desc(desc);
+    if (rc) return rc;
+    LscpmScene* s = new (std::nothrow) LscpmScene();
+    if (!s) return fail(LSCPM_ENOMEM, "out of host memory");
+    if ((rc = lower_scene(desc, s))) { delete s; return rc; }
+    auto bail = [&](int code) { lscpm_scene_destroy(s); return code; };
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        delete s;
+        return fail(LSCPM_ECUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= n_dev) { delete s; return fail(LSCPM_EINVAL, "device index out of range"); }
+    s->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { delete s; return cuda_fail(e, "cudaSetDevice"); }
+
+    std::vector<float> tx, ty, tc;
+    std::vector<int> tb(desc->n_tables + 1, 0);
+    for (int t = 0; t < desc->n_tables; ++t) {
+        const int lo = desc->table_begin[t], n = desc->table_begin[t + 1] - lo;
+        std::vector<double> cdf;
+        trapezoid_cdf(desc->table_x + lo, desc->table_y + lo, n, cdf);
+        tb[t] = (int)tx.size();
+        for (int i = 0; i < n; ++i) { tx.push_back((float)desc->table_x[lo + i]); ty.push_back((float)desc->table_y[lo + i]); tc.push_back((float)cdf[i]); }
+    }
+    tb[desc->n_tables] = (int)tx.size();
+    std::vector<int> abs_outer, abs_inner;
+    for (int k = 0; k < s->n_ch; ++k) {
+        abs_outer.push_back(s->layout.abs_base[s->node_outer[k]]);
+        abs_inner.push_back(s->node_inner[k] >= 0 ? s->layout.abs_base[s->node_inner[k]] : 0);
+    }
+    if ((rc = upload(tx, &s->d_tab_x)) || (rc = upload(ty, &s->d_tab_y)) || (rc = upload(tc, &s->d_tab_cdf)) ||
+        (rc = upload(tb, &s->d_tab_begin)) || (rc = upload(abs_outer, &s->d_abs_outer)) || (rc = upload(abs_inner, &s->d_abs_inner)))
+        return bail(rc);
+    if ((e = cudaMalloc((void**)&s->d_counters, sizeof(unsigned long long) * COUNTER_RING)) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc counters"));
+    s->dev.tab_x = s->d_tab_x; s->dev.tab_y = s->d_tab_y; s->dev.tab_cdf = s->d_tab_cdf; s->dev.tab_begin = s->d_tab_begin;
+    s->dev.abs_base_outer = s->d_abs_outer; s->dev.abs_base_inner = s->d_abs_inner;
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(cuda_fail(e, "cudaGetDeviceProperties"));
+    s->n_sm = prop.multiProcessorCount;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, trace_kernel, TRACE_THREADS, 0)) != cudaSuccess)
+        return bail(cuda_fail(e, "occupancy query (is the library built for this GPU's architecture?)"));
+    if (s->blocks_per_sm < 1) return bail(fail(LSCPM_ECUDA, "trace kernel does not fit on an SM"));
+    *out = s;
+    return LSCPM_OK;
+}
+
+int lscpm_scene_destroy(LscpmScene* s) {
+    if (!s) return LSCPM_OK;
+    cudaFree(s->d_tab_x); cudaFree(s->d_tab_y); cudaFree(s->d_tab_cdf); cudaFree(s->d_tab_begin);
+    cudaFree(s->d_abs_outer); cudaFree(s->d_abs_inner); cudaFree(s->d_counters);
+    delete s;
+    return LSCPM_OK;
+}
+
+int lscpm_scene_n_bins(const LscpmScene* s) { return s ? s->dev.n_bins : fail(LSCPM_EINVAL, "scene is NULL"); }
+
+int lscpm_scene_bin_name(const LscpmScene* s, int bin, char* buf, int buf_len) {
+    if (!s) return fail(LSCPM_EINVAL, "scene is NULL");
+    if (bin < 0 || bin >= s->dev.n_bins) return fail(LSCPM_EINVAL, "bin index out of range");
+    const std::string& name = s->bin_names[bin];
+    if (buf && buf_len > 0) { strncpy(buf, name.c_str(), (size_t)buf_len - 1); buf[buf_len - 1] = 0; }
+    return (int)name.size();
+}
+
+int lscpm_plan_create(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_batches, const LscpmSpectraDesc* spectra,
+                      LscpmPlan** out) {
+    if (!out) return fail(LSCPM_EINVAL, "out pointer is NULL");
+    *out = nullptr;
+    if (!s || !batches || n_batches < 1) return fail(LSCPM_EINVAL, "scene/batches missing");
+    CUDA_TRY(cudaSetDevice(s->device));
+    std::vector<float> sx, sc;
+    std::vector<int> sb(1, 0);
+    if (spectra && spectra->n_spectra > 0) {
+        for (int i = 0; i < spectra->n_spectra; ++i) {
+            const int lo = spectra->begin[i], n = spectra->begin[i + 1] - lo;
+            if (n < 2) return fail(LSCPM_EINVAL, "spectrum needs at least two knots");
+            double total = 0;
+            for (int k = 0; k < n; ++k) {
+                if (!(spectra->y[lo + k] >= 0)) return fail(LSCPM_EINVAL, "spectrum weights must be non-negative");
+                if (k && !(spectra->x[lo + k] > spectra->x[lo + k - 1])) return fail(LSCPM_EINVAL, "spectrum wavelengths must increase");
+                total += spectra->y[lo + k];
+            }
+            if (!(total > 0)) return fail(LSCPM_EINVAL, "spectrum is identically zero");
+            std::vector<double> cdf;
+            trapezoid_cdf(spectra->x + lo, spectra->y + lo, n, cdf);
+            for (int k = 0; k < n; ++k) { sx.push_back((float)spectra->x[lo + k]); sc.push_back((float)cdf[k]); }
+            sb.push_back((int)sx.size());
+        }
+    }
+    std::vector<DevBatch> lowered(n_batches);
+    for (int b = 0; b < n_batches; ++b) {
+        const int rc = lower_batch(s, batches + b, sb, lowered[b]);
+        if (rc) return rc;
+    }
+    LscpmPlan* p = new (std::nothrow) LscpmPlan();
+    if (!p) return fail(LSCPM_ENOMEM, "out of host memory");
+    p->scene = s; p->n_batches = n_batches;
+    int rc;
+    if ((rc = upload(lowered, &p->d_batches)) || (rc = upload(sx, &p->d_spec_x)) || (rc = upload(sc, &p->d_spec_cdf))) {
+        lscpm_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return LSCPM_OK;
+}
+
+int lscpm_plan_destroy(LscpmPlan* p) {
+    if (!p) return LSCPM_OK;
+    cudaFree(p->d_batches); cudaFree(p->d_spec_x); cudaFree(p->d_spec_cdf);
+    delete p;
+    return LSCPM_OK;
+}
+
+int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count, uint64_t seed, int64_t* tallies_dev, void* stream_) {
+    if (!p || !tallies_dev) return fail(LSCPM_EINVAL, "plan/tallies missing");
+    if (photon_count == 0) return LSCPM_OK;
+    LscpmScene* s = p->scene;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    CUDA_TRY(cudaSetDevice(s->device));
+    TraceArgs a{};
+    a.batches = p->d_batches; a.spec_x = p->d_spec_x; a.spec_cdf = p->d_spec_cdf;
+    a.photon_begin = photon_begin; a.photon_count = photon_count;
+    const int grid = s->n_sm * s->blocks_per_sm;
+    const unsigned long long n_warps = (unsigned long long)grid * (TRACE_THREADS / 32);
+    const unsigned long long total = photon_count * (unsigned long long)p->n_batches;
+    unsigned long long chunk = total / (n_warps * 8ULL);
+    chunk = std::min<unsigned long long>(std::max<unsigned long long>(chunk, 32ULL), 4096ULL);
+    chunk = std::min<unsigned long long>((chunk + 31ULL) / 32ULL * 32ULL, std::max<unsigned long long>(photon_count, 1ULL));
+    a.chunk = (unsigned)chunk;
+    a.chunks_per_batch = (photon_count + chunk - 1) / chunk;
+    a.n_chunks = a.chunks_per_batch * (unsigned long long)p->n_batches;
+    a.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    a.tallies = (unsigned long long*)tallies_dev;
+    int rc = pick_counter(s, stream, &a.work_counter);
+    if (rc) return rc;
+    const int blocks = (int)std::min<unsigned long long>((unsigned long long)grid, (a.n_chunks + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32));
+    trace_kernel<<<std::max(blocks, 1), TRACE_THREADS, 0, stream>>>(s->dev, a);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return LSCPM_OK;
+}
+
+int lscpm_trace(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_batches, const LscpmSpectraDesc* spectra,
+                uint64_t photon_begin, uint64_t photon_count, uint64_t seed, int64_t* tallies_dev, void* stream) {
+    LscpmPlan* plan = nullptr;
+    int rc = lscpm_plan_create(s, batches, n_batches, spectra, &plan);
+    if (rc) return rc;
+    rc = lscpm_trace_plan(plan, photon_begin, photon_count, seed, tallies_dev, stream);
+    // the launch reads the plan's device buffers: wait for it before releasing them
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    lscpm_plan_destroy(plan);
+    if (rc) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "trace kernel");
+    return LSCPM_OK;
+}
+
+int lscpm_trace_host(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_batches, const LscpmSpectraDesc* spectra,
+                     uint64_t photon_begin, uint64_t photon_count, uint64_t seed, int64_t* tallies_host) {
+    if (!s || !tallies_host) return fail(LSCPM_EINVAL, "scene/tallies missing");
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t n = (size_t)n_batches * (size_t)(s->dev.n_bins + LSCPM_N_COUNTERS);
+    int64_t* d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d, n * sizeof(int64_t)));
+    cudaError_t e = cudaMemset(d, 0, n * sizeof(int64_t));
+    int rc = e == cudaSuccess ? lscpm_trace(s, batches, n_batches, spectra, photon_begin, photon_count, seed, d, nullptr)
+                              : cuda_fail(e, "cudaMemset");
+    if (!rc && (e = cudaMemcpy(tallies_host, d, n * sizeof(int64_t), cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy tallies");
+    cudaFree(d);
+    return rc;
+}
+
+// ---- per-ray entry points ------------------------------------------------------------------------
+
+namespace {
+// pvtrace's geometric container test in double: a body contains the ray origin iff the ray has exactly one
+// forward intersection with it beyond the zero tolerance.
+constexpr double ZERO_TOL = 1e-12;
+int forward_hits_cylinder(double ox, double oz, double dx, double dz, double r, double y, double dy, double hy) {
+    // side roots clipped to |y| <= hy, plus caps inside the radius
+    int n = 0;
+    const double a = dx * dx + dz * dz, b = 2 * (ox * dx + oz * dz), c = ox * ox + oz * oz - r * r;
+    if (a > 0) {
+        const double disc = b * b - 4 * a * c;
+        if (disc >= 0) {
+            const double sq = std::sqrt(disc), q = -0.5 * (b + std::copysign(sq, b));
+            double t1 = q / a, t2 = q != 0 ? c / q : 0.0;
+            for (double t : {t1, t2})
+                if (t > ZERO_TOL && std::fabs(y + t * dy) <= hy) ++n;
+        }
+    }
+    if (dy != 0)
+        for (double yc : {-hy, hy}) {
+            const double t = (yc - y) / dy;
+            if (t > ZERO_TOL) { const double x = ox + t * dx, z = oz + t * dz; if (x * x + z * z < r * r) ++n; }
+        }
+    return n;
+}
+int forward_hits_box(const double* h, const double* o, const double* d) {
+    double tmin = -INFINITY, tmax = INFINITY;
+    for (int ax = 0; ax < 3; ++ax) {
+        if (d[ax] == 0) { if (std::fabs(o[ax]) > h[ax]) return 0; continue; }
+        double lo = (-h[ax] - o[ax]) / d[ax], hi = (h[ax] - o[ax]) / d[ax];
+        if (lo > hi) std::swap(lo, hi);
+        tmin = std::max(tmin, lo); tmax = std::min(tmax, hi);
+    }
+    if (tmin > tmax) return 0;
+    return (tmin > ZERO_TOL) + (tmax > ZERO_TOL);
+}
+
+// plate-local double ray -> medium + capillary-relative float coordinates
+void classify_ray(const LscpmScene* s, const double* o, const double* d, ProbeIn& q) {
+    int k = s->n_ch > 0 ? (int)std::lrint((o[0] - s->cx0) / s->pitch) : 0;
+    k = std::min(std::max(k, 0), std::max(s->n_ch - 1, 0));
+    const double xr = o[0] - (s->cx0 + k * s->pitch), oz = o[2] - s->zc;
+    q.kc = k; q.xr = (float)xr; q.y = (float)o[1]; q.z = (float)o[2];
+    q.dx = (float)d[0]; q.dy = (float)d[1]; q.dz = (float)d[2];
+    const double h[3] = {s->hx, s->hy, s->hz};
+    q.medium = MED_AIR;
+    if (forward_hits_box(h, o, d) == 1) {
+        q.medium = MED_PLATE;
+        if (s->n_ch > 0 && forward_hits_cylinder(xr, oz, d[0], d[2], s->r_o, o[1], d[1], s->hy) == 1) {
+            q.medium = MED_OUTER;
+            if (s->has_inner && forward_hits_cylinder(xr, oz, d[0], d[2], s->r_i, o[1], d[1], s->hy) == 1) q.medium = MED_INNER;
+        }
+    }
+}
+int node_of(const LscpmScene* s, int medium, int ch) {
+    if (medium == MED_AIR) return 0;
+    if (medium == MED_PLATE) return s->node_plate;
+    if (medium == MED_OUTER) return s->node_outer[ch];
+    return s->node_inner[ch];
+}
+}  // namespace
+
+int lscpm_probe(LscpmScene* s, int64_t n, const double* pos, const double* dir, int32_t* hit, int32_t* container,
+                int32_t* adjacent, int32_t* face, double* distance, double* point, double* normal, double* reflectivity,
+                double* reflected, double* refracted) {
+    if (!s || n < 0 || !pos || !dir) return fail(LSCPM_EINVAL, "scene/rays missing");
+    if (n == 0) return LSCPM_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    std::vector<ProbeIn> in((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        double o[3], d[3];
+        world_point_to_plate(s->plate_pose, pos + 3 * i, o);
+        world_vec_to_plate(s->plate_pose, dir + 3 * i, d);
+        classify_ray(s, o, d, in[(size_t)i]);
+    }
+    ProbeIn* d_in = nullptr; ProbeOut* d_out = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&d_in, sizeof(ProbeIn) * (size_t)n));
+    cudaError_t e = cudaMalloc((void**)&d_out, sizeof(ProbeOut) * (size_t)n);
+    if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(e, "cudaMalloc"); }
+    std::vector<ProbeOut> out((size_t)n);
+    e = cudaMemcpy(d_in, in.data(), sizeof(ProbeIn) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        probe_kernel<<<(unsigned)((n + 127) / 128), 128>>>(s->dev, d_in, d_out, n);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out.data(), d_out, sizeof(ProbeOut) * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return cuda_fail(e, "probe kernel");
+    for (int64_t i = 0; i < n; ++i) {
+        const ProbeOut& o = out[(size_t)i];
+        const ProbeIn& q = in[(size_t)i];
+        hit[i] = container[i] = adjacent[i] = face[i] = -1;
+        distance[i] = reflectivity[i] = 0;
+        for (int c = 0; c < 3; ++c) point[3 * i + c] = normal[3 * i + c] = reflected[3 * i + c] = refracted[3 * i + c] = 0;
+        if (!o.found) {
+            // nothing of the plate assembly ahead: pvtrace reports the world sphere (hit node 0, no adjacent)
+            hit[i] = 0; container[i] = 0; adjacent[i] = -1; face[i] = 0;
+            const double* pw = pos + 3 * i; const double* dw = dir + 3 * i;
+            const double oc[3] = {pw[0] - s->world_centre[0], pw[1] - s->world_centre[1], pw[2] - s->world_centre[2]};
+            const double b = oc[0] * dw[0] + oc[1] * dw[1] + oc[2] * dw[2];
+            const double c = oc[0] * oc[0] + oc[1] * oc[1] + oc[2] * oc[2] - s->world_radius * s->world_radius;
+            const double disc = b * b - c;
+            if (disc < 0 || -b + std::sqrt(disc) <= 0) { hit[i] = container[i] = -1; continue; }   // outside the world
+            distance[i] = -b + std::sqrt(disc);
+            for (int k = 0; k < 3; ++k) point[3 * i + k] = pw[k] + distance[i] * dw[k];
+            continue;
+        }
+        // node bookkeeping of pvtrace's next_hit for this interface
+        int h_node, c_node, a_node;
+        if (q.medium == MED_AIR) { h_node = s->node_plate; c_node = 0; a_node = s->node_plate; }
+        else if (o.kind == SURF_BOX) { h_node = c_node = s->node_plate; a_node = 0; }
+        else if (o.kind == SURF_CAP) { h_node = c_node = s->node_plate; a_node = s->node_outer[q.kc]; }
+        else if (o.kind == SURF_OUTER) {
+            if (q.medium == MED_PLATE) { h_node = a_node = s->node_outer[o.ch]; c_node = s->node_plate; }
+            else { h_node = c_node = s->node_outer[q.kc]; a_node = o.adj == MED_OUTER ? s->node_outer[o.ch] : s->node_plate; }
+        } else {
+            if (q.medium == MED_OUTER) { h_node = a_node = s->node_inner[q.kc]; c_node = s->node_outer[q.kc]; }
+            else { h_node = c_node = s->node_inner[q.kc]; a_node = o.adj == MED_PLATE ? s->node_plate : s->node_outer[q.kc]; }
+        }
+        hit[i] = h_node; container[i] = c_node; adjacent[i] = a_node;
+        face[i] = (o.kind == SURF_BOX || o.kind == SURF_CAP) ? o.face : 0;
+        distance[i] = o.t;
+        for (int c = 0; c < 3; ++c) point[3 * i + c] = pos[3 * i + c] + (double)o.t * dir[3 * i + c];
+        const double nl[3] = {o.nx, o.ny, o.nz}, rl[3] = {o.rx, o.ry, o.rz}, tl[3] = {o.tx, o.ty, o.tz};
+        plate_vec_to_world(s->plate_pose, nl, normal + 3 * i);
+        plate_vec_to_world(s->plate_pose, rl, reflected + 3 * i);
+        plate_vec_to_world(s->plate_pose, tl, refracted + 3 * i);
+        reflectivity[i] = o.R;
+    }
+    return LSCPM_OK;
+}
+
+int lscpm_emit(LscpmScene* s, const LscpmBatchDesc* batch, const LscpmSpectraDesc* spectra, uint64_t photon_begin,
+               int64_t n, uint64_t seed, double* pos, double* dir, double* wavelength) {
+    if (!s || !batch || n < 0) return fail(LSCPM_EINVAL, "scene/batch missing");
+    if (n == 0) return LSCPM_OK;
+    LscpmPlan* plan = nullptr;
+    int rc = lscpm_plan_create(s, batch, 1, spectra, &plan);
+    if (rc) return rc;
+    float* d_out = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_out, sizeof(float) * 7 * (size_t)n);
+    std::vector<float> out((size_t)n * 7);
+    if (e == cudaSuccess) {
+        emit_kernel<<<(unsigned)((n + 127) / 128), 128>>>(s->dev, plan->d_batches, plan->d_spec_x, plan->d_spec_cdf, photon_begin,
+                                                           n, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), d_out);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out.data(), d_out, sizeof(float) * 7 * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(d_out);
+    lscpm_plan_destroy(plan);
+    if (e != cudaSuccess) return cuda_fail(e, "emit kernel");
+    for (int64_t i = 0; i < n; ++i) {
+        const double o[3] = {out[7 * i], out[7 * i + 1], out[7 * i + 2]}, d[3] = {out[7 * i + 3], out[7 * i + 4], out[7 * i + 5]};
+        plate_point_to_world(s->plate_pose, o, pos + 3 * i);
+        plate_vec_to_world(s->plate_pose, d, dir + 3 * i);
+        wavelength[i] = out[7 * i + 6];
+    }
+    return LSCPM_OK;
+}
+
+int lscpm_follow(LscpmScene* s, int64_t n, const double* pos, const double* dir, const double* wavelength, uint32_t batch_id,
+                 uint64_t photon_begin, uint64_t seed, int32_t max_steps, int32_t* n_steps, int32_t* step_event,
+                 int32_t* step_node, double* step_pos, double* step_dir, double* step_wavelength, int32_t* final_bin) {
+    if (!s || n < 0 || !pos || !dir || !wavelength || !n_steps || !final_bin || max_steps < 0) return fail(LSCPM_EINVAL, "bad follow arguments");
+    if (n == 0) return LSCPM_OK;
+    CUDA_TRY(cudaSetDevice(s->device));
+    std::vector<FollowIn> in((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        double o[3], d[3];
+        world_point_to_plate(s->plate_pose, pos + 3 * i, o);
+        world_vec_to_plate(s->plate_pose, dir + 3 * i, d);
+        in[(size_t)i] = {(float)o[0], (float)o[1], (float)o[2], (float)d[0], (float)d[1], (float)d[2], (float)wavelength[i]};
+    }
+    const int ms = std::max(max_steps, 1);
+    FollowIn* d_in = nullptr; FollowStep* d_steps = nullptr; int *d_n = nullptr, *d_bin = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_in, sizeof(FollowIn) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_steps, sizeof(FollowStep) * (size_t)n * ms);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_n, sizeof(int) * (size_t)n);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_bin, sizeof(int) * (size_t)n);
+    std::vector<FollowStep> steps((size_t)n * ms);
+    std::vector<int> ns((size_t)n), bins((size_t)n);
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, in.data(), sizeof(FollowIn) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_steps, 0, sizeof(FollowStep) * (size_t)n * ms);
+    if (e == cudaSuccess) {
+        follow_kernel<<<(unsigned)((n + 127) / 128), 128>>>(s->dev, d_in, n, batch_id, photon_begin,
+                                                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), max_steps, d_n, d_steps, d_bin);
+        g_launches.fetch_add(1);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(steps.data(), d_steps, sizeof(FollowStep) * steps.size(), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ns.data(), d_n, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(bins.data(), d_bin, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(d_in); cudaFree(d_steps); cudaFree(d_n); cudaFree(d_bin);
+    if (e != cudaSuccess) return cuda_fail(e, "follow kernel");
+    for (int64_t i = 0; i < n; ++i) {
+        n_steps[i] = ns[(size_t)i];
+        final_bin[i] = bins[(size_t)i];
+        if (!step_event) continue;
+        for (int k = 0; k < std::min(ns[(size_t)i], max_steps); ++k) {
+            const FollowStep& st = steps[(size_t)i * ms + k];
+            const size_t at = (size_t)i * max_steps + k;
+            step_event[at] = st.event;
+            if (step_node) {
+                // node of the event: the surface's node for surface events, the container for absorption events
+                int node = -1;
+                if (st.event == EV_REFLECT || st.event == EV_TRANSMIT) {
+                    if (st.kind == SURF_BOX || st.kind == SURF_CAP) node = s->node_plate;
+                    else if (st.kind == SURF_OUTER) node = s->node_outer[st.ch];
+                    else if (st.kind == SURF_INNER) node = s->node_inner[st.ch];
+                } else if (st.event == EV_ABSORB || st.event == EV_REACT || st.event == EV_EMIT) node = node_of(s, st.medium, st.ch);
+                step_node[at] = node;
+            }
+            if (step_pos) { const double l[3] = {st.x, st.y, st.z}; plate_point_to_world(s->plate_pose, l, step_pos + 3 * at); }
+            if (step_dir) { const double l[3] = {st.dx, st.dy, st.dz}; plate_vec_to_world(s->plate_pose, l, step_dir + 3 * at); }
+            if (step_wavelength) step_wavelength[at] = st.wl;
+        }
+    }
+    return LSCPM_OK;
+}
+
+}  // extern "C"

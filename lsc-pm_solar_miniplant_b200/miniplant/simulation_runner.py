@@ -1,0 +1,98 @@
+"""Run a direct- or diffuse-light simulation — mirror of reference ``miniplant/simulation_runner.py``.
+
+Same entry points, arguments, return values and error behaviour; the per-photon Python loop
+(``for ray in scene.emit(n): photon_tracer.follow(scene, ray)``, reference ``:38-41``, or
+``scene.simulate(num_rays, workers)``, ``:62-63``) is replaced by one launch of the persistent CUDA
+photon kernel through the C-ABI of ``include/lscpm.h``.  Keyword-only extras (``seed``, ``device``,
+``return_tallies``) default to the reference's behaviour: unseeded, one float returned.
+"""
+from __future__ import annotations
+
+import logging
+from typing import Callable
+
+from ..backend import simulate_scene
+from ..compat import pvtrace_namespace
+from .scene_creator import create_direct_scene, create_diffuse_scene
+
+_pv = pvtrace_namespace()
+Scene, Event, MeshcatRenderer = _pv.Scene, _pv.Event, _pv.MeshcatRenderer
+
+logger = logging.getLogger("pvtrace").getChild("miniplant")
+
+PV_KEYWORDS = ("add_bottom_PV", "add_side_PV")
+
+
+def _common_simulation_runner(
+    scene: Scene,
+    num_photons: int = 100,
+    render: bool = False,
+    workers: int = 1,
+    *,
+    seed: int = None,
+    device=None,
+    return_tallies: bool = False,
+):
+    """Trace ``num_photons`` photons through ``scene`` and return the fraction absorbed by the reaction
+    mixture, ``count[Event.REACT] / num_photons`` (reference ``:65-66``).
+
+    ``workers`` selected a CPU process pool in the reference; on the GPU every photon of the call is traced
+    by one kernel launch, so the value only takes part in the reference's argument check."""
+    logger.debug(f"Starting ray-tracing with {num_photons} photons (Render is {render})")
+
+    if render and workers > 1:
+        raise RuntimeError("Sorry, cannot use renderer if more than 1 worker is used!")
+    if render:
+        # raises: the Meshcat visualiser is outside the hot path (out of scope)
+        MeshcatRenderer(open_browser=True)
+
+    result = simulate_scene(scene, num_photons, seed=seed, device=device)
+    reacted_fraction = result.reacted_fraction
+    logger.debug(f"*** SIMULATION ENDED *** (Efficiency was {reacted_fraction:.3f})")
+    if return_tallies:
+        return reacted_fraction, result
+    return reacted_fraction
+
+
+def run_direct_simulation(
+    tilt_angle: int = 0,
+    solar_elevation: int = 30,
+    solar_azimuth: int = 180,
+    solar_spectrum_function: Callable = lambda: 555,
+    num_photons: int = 100,
+    render: bool = False,
+    workers: int = 1,
+    include_dye: bool = None,
+    **kwargs,
+):
+    """Create a scene for direct irradiation with the provided parameters and run a simulation on it
+    (reference ``:83-105``)."""
+    runner_kwargs = {k: kwargs.pop(k) for k in ("seed", "device", "return_tallies") if k in kwargs}
+    scene = create_direct_scene(
+        tilt_angle=tilt_angle,
+        solar_elevation=solar_elevation,
+        solar_azimuth=solar_azimuth,
+        solar_spectrum_function=solar_spectrum_function,
+        include_dye=include_dye,
+        **kwargs,
+    )
+    return _common_simulation_runner(scene, num_photons, render, workers, **runner_kwargs)
+
+
+def run_diffuse_simulation(
+    tilt_angle: int = 0,
+    solar_spectrum_function: Callable = lambda: 555,
+    num_photons: int = 100,
+    render: bool = False,
+    workers: int = 1,
+    include_dye: bool = None,
+    **runner_kwargs,
+):
+    """Create a scene for diffuse irradiation with the provided parameters and run a simulation on it
+    (reference ``:108-124``)."""
+    scene = create_diffuse_scene(
+        tilt_angle=tilt_angle,
+        solar_spectrum_function=solar_spectrum_function,
+        include_dye=include_dye,
+    )
+    return _common_simulation_runner(scene, num_photons, render, workers, **runner_kwargs)

@@ -1,0 +1,57 @@
+"""The reference's own runner tests (reference tests/test_simulation_runner.py:12-33), unchanged in
+substance, now exercising the CUDA path through the mirrored entry points."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def green_photons():
+    return 555
+
+
+def red_photons():
+    return 700
+
+
+def test_run_direct_simulation(built_library):
+    from miniplant.simulation_runner import run_direct_simulation
+
+    good = run_direct_simulation(tilt_angle=40, solar_elevation=50, solar_azimuth=180,
+                                 solar_spectrum_function=green_photons, num_photons=200)
+    assert 0.20 <= good <= 0.40
+    bad = run_direct_simulation(tilt_angle=0, solar_elevation=10, solar_azimuth=180,
+                                solar_spectrum_function=red_photons, num_photons=200)
+    assert bad <= 0.2
+
+
+def test_run_diffuse_simulation(built_library):
+    from miniplant.simulation_runner import run_diffuse_simulation
+
+    standard = run_diffuse_simulation(solar_spectrum_function=green_photons)
+    assert 0.20 <= standard <= 0.40
+
+
+def test_render_with_workers_raises(built_library):
+    from miniplant.simulation_runner import run_direct_simulation
+
+    with pytest.raises(RuntimeError):
+        run_direct_simulation(render=True, workers=2)
+
+
+def test_unknown_wavelength_callable_is_host_emitted(built_library):
+    """An arbitrary random callable is not recognised by the flattener: rays are emitted on the host by the
+    scene's own callables and traced on the device."""
+    import random
+
+    from miniplant.simulation_runner import run_direct_simulation
+
+    rng = random.Random(3)
+    value = run_direct_simulation(tilt_angle=0, solar_elevation=90, solar_spectrum_function=lambda: rng.choice([555, 585]),
+                                  num_photons=4000, seed=1)
+    assert 0.25 <= value <= 0.35
+
+
+def test_smoke(built_library):
+    import __graft_entry__ as entry
+
+    entry.smoke()
