@@ -179,6 +179,8 @@ int lscpm_plan_create(LscpmScene* scene, const LscpmBatchDesc* batches, int32_t 
 int lscpm_plan_destroy(LscpmPlan* plan);
 int lscpm_trace_plan(LscpmPlan* plan, uint64_t photon_begin, uint64_t photon_count, uint64_t seed,
                      int64_t* tallies_dev, void* stream);
+/* Bytes lscpm_plan_create copied host->device for this plan (lowered batch descriptors + spectra). */
+uint64_t lscpm_plan_h2d_bytes(const LscpmPlan* plan);
 /* Number of kernel launches the library has issued on the calling process so far (all entry points). */
 uint64_t lscpm_launch_count(void);
 

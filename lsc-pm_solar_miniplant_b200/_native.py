@@ -171,6 +171,11 @@ _SIGNATURES = {
                               C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "lscpm_trace_host": (C.c_int, [C.c_void_p, C.POINTER(BatchDesc), C.c_int32, C.POINTER(SpectraDesc), C.c_uint64,
                                    C.c_uint64, C.c_uint64, c_int64_p]),
+    "lscpm_plan_create": (C.c_int, [C.c_void_p, C.POINTER(BatchDesc), C.c_int32, C.POINTER(SpectraDesc), C.POINTER(C.c_void_p)]),
+    "lscpm_plan_destroy": (C.c_int, [C.c_void_p]),
+    "lscpm_trace_plan": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "lscpm_plan_h2d_bytes": (C.c_uint64, [C.c_void_p]),
+    "lscpm_launch_count": (C.c_uint64, []),
     "lscpm_probe": (C.c_int, [C.c_void_p, C.c_int64, c_double_p, c_double_p, c_int32_p, c_int32_p, c_int32_p,
                               c_int32_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p]),
     "lscpm_emit": (C.c_int, [C.c_void_p, C.POINTER(BatchDesc), C.POINTER(SpectraDesc), C.c_uint64, C.c_int64,

@@ -357,6 +357,7 @@ struct LscpmPlan {
     int n_batches = 0;
     DevBatch* d_batches = nullptr;
     float *d_spec_x = nullptr, *d_spec_cdf = nullptr;
+    uint64_t h2d_bytes = 0;
 };
 
 namespace {
@@ -705,6 +706,7 @@ int lscpm_plan_create(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_ba
     LscpmPlan* p = new (std::nothrow) LscpmPlan();
     if (!p) return fail(LSCPM_ENOMEM, "out of host memory");
     p->scene = s; p->n_batches = n_batches;
+    p->h2d_bytes = lowered.size() * sizeof(DevBatch) + (sx.size() + sc.size()) * sizeof(float);
     int rc;
     if ((rc = upload(lowered, &p->d_batches)) || (rc = upload(sx, &p->d_spec_x)) || (rc = upload(sc, &p->d_spec_cdf))) {
         lscpm_plan_destroy(p);
@@ -713,6 +715,8 @@ int lscpm_plan_create(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_ba
     *out = p;
     return LSCPM_OK;
 }
+
+uint64_t lscpm_plan_h2d_bytes(const LscpmPlan* p) { return p ? p->h2d_bytes : 0; }
 
 int lscpm_plan_destroy(LscpmPlan* p) {
     if (!p) return LSCPM_OK;
