@@ -19,12 +19,16 @@ using namespace lscpm;
 // kernels
 // =================================================================================================
 constexpr int TRACE_THREADS = 128;
+#ifndef TRACE_MIN_BLOCKS
+#define TRACE_MIN_BLOCKS 8
+#endif
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 struct TraceArgs {
     const DevBatch* batches;
     const float* spec_x;
     const float* spec_cdf;
+    const unsigned short* spec_guide;
     unsigned long long photon_begin;    // first photon index of every batch in this launch
     unsigned long long photon_count;    // photons per batch in this launch
     unsigned long long chunks_per_batch;
@@ -35,15 +39,39 @@ struct TraceArgs {
     unsigned long long* tallies;         // [n_batches][n_bins + LSCPM_N_COUNTERS]
 };
 
+__device__ __forceinline__ bool counts_as_event(int ev) {
+    return ev == EV_REFLECT || ev == EV_TRANSMIT || ev == EV_ABSORB || ev == EV_REACT || ev == EV_EMIT;
+}
+
 // K2: persistent photon kernel.  Every lane carries one photon in registers and steps it until it
 // terminates; dead lanes are refilled at the top of the loop from the warp's current work item
-// (ballot + popc ranks), work items are claimed with one atomic per warp.  The photon's result depends only
-// on (seed, batch id, photon index) so the scheduling does not influence the tallies.
-__global__ void __launch_bounds__(TRACE_THREADS)
+// (ballot + popc ranks), work items are claimed with one atomic per warp.  A refilled lane generates its
+// photon from the SAME Philox draw the other lanes use for their step and then joins the common step for
+// its entry Fresnel test.  The photon's result depends only on (seed, batch id, photon index), so the
+// scheduling does not influence the tallies.
+// Per-warp tally rows live in shared memory: a warp adds the photons of the batch it is currently drawing from
+// to its own row with shared-memory atomics and flushes the row to the global tallies (one 64-bit atomic per
+// non-zero bin) when it moves on to another batch and at the end.  Stragglers of an earlier batch go to global
+// memory directly.  Without this the per-batch counters serialise in L2 (one hot address per batch).
+__device__ __forceinline__ void flush_row(unsigned int* hist, unsigned long long* row, int stride, int lane) {
+    __syncwarp();
+    for (int b = lane; b < stride; b += 32) {
+        const unsigned int v = hist[b];
+        if (v) { atomicAdd(row + b, (unsigned long long)v); hist[b] = 0u; }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceArgs A) {
+    extern __shared__ unsigned int smem_rows[];
     const int lane = threadIdx.x & 31;
     const unsigned lane_lt = (1u << lane) - 1u;
     const int stride = S.n_bins + LSCPM_N_COUNTERS;
+    unsigned int* hist = smem_rows + (threadIdx.x >> 5) * stride;
+    for (int b = lane; b < stride; b += 32) hist[b] = 0u;
+    __syncwarp();
+    int hbatch = -1;                        // warp-uniform: batch whose photons the shared row accumulates
 
     unsigned long long cur = 0, end = 0;   // warp-uniform: photons [cur, end) of batch `cbatch` are unclaimed
     int cbatch = 0;
@@ -53,13 +81,12 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
     Rng rng;
     int batch = 0;
     bool alive = false;
-    unsigned n_events = 0, n_emit = 0;
+    unsigned n_events = 0;                  // low 16 bits: interaction events, high 16 bits: emissions
 
     for (;;) {
         // ---- refill dead lanes ------------------------------------------------------------------
         bool want = !alive;
         bool fresh = false;
-        unsigned long long g = 0;
         while (true) {
             const unsigned pending = __ballot_sync(FULL_MASK, want);
             if (!pending) break;
@@ -72,56 +99,78 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
                 cbatch = (int)(id / A.chunks_per_batch);
                 cur = (id % A.chunks_per_batch) * (unsigned long long)A.chunk;
                 end = min(cur + (unsigned long long)A.chunk, A.photon_count);
+                if (cbatch != hbatch) {
+                    if (hbatch >= 0) flush_row(hist, A.tallies + (size_t)hbatch * stride, stride, lane);
+                    hbatch = cbatch;
+                }
             }
             const unsigned long long avail = end - cur;
             const unsigned rank = __popc(pending & lane_lt);
             if (want && rank < avail) {
-                g = A.photon_begin + cur + rank;
+                const unsigned long long g = A.photon_begin + cur + rank;
                 batch = cbatch;
+                rng.key = A.key; rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32);
+                rng.batch = A.batches[batch].batch_id; rng.calls = 0;
                 want = false;
                 fresh = true;
             }
             cur += min((unsigned long long)__popc(pending), avail);
         }
-        int bin = -1;
-        if (fresh) {
-            const DevBatch& B = A.batches[batch];
-            rng.key = A.key; rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32); rng.batch = B.batch_id; rng.calls = 0;
-            const RayStart r = generate_ray(S, B, A.spec_x, A.spec_cdf, rng);
-            p.dx = r.dx; p.dy = r.dy; p.dz = r.dz; p.wl = r.wl;
-            refresh_alphas(S, p);
-            StepOut so;
-            bin = photon_start(S, p, r.ox, r.oy, r.oz, B.anchor_on_top && r.dz < 0.f, r.ax, r.ay, rng, so);
-            n_events = p.n_surface; n_emit = 0;
-            alive = true;
-        } else if (alive) {
-            StepOut so;
-            bin = photon_step(S, p, rng, so);
-            if (so.event != EV_KILL) ++n_events;
-            if (so.event == EV_EMIT) ++n_emit;
+        const bool active = alive || fresh;
+        if (!__any_sync(FULL_MASK, active)) {
+            if (!more && cur >= end) break;
+            continue;
         }
-        if (alive && bin >= 0) {
-            unsigned long long* row = A.tallies + (size_t)batch * stride;
-            atomicAdd(row + bin, 1ULL);
-            atomicAdd(row + S.n_bins, (unsigned long long)n_events);
-            if (n_emit) atomicAdd(row + S.n_bins + 1, (unsigned long long)n_emit);
-            alive = false;
+        if (active) {
+            const uint4 w = rng.next();
+            float u_surf = u01(w.y);
+            int bin = -1;
+            bool step_now = true;
+            if (fresh) {
+                bin = generate_photon(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, w, p, nullptr);
+                alive = true;
+                n_events = 0;
+                u_surf = u01(w.w);
+                step_now = p.medium == MED_AIR;     // born inside the plate: take fresh uniforms next iteration
+            }
+            if (bin < 0 && step_now) {
+                StepOut so;
+                bin = photon_step(S, p, rng, w.x, u_surf, u01(w.z), so);
+                if (counts_as_event(so.event)) ++n_events;
+                if (so.event == EV_EMIT) n_events += 0x10000u;
+            }
+            if (bin >= 0) {
+                if (batch == hbatch) {
+                    atomicAdd(hist + bin, 1u);
+                    atomicAdd(hist + S.n_bins, n_events & 0xffffu);
+                    if (n_events >> 16) atomicAdd(hist + S.n_bins + 1, n_events >> 16);
+                } else {
+                    unsigned long long* row = A.tallies + (size_t)batch * stride;
+                    atomicAdd(row + bin, 1ULL);
+                    atomicAdd(row + S.n_bins, (unsigned long long)(n_events & 0xffffu));
+                    if (n_events >> 16) atomicAdd(row + S.n_bins + 1, (unsigned long long)(n_events >> 16));
+                }
+                alive = false;
+            }
         }
-        if (!__any_sync(FULL_MASK, alive) && !more && cur >= end) break;
     }
+    if (hbatch >= 0) flush_row(hist, A.tallies + (size_t)hbatch * stride, stride, lane);
 }
 
 // K1 (debug/emit): the rays a batch generates, in plate-local coordinates
 __global__ void emit_kernel(const __grid_constant__ DevScene S, const DevBatch* batch, const float* spec_x,
-                            const float* spec_cdf, unsigned long long photon_begin, long long n, uint2 key,
-                            float* out /* [n][7]: origin, direction, wavelength */) {
+                            const float* spec_cdf, const unsigned short* spec_guide, unsigned long long photon_begin,
+                            long long n, uint2 key, float* out /* [n][7]: origin, direction, wavelength */) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long g = photon_begin + (unsigned long long)i;
     Rng rng; rng.key = key; rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32); rng.batch = batch->batch_id; rng.calls = 0;
-    const RayStart r = generate_ray(S, *batch, spec_x, spec_cdf, rng);
+    const uint4 w = rng.next();
+    Photon p;
+    float origin[3];
+    generate_photon(S, *batch, spec_x, spec_cdf, spec_guide, rng, w, p, origin);
     float* o = out + 7 * i;
-    o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; o[3] = r.dx; o[4] = r.dy; o[5] = r.dz; o[6] = r.wl;
+    o[0] = origin[0]; o[1] = origin[1]; o[2] = origin[2]; o[3] = p.dx; o[4] = p.dy; o[5] = p.dz; o[6] = p.wl;
 }
 
 // K5: deterministic per-ray probe — next interface and both outgoing directions
@@ -139,34 +188,42 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
     ProbeOut o;
     memset(&o, 0, sizeof(o));
     Photon p;
-    p.xr = q.xr; p.y = q.y; p.z = q.z; p.dx = q.dx; p.dy = q.dy; p.dz = q.dz; p.kc = q.kc; p.medium = q.medium;
-    p.wl = 555.f; p.a_plate = p.a_outer = p.a_inner = 0.f; p.steps = 0; p.n_surface = 0; p.emitted = 0;
+    p.xr = q.xr; p.y = q.y; p.z = q.z - S.zc; p.dx = q.dx; p.dy = q.dy; p.dz = q.dz; p.kc = q.kc; p.medium = q.medium;
+    p.wl = 555.f; p.a_plate = p.a_outer = p.a_inner = 0.f; p.steps = 0; p.aux = 0;
     float nx, ny, nz;
     if (q.medium == MED_AIR) {
         float t; int face;
-        const float xa = abs_x(S, p);
-        if (!box_enter(S, xa, p.y, p.z, p.dx, p.dy, p.dz, t, face)) { out[i] = o; return; }
+        if (!box_enter(S, abs_x(S, p), p.y, q.z, p.dx, p.dy, p.dz, t, face)) { out[i] = o; return; }
         o.found = 1; o.t = t; o.kind = SURF_BOX; o.face = face; o.container = MED_AIR; o.adj = MED_PLATE; o.ch = 0;
-        o.n1 = S.med[MED_AIR].n; o.n2 = S.med[MED_PLATE].n;
         box_normal(face, nx, ny, nz);
     } else {
-        const Hit h = find_hit(S, p);
-        o.found = 1; o.t = h.t; o.kind = h.kind; o.face = h.face; o.ch = h.ch; o.container = h.container; o.adj = h.adj;
-        o.n1 = h.n1; o.n2 = h.n2;
+        // march over virtual cell crossings until a real interface
+        float travelled = 0.f;
+        Hit h = compute_hit(S, p);
+        while (h.kind == SURF_CELL) {
+            travelled += h.t;
+            p.y = fmaf(p.dy, h.t, p.y); p.z = fmaf(p.dz, h.t, p.z);
+            p.kc += h.face; p.xr = h.face > 0 ? -0.5f * S.pitch : 0.5f * S.pitch;
+            h = compute_hit(S, p);
+        }
+        const float xr = fmaf(p.dx, h.t, p.xr), yy = fmaf(p.dy, h.t, p.y), zz = fmaf(p.dz, h.t, p.z);
+        o.found = 1; o.t = travelled + h.t; o.kind = h.kind; o.face = h.face; o.ch = p.kc; o.container = h.container; o.adj = h.adj;
         if (h.kind == SURF_BOX || h.kind == SURF_CAP) box_normal(h.face, nx, ny, nz);
         else {
-            const int surf_ch = (p.medium == MED_PLATE) ? h.ch : p.kc;
-            float xr = fmaf(p.dx, h.t, p.xr) - (float)(surf_ch - p.kc) * S.pitch;
-            const float oz = fmaf(p.dz, h.t, p.z) - S.zc;
-            const float inv = rsqrtf(xr * xr + oz * oz);
-            nx = xr * inv; ny = 0.f; nz = oz * inv;
+            const float inv = rsqrtf(xr * xr + zz * zz);
+            nx = xr * inv; ny = 0.f; nz = zz * inv;
+            if (h.kind == SURF_OUTER && p.medium == MED_OUTER) {
+                const int j = sibling_ahead(S, p.kc, xr, yy, zz, p.dx, p.dy, p.dz);
+                if (j >= 0) { o.adj = MED_OUTER; o.ch = j; }
+            }
         }
     }
+    o.n1 = S.med[o.container].n; o.n2 = S.med[o.adj].n;
     const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, o.n1, o.n2);
     o.R = I.R; o.cosi = I.cosi; o.nx = I.nx; o.ny = I.ny; o.nz = I.nz;
     Photon r = p; reflect_dir(r, I);
     o.rx = r.dx; o.ry = r.dy; o.rz = r.dz;
-    if (I.R < 1.f) { Photon t = p; refract_dir(t, I, o.n1, o.n2); o.tx = t.dx; o.ty = t.dy; o.tz = t.dz; }
+    if (I.R < 1.f) { Photon t = p; refract_dir(t, I); o.tx = t.dx; o.ty = t.dy; o.tz = t.dz; }
     out[i] = o;
 }
 
@@ -184,23 +241,21 @@ __global__ void follow_kernel(const __grid_constant__ DevScene S, const FollowIn
     Rng rng; rng.key = key; rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32); rng.batch = batch_id; rng.calls = 0;
     Photon p;
     p.dx = q.dx; p.dy = q.dy; p.dz = q.dz; p.wl = q.wl;
-    p.kc = 0; p.xr = 0.f; p.y = 0.f; p.z = 0.f; p.medium = MED_AIR;
+    p.kc = 0; p.xr = 0.f; p.y = 0.f; p.z = 0.f; p.medium = MED_AIR; p.aux = 0;
     refresh_alphas(S, p);
     int k = 0;
-    auto rec = [&](const StepOut& so) {
+    int bin = place_photon(S, p, q.ox, q.oy, q.oz, false, 0.f, 0.f);
+    while (bin < 0) {
+        const uint4 w = rng.next();
+        StepOut so;
+        bin = photon_step(S, p, rng, w.x, u01(w.y), u01(w.z), so);
+        if (so.event == EV_NONE) continue;
         if (k < max_steps) {
             FollowStep& s = steps[(size_t)i * max_steps + k];
-            s.x = abs_x(S, p); s.y = p.y; s.z = p.z; s.dx = p.dx; s.dy = p.dy; s.dz = p.dz; s.wl = p.wl;
+            s.x = abs_x(S, p); s.y = p.y; s.z = p.z + S.zc; s.dx = p.dx; s.dy = p.dy; s.dz = p.dz; s.wl = p.wl;
             s.event = so.event; s.medium = so.medium; s.ch = so.ch; s.kind = so.kind; s.face = so.face;
         }
         ++k;
-    };
-    StepOut so;
-    int bin = photon_start(S, p, q.ox, q.oy, q.oz, false, 0.f, 0.f, rng, so);
-    if (so.event != EV_GENERATE) rec(so);
-    while (bin < 0) {
-        bin = photon_step(S, p, rng, so);
-        rec(so);
     }
     n_steps[i] = k;
     final_bin[i] = bin;
@@ -345,10 +400,12 @@ struct LscpmScene {
     std::vector<std::string> bin_names;
     // device allocations
     float *d_tab_x = nullptr, *d_tab_y = nullptr, *d_tab_cdf = nullptr;
-    int *d_tab_begin = nullptr, *d_abs_outer = nullptr, *d_abs_inner = nullptr;
+    unsigned short *d_tab_fwd = nullptr, *d_tab_inv = nullptr;
+    int *d_abs_outer = nullptr, *d_abs_inner = nullptr;
     unsigned long long* d_counters = nullptr;   // ring of work counters
     std::atomic<unsigned> next_counter{0};
     int n_sm = 0, blocks_per_sm = 0;
+    size_t trace_smem = 0;
 };
 constexpr int COUNTER_RING = 256;
 
@@ -357,6 +414,7 @@ struct LscpmPlan {
     int n_batches = 0;
     DevBatch* d_batches = nullptr;
     float *d_spec_x = nullptr, *d_spec_cdf = nullptr;
+    unsigned short* d_spec_guide = nullptr;
     uint64_t h2d_bytes = 0;
 };
 
@@ -377,6 +435,15 @@ int lower_medium(const LscpmSceneDesc* d, int material, DevMedium& m) {
         if (dc.kind != LSCPM_COMP_ABSORBER && dc.kind != LSCPM_COMP_LUMINOPHORE && dc.kind != LSCPM_COMP_REACTOR)
             return fail(LSCPM_EINVAL, "unknown component kind");
     }
+    int n_tab = 0;
+    m.single_tab = -1;
+    double const_sum = 0;
+    for (int c = 0; c < m.n_comp; ++c) {
+        if (m.comp[c].abs_table >= 0) { ++n_tab; m.single_tab = c; }
+        else const_sum += d->comp_coefficient[c0 + c];
+    }
+    if (n_tab != 1) m.single_tab = -1;
+    m.const_sum = (float)const_sum;
     return LSCPM_OK;
 }
 
@@ -472,10 +539,24 @@ int lower_scene(const LscpmSceneDesc* d, LscpmScene* s) {
 
     DevScene& D = s->dev;
     memset(&D, 0, sizeof(D));
+    if (d->n_tables > MAX_TABLES) return fail(LSCPM_EUNSUPPORTED, "more than 8 spectrum tables in one scene");
     D.hx = (float)s->hx; D.hy = (float)s->hy; D.hz = (float)s->hz;
-    D.cx0 = (float)s->cx0; D.pitch = (float)s->pitch; D.zc = (float)s->zc; D.inv_pitch = (float)(1.0 / s->pitch);
-    D.n_ch = s->n_ch; D.has_inner = s->has_inner;
-    D.r_o = (float)s->r_o; D.r_i = (float)s->r_i; D.r_o2 = (float)(s->r_o * s->r_o); D.r_i2 = (float)(s->r_i * s->r_i);
+    D.has_caps = s->n_ch > 0;
+    D.has_inner = s->has_inner;
+    if (s->n_ch > 0) {
+        D.cx0 = (float)s->cx0; D.pitch = (float)s->pitch; D.zc = (float)s->zc; D.inv_pitch = (float)(1.0 / s->pitch);
+        D.n_ch = s->n_ch;
+        D.cell_lo_first = (float)(-s->hx - s->cx0);
+        D.cell_hi_last = (float)(s->hx - (s->cx0 + (s->n_ch - 1) * s->pitch));
+        D.r_o = (float)s->r_o; D.r_o2 = (float)(s->r_o * s->r_o);
+        D.r_i = (float)s->r_i; D.r_i2 = s->has_inner ? (float)(s->r_i * s->r_i) : -1.f;
+    } else {
+        // a bare plate is one cell without a capillary: negative squared radii never produce a root
+        D.cx0 = 0.f; D.pitch = (float)(4 * s->hx); D.zc = 0.f; D.inv_pitch = (float)(1.0 / (4 * s->hx));
+        D.n_ch = 1;
+        D.cell_lo_first = (float)(-s->hx); D.cell_hi_last = (float)s->hx;
+        D.r_o = D.r_i = 0.f; D.r_o2 = D.r_i2 = -1.f;
+    }
     D.med[MED_AIR].n = (float)d->mat_refractive_index[d->node_material[0]];
     D.med[MED_AIR].n_comp = 0;
     int rc = lower_medium(d, d->node_material[plate], D.med[MED_PLATE]);
@@ -531,6 +612,7 @@ int lower_batch(const LscpmScene* s, const LscpmBatchDesc* b, const std::vector<
         if (b->spectrum + 1 >= (int)spec_begin.size()) return fail(LSCPM_EINVAL, "batch spectrum index out of range");
         o.spec_begin = spec_begin[b->spectrum];
         o.spec_n = spec_begin[b->spectrum + 1] - spec_begin[b->spectrum];
+        o.spec_guide = b->spectrum * (SPEC_BUCKETS + 1);
     } else {
         o.spec_begin = -1; o.spec_n = 0;
         if (!(b->wavelength_nm > 0)) return fail(LSCPM_EINVAL, "constant wavelength must be positive");
@@ -625,30 +707,61 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
     if ((e = cudaSetDevice(device)) != cudaSuccess) { delete s; return cuda_fail(e, "cudaSetDevice"); }
 
     std::vector<float> tx, ty, tc;
-    std::vector<int> tb(desc->n_tables + 1, 0);
+    std::vector<unsigned short> fwd, inv;
     for (int t = 0; t < desc->n_tables; ++t) {
         const int lo = desc->table_begin[t], n = desc->table_begin[t + 1] - lo;
+        if (n > 65000) return bail(fail(LSCPM_EUNSUPPORTED, "spectrum table with more than 65000 knots"));
+        const double* x = desc->table_x + lo;
         std::vector<double> cdf;
-        trapezoid_cdf(desc->table_x + lo, desc->table_y + lo, n, cdf);
-        tb[t] = (int)tx.size();
-        for (int i = 0; i < n; ++i) { tx.push_back((float)desc->table_x[lo + i]); ty.push_back((float)desc->table_y[lo + i]); tc.push_back((float)cdf[i]); }
+        trapezoid_cdf(x, desc->table_y + lo, n, cdf);
+        DevTable& T = s->dev.tab[t];
+        T.begin = (int)tx.size(); T.n = n;
+        for (int i = 0; i < n; ++i) { tx.push_back((float)x[i]); ty.push_back((float)desc->table_y[lo + i]); tc.push_back((float)cdf[i]); }
+        // forward index: bucket width = smallest knot spacing (capped at 16384 buckets; table_at() then walks a little)
+        double wmin = x[n - 1] - x[0];
+        for (int i = 1; i < n; ++i) wmin = std::min(wmin, x[i] - x[i - 1]);
+        const double range = x[n - 1] - x[0];
+        int nb = (int)std::ceil(range / wmin);
+        nb = std::max(1, std::min(nb, 16384));
+        const double w = range / nb;
+        T.x0 = (float)x[0]; T.inv_w = (float)(1.0 / w); T.fwd_begin = (int)fwd.size(); T.fwd_n = nb;
+        int j = 0;
+        for (int b = 0; b < nb; ++b) {
+            const double start = x[0] + b * w;
+            while (j + 2 < n && x[j + 1] <= start) ++j;
+            fwd.push_back((unsigned short)j);
+        }
+        // inverse guide on the CDF: idx[b] = last knot (<= n-2) with cdf <= b / G
+        T.inv_begin = (int)inv.size();
+        j = 0;
+        for (int b = 0; b <= INV_CDF_BUCKETS; ++b) {
+            const double level = (double)b / INV_CDF_BUCKETS;
+            while (j + 2 < n && cdf[j + 1] <= level) ++j;
+            inv.push_back((unsigned short)j);
+        }
     }
-    tb[desc->n_tables] = (int)tx.size();
     std::vector<int> abs_outer, abs_inner;
     for (int k = 0; k < s->n_ch; ++k) {
         abs_outer.push_back(s->layout.abs_base[s->node_outer[k]]);
         abs_inner.push_back(s->node_inner[k] >= 0 ? s->layout.abs_base[s->node_inner[k]] : 0);
     }
     if ((rc = upload(tx, &s->d_tab_x)) || (rc = upload(ty, &s->d_tab_y)) || (rc = upload(tc, &s->d_tab_cdf)) ||
-        (rc = upload(tb, &s->d_tab_begin)) || (rc = upload(abs_outer, &s->d_abs_outer)) || (rc = upload(abs_inner, &s->d_abs_inner)))
+        (rc = upload(fwd, &s->d_tab_fwd)) || (rc = upload(inv, &s->d_tab_inv)) ||
+        (rc = upload(abs_outer, &s->d_abs_outer)) || (rc = upload(abs_inner, &s->d_abs_inner)))
         return bail(rc);
     if ((e = cudaMalloc((void**)&s->d_counters, sizeof(unsigned long long) * COUNTER_RING)) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc counters"));
-    s->dev.tab_x = s->d_tab_x; s->dev.tab_y = s->d_tab_y; s->dev.tab_cdf = s->d_tab_cdf; s->dev.tab_begin = s->d_tab_begin;
+    s->dev.tab_x = s->d_tab_x; s->dev.tab_y = s->d_tab_y; s->dev.tab_cdf = s->d_tab_cdf;
+    s->dev.tab_fwd = s->d_tab_fwd; s->dev.tab_inv = s->d_tab_inv;
     s->dev.abs_base_outer = s->d_abs_outer; s->dev.abs_base_inner = s->d_abs_inner;
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(cuda_fail(e, "cudaGetDeviceProperties"));
     s->n_sm = prop.multiProcessorCount;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, trace_kernel, TRACE_THREADS, 0)) != cudaSuccess)
+    s->trace_smem = (size_t)(TRACE_THREADS / 32) * (size_t)(s->dev.n_bins + LSCPM_N_COUNTERS) * sizeof(unsigned int);
+    if (s->trace_smem > 200 * 1024) return bail(fail(LSCPM_EUNSUPPORTED, "too many tally bins for the per-warp shared rows"));
+    if (s->trace_smem > 48 * 1024 &&
+        (e = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->trace_smem)) != cudaSuccess)
+        return bail(cuda_fail(e, "cudaFuncSetAttribute"));
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, trace_kernel, TRACE_THREADS, s->trace_smem)) != cudaSuccess)
         return bail(cuda_fail(e, "occupancy query (is the library built for this GPU's architecture?)"));
     if (s->blocks_per_sm < 1) return bail(fail(LSCPM_ECUDA, "trace kernel does not fit on an SM"));
     *out = s;
@@ -657,7 +770,7 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
 
 int lscpm_scene_destroy(LscpmScene* s) {
     if (!s) return LSCPM_OK;
-    cudaFree(s->d_tab_x); cudaFree(s->d_tab_y); cudaFree(s->d_tab_cdf); cudaFree(s->d_tab_begin);
+    cudaFree(s->d_tab_x); cudaFree(s->d_tab_y); cudaFree(s->d_tab_cdf); cudaFree(s->d_tab_fwd); cudaFree(s->d_tab_inv);
     cudaFree(s->d_abs_outer); cudaFree(s->d_abs_inner); cudaFree(s->d_counters);
     delete s;
     return LSCPM_OK;
@@ -680,6 +793,7 @@ int lscpm_plan_create(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_ba
     if (!s || !batches || n_batches < 1) return fail(LSCPM_EINVAL, "scene/batches missing");
     CUDA_TRY(cudaSetDevice(s->device));
     std::vector<float> sx, sc;
+    std::vector<unsigned short> sg;
     std::vector<int> sb(1, 0);
     if (spectra && spectra->n_spectra > 0) {
         for (int i = 0; i < spectra->n_spectra; ++i) {
@@ -694,8 +808,15 @@ int lscpm_plan_create(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_ba
             if (!(total > 0)) return fail(LSCPM_EINVAL, "spectrum is identically zero");
             std::vector<double> cdf;
             trapezoid_cdf(spectra->x + lo, spectra->y + lo, n, cdf);
+            if (n > 65000) return fail(LSCPM_EUNSUPPORTED, "spectrum with more than 65000 knots");
             for (int k = 0; k < n; ++k) { sx.push_back((float)spectra->x[lo + k]); sc.push_back((float)cdf[k]); }
             sb.push_back((int)sx.size());
+            int j = 0;
+            for (int b = 0; b <= SPEC_BUCKETS; ++b) {
+                const double level = (double)b / SPEC_BUCKETS;
+                while (j + 2 < n && cdf[j + 1] <= level) ++j;
+                sg.push_back((unsigned short)j);
+            }
         }
     }
     std::vector<DevBatch> lowered(n_batches);
@@ -706,9 +827,10 @@ int lscpm_plan_create(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_ba
     LscpmPlan* p = new (std::nothrow) LscpmPlan();
     if (!p) return fail(LSCPM_ENOMEM, "out of host memory");
     p->scene = s; p->n_batches = n_batches;
-    p->h2d_bytes = lowered.size() * sizeof(DevBatch) + (sx.size() + sc.size()) * sizeof(float);
+    p->h2d_bytes = lowered.size() * sizeof(DevBatch) + (sx.size() + sc.size()) * sizeof(float) + sg.size() * sizeof(unsigned short);
     int rc;
-    if ((rc = upload(lowered, &p->d_batches)) || (rc = upload(sx, &p->d_spec_x)) || (rc = upload(sc, &p->d_spec_cdf))) {
+    if ((rc = upload(lowered, &p->d_batches)) || (rc = upload(sx, &p->d_spec_x)) || (rc = upload(sc, &p->d_spec_cdf)) ||
+        (rc = upload(sg, &p->d_spec_guide))) {
         lscpm_plan_destroy(p);
         return rc;
     }
@@ -720,7 +842,7 @@ uint64_t lscpm_plan_h2d_bytes(const LscpmPlan* p) { return p ? p->h2d_bytes : 0;
 
 int lscpm_plan_destroy(LscpmPlan* p) {
     if (!p) return LSCPM_OK;
-    cudaFree(p->d_batches); cudaFree(p->d_spec_x); cudaFree(p->d_spec_cdf);
+    cudaFree(p->d_batches); cudaFree(p->d_spec_x); cudaFree(p->d_spec_cdf); cudaFree(p->d_spec_guide);
     delete p;
     return LSCPM_OK;
 }
@@ -732,7 +854,7 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
     cudaStream_t stream = (cudaStream_t)stream_;
     CUDA_TRY(cudaSetDevice(s->device));
     TraceArgs a{};
-    a.batches = p->d_batches; a.spec_x = p->d_spec_x; a.spec_cdf = p->d_spec_cdf;
+    a.batches = p->d_batches; a.spec_x = p->d_spec_x; a.spec_cdf = p->d_spec_cdf; a.spec_guide = p->d_spec_guide;
     a.photon_begin = photon_begin; a.photon_count = photon_count;
     const int grid = s->n_sm * s->blocks_per_sm;
     const unsigned long long n_warps = (unsigned long long)grid * (TRACE_THREADS / 32);
@@ -748,7 +870,7 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
     int rc = pick_counter(s, stream, &a.work_counter);
     if (rc) return rc;
     const int blocks = (int)std::min<unsigned long long>((unsigned long long)grid, (a.n_chunks + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32));
-    trace_kernel<<<std::max(blocks, 1), TRACE_THREADS, 0, stream>>>(s->dev, a);
+    trace_kernel<<<std::max(blocks, 1), TRACE_THREADS, s->trace_smem, stream>>>(s->dev, a);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return LSCPM_OK;
@@ -825,7 +947,7 @@ int forward_hits_box(const double* h, const double* o, const double* d) {
 void classify_ray(const LscpmScene* s, const double* o, const double* d, ProbeIn& q) {
     int k = s->n_ch > 0 ? (int)std::lrint((o[0] - s->cx0) / s->pitch) : 0;
     k = std::min(std::max(k, 0), std::max(s->n_ch - 1, 0));
-    const double xr = o[0] - (s->cx0 + k * s->pitch), oz = o[2] - s->zc;
+    const double xr = s->n_ch > 0 ? o[0] - (s->cx0 + k * s->pitch) : o[0], oz = s->n_ch > 0 ? o[2] - s->zc : o[2];
     q.kc = k; q.xr = (float)xr; q.y = (float)o[1]; q.z = (float)o[2];
     q.dx = (float)d[0]; q.dy = (float)d[1]; q.dz = (float)d[2];
     const double h[3] = {s->hx, s->hy, s->hz};
@@ -928,7 +1050,7 @@ int lscpm_emit(LscpmScene* s, const LscpmBatchDesc* batch, const LscpmSpectraDes
     cudaError_t e = cudaMalloc((void**)&d_out, sizeof(float) * 7 * (size_t)n);
     std::vector<float> out((size_t)n * 7);
     if (e == cudaSuccess) {
-        emit_kernel<<<(unsigned)((n + 127) / 128), 128>>>(s->dev, plan->d_batches, plan->d_spec_x, plan->d_spec_cdf, photon_begin,
+        emit_kernel<<<(unsigned)((n + 127) / 128), 128>>>(s->dev, plan->d_batches, plan->d_spec_x, plan->d_spec_cdf, plan->d_spec_guide, photon_begin,
                                                            n, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), d_out);
         g_launches.fetch_add(1);
         e = cudaGetLastError();

@@ -6,10 +6,10 @@
 // equally spaced capillary Cylinders (outer tube + optional coaxial inner cylinder) whose end caps are
 // coplanar with the plate's +-y faces.  The generic algorithm (brute force over every node, container =
 // nearest node hit exactly once, adjacent = second intersection) is kept as the CPU oracle in oracle/;
-// this file reproduces its outcomes with a medium state machine instead:
+// this file reproduces its outcomes with a medium state machine:
 //
-//   AIR   -> only the plate can be hit (entry), or nothing (exit/miss)
-//   PLATE -> plate faces (container==hit -> adjacent = world) or the first capillary along the ray
+//   AIR   -> a fresh photon sitting on the plate face it is about to enter (entry Fresnel test)
+//   PLATE -> plate faces (container==hit -> adjacent = world) or the capillary of the current cell
 //   OUTER -> in the tube wall of capillary k: inner cylinder, outer cylinder, or the +-y caps
 //   INNER -> in the reaction mixture of capillary k: inner cylinder or the +-y caps
 //
@@ -18,6 +18,15 @@
 //   * leaving the inner cylinder when the straight continuation reaches a cap first takes n2 from the plate;
 //   * a segment that ends on a cap (coincident with the plate's +-y face; ties resolve in scene-graph order,
 //     plate first) is traced with the plate as container: plate material for absorption, n1 = plate, n2 = tube.
+//
+// Divergence control (what the ncu profile of the first version asked for):
+//   * ONE code path computes every candidate distance (three slabs, near/far roots of both cylinders about
+//     the current capillary axis) for all media and selects by medium — no per-medium branches;
+//   * in the plate the photon marches cell by cell (a cell = the x-interval owned by one capillary), so each
+//     iteration tests exactly one capillary; crossing a cell boundary is a virtual, uncounted step (free paths
+//     are memoryless, so re-sampling the Beer-Lambert depth per sub-segment leaves the statistics unchanged);
+//   * table lookups are O(1) through bucket indices instead of binary searches;
+//   * a fresh photon shares the iteration's Philox call and its entry Fresnel test runs in the common step.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -25,17 +34,20 @@
 namespace lscpm {
 
 constexpr int MAX_COMP = 4;
+constexpr int MAX_TABLES = 8;
 constexpr int MED_AIR = 0, MED_PLATE = 1, MED_OUTER = 2, MED_INNER = 3;
 constexpr int COMP_ABSORBER = 0, COMP_LUMINOPHORE = 1, COMP_REACTOR = 2;
 constexpr int LIGHT_DIRECT = 0, LIGHT_DIFFUSE = 1;
 constexpr int EV_GENERATE = 0, EV_REFLECT = 1, EV_TRANSMIT = 2, EV_ABSORB = 3, EV_EMIT = 4, EV_EXIT = 5, EV_KILL = 6,
-              EV_REACT = 7;
+              EV_REACT = 7, EV_NONE = -1;
 constexpr int BIN_KILL = 0, BIN_MISS = 1, BIN_ENTRY_REFLECT = 2;
-constexpr int SURF_NONE = 0, SURF_BOX = 1, SURF_OUTER = 2, SURF_INNER = 3, SURF_CAP = 4;
+constexpr int SURF_NONE = 0, SURF_BOX = 1, SURF_OUTER = 2, SURF_INNER = 3, SURF_CAP = 4, SURF_CELL = 5;
 constexpr int MAXSTEPS = 1000;            // pvtrace follow(maxsteps=1000)
 constexpr float ALPHA_ZERO = 1e-8f;       // numpy.isclose(alpha, 0) in Material.penetration_depth
 constexpr float KB_EV = 8.617333262145e-5f;
 constexpr float HC_EV_NM = 1240.8f;
+constexpr int INV_CDF_BUCKETS = 1024;     // guide-table resolution for inverse-CDF lookups of scene tables
+constexpr int SPEC_BUCKETS = 32;          // guide-table resolution for the per-batch solar spectra
 #define LSCPM_INF __int_as_float(0x7f800000)
 
 struct DevComponent {
@@ -49,7 +61,17 @@ struct DevComponent {
 struct DevMedium {
     float n;
     int n_comp;
+    int single_tab;      // index of the only tabulated component (its alpha = total - const_sum), or -1
+    float const_sum;     // sum of the constant coefficients
     DevComponent comp[MAX_COMP];
+};
+
+// knot table with O(1) forward lookup (value at abscissa) and guided inverse-CDF lookup
+struct DevTable {
+    int begin, n;        // knots [begin, begin+n) of tab_x / tab_y / tab_cdf
+    float x0, inv_w;     // bucket b covers x0 + [b, b+1) / inv_w; bucket width <= smallest knot spacing
+    int fwd_begin, fwd_n;// forward bucket index (uint16 knot numbers) in tab_fwd
+    int inv_begin;       // inverse guide table (INV_CDF_BUCKETS + 1 entries) in tab_inv, or -1
 };
 
 // Lowered scene, passed to every kernel by value (constant bank).
@@ -57,14 +79,18 @@ struct DevScene {
     float hx, hy, hz;          // plate half extents
     float cx0, pitch, zc;      // capillary k: axis along y through (cx0 + k*pitch, zc)
     float inv_pitch;
-    int n_ch;
+    float cell_lo_first, cell_hi_last;   // x-extent (relative to the axis) of the first / last cell: out to the plate faces
+    int n_ch;                  // number of cells (>= 1; a plate without capillaries is one cell with r_o2 < 0)
+    int has_caps;              // capillaries present
     float r_o, r_i, r_o2, r_i2;
     int has_inner;
     DevMedium med[4];          // indexed by MED_*; med[MED_AIR] carries the world's refractive index only
+    DevTable tab[MAX_TABLES];
     const float* tab_x;        // concatenated knot tables (scene spectra)
     const float* tab_y;
-    const float* tab_cdf;      // trapezoid CDF, normalised (used for emission tables)
-    const int* tab_begin;      // [n_tables + 1]
+    const float* tab_cdf;      // trapezoid CDF, normalised
+    const unsigned short* tab_fwd;
+    const unsigned short* tab_inv;
     int n_bins;
     int exit_base_plate;       // + box face
     int abs_base_plate;        // + component
@@ -77,6 +103,7 @@ struct DevBatch {
     int light_kind;
     int spec_begin;            // -1: constant wavelength
     int spec_n;
+    int spec_guide;            // offset of this spectrum's guide table (SPEC_BUCKETS + 1 entries)
     uint32_t batch_id;
     int anchor_on_top;         // anchors lie on the plate's top face: a ray heading down enters at its anchor
     float wavelength;
@@ -88,25 +115,23 @@ struct DevBatch {
 };
 
 struct Photon {
-    float xr, y, z;            // x is stored relative to the axis of capillary kc
+    float xr, y, z;            // x relative to the axis of capillary (cell) kc, z relative to the axis height zc
     float dx, dy, dz;
     float wl;
     float a_plate, a_outer, a_inner;   // total attenuation of the three media at wl
     int kc;
     int medium;
     int steps;                 // follow-loop iterations so far
-    int n_surface;             // surface events so far
-    int emitted;
+    int aux;                   // AIR: entry face | inside medium << 4.   bit 8: has emitted
 };
 
 struct Hit {
     float t;
     int kind;                  // SURF_*
-    int face;                  // box face for SURF_BOX / SURF_CAP
-    int ch;                    // capillary entered (SURF_OUTER from the plate)
+    int face;                  // box face for SURF_BOX / SURF_CAP; direction (+1/-1) for SURF_CELL
+    int ch;                    // sibling capillary (probe only)
     int container;             // medium whose material governs the segment
     int adj;                   // medium on the far side of the interface (pvtrace's `adjacent`)
-    float n1, n2;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -143,185 +168,182 @@ struct Rng {
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
 __device__ __forceinline__ float one_minus_u01(uint32_t x) { return (float)(((~x) >> 8) + 1u) * 5.9604644775390625e-8f; }
 
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+
 // ------------------------------------------------------------------------------------------------
-// numpy.interp semantics on a knot table: clamped; segment = last j with xp[j] <= v
+// table lookups with numpy.interp semantics (clamped; segment = last j with xp[j] <= v)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float interp(float v, const float* __restrict__ xp, const float* __restrict__ fp, int n) {
+__device__ __forceinline__ float lerp_knots(float v, const float* __restrict__ xp, const float* __restrict__ fp, int j) {
+    const float x0 = __ldg(xp + j), x1 = __ldg(xp + j + 1), f0 = __ldg(fp + j), f1 = __ldg(fp + j + 1);
+    const float den = x1 - x0;
+    return den > 0.f ? fmaf(fdiv(f1 - f0, den), v - x0, f0) : f0;
+}
+
+// value of column `col` (tab_y or tab_cdf) at abscissa v
+__device__ __forceinline__ float table_at(const DevScene& S, int t, float v, const float* __restrict__ col) {
+    const DevTable& T = S.tab[t];
+    const float* xp = S.tab_x + T.begin;
+    const float* fp = col + T.begin;
     if (v <= __ldg(xp)) return __ldg(fp);
-    if (v >= __ldg(xp + n - 1)) return __ldg(fp + n - 1);
-    int lo = 0, hi = n - 1;
+    if (v >= __ldg(xp + T.n - 1)) return __ldg(fp + T.n - 1);
+    int b = (int)((v - T.x0) * T.inv_w);
+    b = min(max(b, 0), T.fwd_n - 1);
+    int j = __ldg(S.tab_fwd + T.fwd_begin + b);
+    // the bucket is no wider than the smallest knot spacing: at most one knot boundary either side
+    if (j + 2 < T.n && v >= __ldg(xp + j + 1)) ++j;
+    if (j + 2 < T.n && v >= __ldg(xp + j + 1)) ++j;
+    if (j > 0 && v < __ldg(xp + j)) --j;
+    return lerp_knots(v, xp, fp, j);
+}
+
+// inverse CDF through a guide table: bracket [idx[b], idx[b+1]+1] then a (usually empty) bisection
+__device__ __forceinline__ float inverse_cdf(float u, const float* __restrict__ cdf, const float* __restrict__ xs, int n,
+                                             const unsigned short* __restrict__ guide, int buckets) {
+    if (u <= __ldg(cdf)) return __ldg(xs);
+    if (u >= __ldg(cdf + n - 1)) return __ldg(xs + n - 1);
+    const int b = min((int)(u * (float)buckets), buckets - 1);
+    int lo = __ldg(guide + b), hi = min((int)__ldg(guide + b + 1) + 1, n - 1);
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
-        if (__ldg(xp + mid) <= v) lo = mid; else hi = mid;
+        if (__ldg(cdf + mid) <= u) lo = mid; else hi = mid;
     }
-    const float x0 = __ldg(xp + lo), x1 = __ldg(xp + lo + 1), f0 = __ldg(fp + lo), f1 = __ldg(fp + lo + 1);
-    return fmaf((f1 - f0) / (x1 - x0), v - x0, f0);
+    return lerp_knots(u, cdf, xs, lo);
 }
 
 __device__ __forceinline__ float component_alpha(const DevScene& S, const DevComponent& c, float wl) {
-    if (c.abs_table < 0) return c.coef;
-    const int lo = __ldg(S.tab_begin + c.abs_table), n = __ldg(S.tab_begin + c.abs_table + 1) - lo;
-    return interp(wl, S.tab_x + lo, S.tab_y + lo, n);
+    return c.abs_table < 0 ? c.coef : table_at(S, c.abs_table, wl, S.tab_y);
 }
 
 __device__ __forceinline__ float medium_alpha(const DevScene& S, int medium, float wl) {
-    float a = 0.f;
     const DevMedium& m = S.med[medium];
+    float a = m.const_sum;
 #pragma unroll
     for (int c = 0; c < MAX_COMP; ++c)
-        if (c < m.n_comp) a += component_alpha(S, m.comp[c], wl);
+        if (c < m.n_comp && m.comp[c].abs_table >= 0) a += table_at(S, m.comp[c].abs_table, wl, S.tab_y);
     return a;
 }
 
 __device__ __forceinline__ void refresh_alphas(const DevScene& S, Photon& p) {
     p.a_plate = medium_alpha(S, MED_PLATE, p.wl);
-    p.a_outer = medium_alpha(S, MED_OUTER, p.wl);
+    p.a_outer = S.has_caps ? medium_alpha(S, MED_OUTER, p.wl) : 0.f;
     p.a_inner = S.has_inner ? medium_alpha(S, MED_INNER, p.wl) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
 // geometry
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float plane_t(float target_pos, float target_neg, float o, float d) {
-    // distance along d to the slab face the ray is heading to
-    return d > 0.f ? (target_pos - o) / d : (d < 0.f ? (target_neg - o) / d : LSCPM_INF);
+__device__ __forceinline__ float axis_x(const DevScene& S, int k) { return fmaf((float)k, S.pitch, S.cx0); }
+__device__ __forceinline__ float abs_x(const DevScene& S, const Photon& p) { return axis_x(S, p.kc) + p.xr; }
+
+// near and far roots of a cylinder of squared radius r2 about the current axis; a,b,cross,rr shared.
+// near = INF unless the ray is approaching and actually crosses; far is the exit distance for a ray inside.
+__device__ __forceinline__ void cylinder_roots(float a, float inv_a, float b, float cross2, float rr, float r2,
+                                               float& t_near, float& t_far) {
+    const float disc = fmaf(a, r2, -cross2);            // = b^2 - a*c without the cancellation
+    const float s = sqrtf(fmaxf(disc, 0.f));
+    const float c = rr - r2;
+    const float q = s + fabsf(b);
+    const float r1 = fdiv(c, q), r2_ = q * inv_a;
+    // b < 0 (approaching the axis): near = c/q, far = q/a;   b >= 0: near = -q/a (behind), far = -c/q
+    const float near_ = b < 0.f ? r1 : -r2_;
+    const float far_ = b < 0.f ? r2_ : -r1;
+    t_near = (disc > 0.f && b < 0.f && near_ > 0.f) ? near_ : LSCPM_INF;
+    t_far = fmaxf(far_, 0.f);
 }
 
-__device__ __forceinline__ float abs_x(const DevScene& S, const Photon& p) { return fmaf((float)p.kc, S.pitch, S.cx0) + p.xr; }
-
-// exit of the plate box from inside
-__device__ __forceinline__ void box_exit(const DevScene& S, const Photon& p, float& t, int& face) {
-    const float tx = plane_t(S.hx, -S.hx, abs_x(S, p), p.dx);
-    const float ty = plane_t(S.hy, -S.hy, p.y, p.dy);
-    const float tz = plane_t(S.hz, -S.hz, p.z, p.dz);
-    t = tx; face = p.dx > 0.f ? 1 : 0;
-    if (ty < t) { t = ty; face = p.dy > 0.f ? 3 : 2; }
-    if (tz < t) { t = tz; face = p.dz > 0.f ? 5 : 4; }
-    t = fmaxf(t, 0.f);
-}
-
-// First capillary (outer cylinder) entered by a ray that is outside all capillaries, within tmax.
-// Capillaries are parallel to y and ordered in x with disjoint x-extents, so the first hit in x order is the nearest.
-__device__ __forceinline__ bool capillary_search(const DevScene& S, const Photon& p, float tmax, float& t_hit, int& j_hit) {
-    const float a = p.dx * p.dx + p.dz * p.dz;
-    if (!(a > 1e-30f)) return false;
-    const float oz = p.z - S.zc;
-    const float xe = fmaf(p.dx, tmax, p.xr);   // end of the segment, relative to capillary kc
-    int j0, j1, step;
-    if (p.dx >= 0.f) {
-        j0 = p.kc + (int)ceilf((p.xr - S.r_o) * S.inv_pitch);
-        j1 = p.kc + (int)floorf((xe + S.r_o) * S.inv_pitch);
-        j0 = max(j0, 0); j1 = min(j1, S.n_ch - 1); step = 1;
-    } else {
-        j0 = p.kc + (int)floorf((p.xr + S.r_o) * S.inv_pitch);
-        j1 = p.kc + (int)ceilf((xe - S.r_o) * S.inv_pitch);
-        j0 = min(j0, S.n_ch - 1); j1 = max(j1, 0); step = -1;
-    }
-    const float ar2 = a * S.r_o2;
-    for (int j = j0; step > 0 ? j <= j1 : j >= j1; j += step) {
-        const float ox = p.xr - (float)(j - p.kc) * S.pitch;
-        const float b = ox * p.dx + oz * p.dz;
-        if (b >= 0.f) continue;                       // moving away from this axis
-        const float cross = ox * p.dz - oz * p.dx;
-        const float disc = ar2 - cross * cross;      // = b^2 - a*c without the cancellation
-        if (disc <= 0.f) continue;
-        const float c = ox * ox + oz * oz - S.r_o2;
-        const float t = c / (sqrtf(disc) - b);
-        if (t >= tmax) return false;                  // later capillaries are farther still
-        if (t > 0.f) { t_hit = t; j_hit = j; return true; }
-    }
-    return false;
-}
-
-// far root of a cylinder of squared radius r2 about the axis of capillary kc, for a ray starting inside it
-__device__ __forceinline__ float cylinder_exit(float ox, float oz, float dx, float dz, float r2) {
-    const float a = dx * dx + dz * dz;
-    if (!(a > 1e-30f)) return LSCPM_INF;
-    const float b = ox * dx + oz * dz;
-    const float cross = ox * dz - oz * dx;
-    const float s = sqrtf(fmaxf(fmaf(a, r2, -cross * cross), 0.f));
-    const float c = ox * ox + oz * oz - r2;           // <= 0 inside
-    const float t = b > 0.f ? -c / (b + s) : (s - b) / a;
-    return fmaxf(t, 0.f);
-}
-
-// near root for a ray starting outside (or on) the cylinder; INF when it does not enter
-__device__ __forceinline__ float cylinder_enter(float ox, float oz, float dx, float dz, float r2) {
-    const float a = dx * dx + dz * dz;
-    const float b = ox * dx + oz * dz;
-    if (!(b < 0.f)) return LSCPM_INF;
-    const float cross = ox * dz - oz * dx;
-    const float disc = fmaf(a, r2, -cross * cross);
-    if (!(disc > 0.f)) return LSCPM_INF;
-    const float c = ox * ox + oz * oz - r2;
-    const float t = c / (sqrtf(disc) - b);
-    return t > 0.f ? t : LSCPM_INF;
-}
-
-// ------------------------------------------------------------------------------------------------
-// next interface for a photon in PLATE / OUTER / INNER (pvtrace next_hit, literal outcomes)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ Hit find_hit(const DevScene& S, const Photon& p) {
+// Next interface for a photon in PLATE / OUTER / INNER (pvtrace next_hit, literal outcomes); also returns the
+// virtual cell crossing (SURF_CELL) for plate flights.  One code path for all media.
+__device__ __forceinline__ Hit compute_hit(const DevScene& S, const Photon& p) {
     Hit h;
     h.ch = p.kc;
-    h.face = 0;
+    // slabs
+    const float ty = p.dy > 0.f ? fdiv(S.hy - p.y, p.dy) : (p.dy < 0.f ? fdiv(-S.hy - p.y, p.dy) : LSCPM_INF);
+    const float tz = p.dz > 0.f ? fdiv(S.hz - S.zc - p.z, p.dz) : (p.dz < 0.f ? fdiv(-S.hz - S.zc - p.z, p.dz) : LSCPM_INF);
+    const bool first = p.kc == 0, last = p.kc == S.n_ch - 1;
+    const float half = 0.5f * S.pitch;
+    const float x_hi = last ? S.cell_hi_last : half, x_lo = first ? S.cell_lo_first : -half;
+    const float tx = p.dx > 0.f ? fdiv(x_hi - p.xr, p.dx) : (p.dx < 0.f ? fdiv(x_lo - p.xr, p.dx) : LSCPM_INF);
+    // cylinders about the current axis
+    const float a = fmaf(p.dx, p.dx, p.dz * p.dz);
+    const bool has_a = a > 1e-30f;
+    const float inv_a = has_a ? fdiv(1.f, a) : 0.f;
+    const float b = fmaf(p.xr, p.dx, p.z * p.dz);
+    const float cross = fmaf(p.xr, p.dz, -p.z * p.dx);
+    const float cross2 = cross * cross;
+    const float rr = fmaf(p.xr, p.xr, p.z * p.z);
+    float o_near, o_far, i_near, i_far;
+    cylinder_roots(a, inv_a, b, cross2, rr, S.r_o2, o_near, o_far);
+    cylinder_roots(a, inv_a, b, cross2, rr, S.r_i2, i_near, i_far);
+    if (!has_a) { o_near = i_near = LSCPM_INF; o_far = i_far = LSCPM_INF; }
+    if (!S.has_inner) i_near = LSCPM_INF;
+
+    const int yface = p.dy > 0.f ? 3 : 2;
     if (p.medium == MED_PLATE) {
-        float t_box; int face;
-        box_exit(S, p, t_box, face);
-        float t_c; int j;
         h.container = MED_PLATE;
-        h.n1 = S.med[MED_PLATE].n;
-        if (capillary_search(S, p, t_box, t_c, j)) {
-            h.t = t_c; h.kind = SURF_OUTER; h.ch = j; h.adj = MED_OUTER;
-        } else {
-            h.t = t_box; h.kind = SURF_BOX; h.face = face; h.adj = MED_AIR;
+        // box faces / cell boundary
+        float t = tz; int kind = SURF_BOX, face = p.dz > 0.f ? 5 : 4;
+        if (ty < t) { t = ty; face = yface; }
+        if (tx < t) {
+            t = tx;
+            const bool plate_face = p.dx > 0.f ? last : first;
+            kind = plate_face ? SURF_BOX : SURF_CELL;
+            face = plate_face ? (p.dx > 0.f ? 1 : 0) : (p.dx > 0.f ? 1 : -1);
         }
-        h.n2 = S.med[h.adj].n;
+        h.adj = MED_AIR;
+        if (o_near < t) { t = o_near; kind = SURF_OUTER; face = 0; h.adj = MED_OUTER; }
+        h.t = fmaxf(t, 0.f); h.kind = kind; h.face = face;
         return h;
     }
-    const float oz = p.z - S.zc;
-    const float t_cap = plane_t(S.hy, -S.hy, p.y, p.dy);
-    const int cap_face = p.dy > 0.f ? 3 : 2;
     if (p.medium == MED_OUTER) {
-        const float t_out = cylinder_exit(p.xr, oz, p.dx, p.dz, S.r_o2);
-        const float t_in = S.has_inner ? cylinder_enter(p.xr, oz, p.dx, p.dz, S.r_i2) : LSCPM_INF;
-        if (t_in < t_out && t_in < t_cap) {
-            h.t = t_in; h.kind = SURF_INNER; h.container = MED_OUTER; h.adj = MED_INNER;
-            h.n1 = S.med[MED_OUTER].n; h.n2 = S.med[MED_INNER].n;
-        } else if (t_cap <= t_out) {
+        if (i_near < o_far && i_near < ty) {
+            h.t = i_near; h.kind = SURF_INNER; h.face = 0; h.container = MED_OUTER; h.adj = MED_INNER;
+        } else if (ty <= o_far) {
             // cap coincides with the plate face; the plate sorts first and becomes container and hit node
-            h.t = fmaxf(t_cap, 0.f); h.kind = SURF_CAP; h.face = cap_face; h.container = MED_PLATE; h.adj = MED_OUTER;
-            h.n1 = S.med[MED_PLATE].n; h.n2 = S.med[MED_OUTER].n;
+            h.t = fmaxf(ty, 0.f); h.kind = SURF_CAP; h.face = yface; h.container = MED_PLATE; h.adj = MED_OUTER;
         } else {
-            h.t = t_out; h.kind = SURF_OUTER; h.container = MED_OUTER;
-            h.n1 = S.med[MED_OUTER].n;
-            // adjacent = whatever the straight continuation meets next: a sibling capillary, else the plate
-            Photon q = p;
-            q.xr = fmaf(p.dx, t_out, p.xr); q.y = fmaf(p.dy, t_out, p.y); q.z = fmaf(p.dz, t_out, p.z);
-            float t_box; int face; box_exit(S, q, t_box, face);
-            float t_s; int j;
-            // the capillary being left cannot be re-entered: on its surface heading outward, b >= 0
-            const bool sibling = capillary_search(S, q, t_box, t_s, j) && j != p.kc;
-            h.adj = sibling ? MED_OUTER : MED_PLATE;
-            if (sibling) h.ch = j;    // which sibling (only read by the probe; a leaving photon keeps kc)
-            h.n2 = S.med[h.adj].n;
+            h.t = o_far; h.kind = SURF_OUTER; h.face = 0; h.container = MED_OUTER;
+            h.adj = MED_PLATE;     // provisional: sibling_ahead() upgrades it to MED_OUTER
         }
         return h;
     }
     // MED_INNER
-    const float t_side = cylinder_exit(p.xr, oz, p.dx, p.dz, S.r_i2);
-    if (t_cap <= t_side) {
-        h.t = fmaxf(t_cap, 0.f); h.kind = SURF_CAP; h.face = cap_face; h.container = MED_PLATE; h.adj = MED_OUTER;
-        h.n1 = S.med[MED_PLATE].n; h.n2 = S.med[MED_OUTER].n;
+    if (ty <= i_far) {
+        h.t = fmaxf(ty, 0.f); h.kind = SURF_CAP; h.face = yface; h.container = MED_PLATE; h.adj = MED_OUTER;
     } else {
-        h.t = t_side; h.kind = SURF_INNER; h.container = MED_INNER;
-        h.n1 = S.med[MED_INNER].n;
+        h.t = i_far; h.kind = SURF_INNER; h.face = 0; h.container = MED_INNER;
         // adjacent = second intersection: the tube wall's outer surface, unless the cap (plate first) comes earlier
-        const float t_wall = cylinder_exit(p.xr, oz, p.dx, p.dz, S.r_o2);
-        h.adj = (t_cap <= t_wall) ? MED_PLATE : MED_OUTER;
-        h.n2 = S.med[h.adj].n;
+        h.adj = (ty <= o_far) ? MED_PLATE : MED_OUTER;
     }
     return h;
+}
+
+// pvtrace's adjacent for a photon leaving tube wall kc through its side at (xr, y, z): does the straight
+// continuation enter a sibling capillary before it leaves the plate?  Rare (tube-wall exits), so a plain loop.
+__device__ __noinline__ int sibling_ahead(const DevScene& S, int kc, float xr, float y, float z, float dx, float dy, float dz) {
+    const float a = fmaf(dx, dx, dz * dz);
+    if (!(a > 1e-30f) || dx == 0.f) return -1;
+    const float ty = dy > 0.f ? fdiv(S.hy - y, dy) : (dy < 0.f ? fdiv(-S.hy - y, dy) : LSCPM_INF);
+    const float tz = dz > 0.f ? fdiv(S.hz - S.zc - z, dz) : (dz < 0.f ? fdiv(-S.hz - S.zc - z, dz) : LSCPM_INF);
+    const float x_abs = axis_x(S, kc) + xr;
+    const float tx = dx > 0.f ? fdiv(S.hx - x_abs, dx) : fdiv(-S.hx - x_abs, dx);
+    const float t_box = fminf(fminf(ty, tz), tx);
+    const int step = dx > 0.f ? 1 : -1;
+    const float ar2 = a * S.r_o2;
+    for (int j = kc + step; j >= 0 && j < S.n_ch; j += step) {
+        const float ox = xr - (float)(j - kc) * S.pitch;
+        // capillary j starts at |ox| - r_o along x: beyond the plate exit -> no sibling
+        if ((fabsf(ox) - S.r_o) > fabsf(dx) * t_box) return -1;
+        const float b = fmaf(ox, dx, z * dz);
+        if (b >= 0.f) continue;
+        const float cross = fmaf(ox, dz, -z * dx);
+        const float disc = fmaf(-cross, cross, ar2);
+        if (disc <= 0.f) continue;
+        const float c = fmaf(ox, ox, z * z) - S.r_o2;
+        const float t = fdiv(c, sqrtf(disc) - b);
+        if (t >= t_box) return -1;
+        if (t > 0.f) return j;
+    }
+    return -1;
 }
 
 // entry of the plate box for a ray starting outside it (slab test); false when it misses
@@ -355,6 +377,7 @@ struct Interface {
     float nx, ny, nz;   // unit normal facing along the ray
     float cosi;         // d . n  (> 0)
     float k;            // cos of the refracted angle
+    float eta;          // n1 / n2
     float R;
 };
 
@@ -365,13 +388,14 @@ __device__ __forceinline__ Interface interface_eval(float dx, float dy, float dz
     if (c < 0.f) { nx = -nx; ny = -ny; nz = -nz; c = -c; }
     c = fminf(c, 1.f);
     I.nx = nx; I.ny = ny; I.nz = nz; I.cosi = c;
-    const float eta = n1 / n2;
-    const float s2 = fmaxf(1.f - c * c, 0.f);
-    const float k2 = 1.f - eta * eta * s2;
+    const float eta = fdiv(n1, n2);
+    I.eta = eta;
+    const float s2 = fmaxf(fmaf(-c, c, 1.f), 0.f);
+    const float k2 = fmaf(-eta * eta, s2, 1.f);
     if (n2 < n1 && k2 < 0.f) { I.R = 1.f; I.k = 0.f; return I; }   // beyond the critical angle
     const float k = sqrtf(fmaxf(k2, 0.f));
-    const float rs = (n1 * c - n2 * k) / (n1 * c + n2 * k);
-    const float rp = (n1 * k - n2 * c) / (n1 * k + n2 * c);
+    const float rs = fdiv(n1 * c - n2 * k, n1 * c + n2 * k);
+    const float rp = fdiv(n1 * k - n2 * c, n1 * k + n2 * c);
     I.k = k;
     I.R = 0.5f * (rs * rs + rp * rp);
     return I;
@@ -388,41 +412,73 @@ __device__ __forceinline__ void reflect_dir(Photon& p, const Interface& I) {
     normalise(p.dx, p.dy, p.dz);
 }
 
-__device__ __forceinline__ void refract_dir(Photon& p, const Interface& I, float n1, float n2) {
-    const float eta = n1 / n2;
-    const float g = I.k - eta * I.cosi;
-    p.dx = fmaf(eta, p.dx, g * I.nx); p.dy = fmaf(eta, p.dy, g * I.ny); p.dz = fmaf(eta, p.dz, g * I.nz);
+__device__ __forceinline__ void refract_dir(Photon& p, const Interface& I) {
+    const float g = I.k - I.eta * I.cosi;
+    p.dx = fmaf(I.eta, p.dx, g * I.nx); p.dy = fmaf(I.eta, p.dy, g * I.ny); p.dz = fmaf(I.eta, p.dz, g * I.nz);
     normalise(p.dx, p.dy, p.dz);
 }
 
 __device__ __forceinline__ void box_normal(int face, float& nx, float& ny, float& nz) {
-    nx = ny = nz = 0.f;
     const float s = (face & 1) ? 1.f : -1.f;
-    if (face < 2) nx = s; else if (face < 4) ny = s; else nz = s;
+    nx = face < 2 ? s : 0.f;
+    ny = (face >= 2 && face < 4) ? s : 0.f;
+    nz = face >= 4 ? s : 0.f;
+}
+
+// which capillary (if any) contains the plate-local point; sets kc/xr/z/medium
+__device__ __forceinline__ void locate_in_plate(const DevScene& S, Photon& p, float x_abs, float z_abs) {
+    int k = (int)rintf((x_abs - S.cx0) * S.inv_pitch);
+    k = min(max(k, 0), S.n_ch - 1);
+    p.kc = k;
+    p.xr = x_abs - axis_x(S, k);
+    p.z = z_abs - S.zc;
+    p.medium = MED_PLATE;
+    const float rr = fmaf(p.xr, p.xr, p.z * p.z);
+    if (rr < S.r_o2) p.medium = (S.has_inner && rr < S.r_i2) ? MED_INNER : MED_OUTER;
+}
+
+// put a ray that starts at plate-local (ox,oy,oz) on the plate: inside -> its medium, outside -> AIR on the entry
+// face (or BIN_MISS).  `anchored`: the entry point is already known to be (ax, ay) on the top face.
+__device__ __forceinline__ int place_photon(const DevScene& S, Photon& p, float ox, float oy, float oz, bool anchored,
+                                            float ax, float ay) {
+    p.steps = 0;
+    int face; float px, py, pz;
+    if (anchored) { face = 5; px = ax; py = ay; pz = S.hz; }
+    else {
+        if (fabsf(ox) < S.hx && fabsf(oy) < S.hy && fabsf(oz) < S.hz) {   // born inside the plate: no entry event
+            p.y = oy; locate_in_plate(S, p, ox, oz); p.aux = 0;
+            return -1;
+        }
+        float t;
+        if (!box_enter(S, ox, oy, oz, p.dx, p.dy, p.dz, t, face)) { p.steps = 1; return BIN_MISS; }
+        px = fmaf(p.dx, t, ox); py = fmaf(p.dy, t, oy); pz = fmaf(p.dz, t, oz);
+        if (face < 2) px = (face & 1) ? S.hx : -S.hx; else if (face < 4) py = (face & 1) ? S.hy : -S.hy; else pz = (face & 1) ? S.hz : -S.hz;
+    }
+    p.y = py;
+    locate_in_plate(S, p, px, pz);
+    p.aux = face | (p.medium << 4);
+    p.medium = MED_AIR;
+    return -1;
 }
 
 // ------------------------------------------------------------------------------------------------
-// photon generation (reference miniplant/utils.py:87-142, scene_creator.py:288-304)
+// photon generation (reference miniplant/utils.py:87-142, scene_creator.py:288-304).
+// Consumes the iteration's Philox draw `w` (x, y: mask point; z: wavelength) and leaves w.w for the entry
+// Fresnel test.  Returns -1 with the photon placed, or BIN_MISS when the ray never touches the plate.
 // ------------------------------------------------------------------------------------------------
-struct RayStart {
-    float ox, oy, oz;   // plate-local origin of the ray (anchor - back_off * d)
-    float ax, ay, az;   // anchor
-    float dx, dy, dz;
-    float wl;
-};
-
-__device__ __forceinline__ RayStart generate_ray(const DevScene& S, const DevBatch& B, const float* __restrict__ spec_x,
-                                                 const float* __restrict__ spec_cdf, Rng& rng) {
-    RayStart r;
-    uint4 w = rng.next();
+__device__ __forceinline__ int generate_photon(const DevScene& S, const DevBatch& B, const float* __restrict__ spec_x,
+                                               const float* __restrict__ spec_cdf, const unsigned short* __restrict__ spec_guide,
+                                               Rng& rng, const uint4 w, Photon& p, float* origin /* optional [3] */) {
     const float mx = (2.f * u01(w.x) - 1.f) * B.mask_half[0];
     const float my = (2.f * u01(w.y) - 1.f) * B.mask_half[1];
-    r.ax = fmaf(B.A[0], mx, fmaf(B.A[1], my, B.A[3]));
-    r.ay = fmaf(B.A[4], mx, fmaf(B.A[5], my, B.A[7]));
-    r.az = fmaf(B.A[8], mx, fmaf(B.A[9], my, B.A[11]));
-    r.wl = B.spec_begin < 0 ? B.wavelength : interp(u01(w.z), spec_cdf + B.spec_begin, spec_x + B.spec_begin, B.spec_n);
+    const float ax = fmaf(B.A[0], mx, fmaf(B.A[1], my, B.A[3]));
+    const float ay = fmaf(B.A[4], mx, fmaf(B.A[5], my, B.A[7]));
+    const float az = fmaf(B.A[8], mx, fmaf(B.A[9], my, B.A[11]));
+    p.wl = B.spec_begin < 0 ? B.wavelength
+                            : inverse_cdf(u01(w.z), spec_cdf + B.spec_begin, spec_x + B.spec_begin, B.spec_n,
+                                          spec_guide + B.spec_guide, SPEC_BUCKETS);
     if (B.light_kind == LIGHT_DIRECT) {
-        r.dx = B.dir[0]; r.dy = B.dir[1]; r.dz = B.dir[2];
+        p.dx = B.dir[0]; p.dy = B.dir[1]; p.dz = B.dir[2];
     } else {
         float sz, cz, sa, ca;
         for (;;) {   // front-face rejection, uniform in (zenith, azimuth) angle
@@ -432,88 +488,76 @@ __device__ __forceinline__ RayStart generate_ray(const DevScene& S, const DevBat
             if (B.cos_tilt * cz + B.sin_tilt * sz * ca >= 0.f) break;
         }
         const float wx = -sz * ca, wy = -sz * sa, wz = -cz;   // world direction = -sky
-        r.dx = S.w2l[0] * wx + S.w2l[1] * wy + S.w2l[2] * wz;
-        r.dy = S.w2l[3] * wx + S.w2l[4] * wy + S.w2l[5] * wz;
-        r.dz = S.w2l[6] * wx + S.w2l[7] * wy + S.w2l[8] * wz;
+        p.dx = S.w2l[0] * wx + S.w2l[1] * wy + S.w2l[2] * wz;
+        p.dy = S.w2l[3] * wx + S.w2l[4] * wy + S.w2l[5] * wz;
+        p.dz = S.w2l[6] * wx + S.w2l[7] * wy + S.w2l[8] * wz;
     }
-    r.ox = fmaf(-B.back_off, r.dx, r.ax);
-    r.oy = fmaf(-B.back_off, r.dy, r.ay);
-    r.oz = fmaf(-B.back_off, r.dz, r.az);
-    return r;
-}
-
-// which capillary (if any) contains the plate-local point; sets kc/xr/medium
-__device__ __forceinline__ void locate_in_plate(const DevScene& S, Photon& p, float x_abs) {
-    int k = (int)rintf((x_abs - S.cx0) * S.inv_pitch);
-    k = min(max(k, 0), max(S.n_ch - 1, 0));
-    p.kc = k;
-    p.xr = x_abs - fmaf((float)k, S.pitch, S.cx0);
-    p.medium = MED_PLATE;
-    if (S.n_ch > 0) {
-        const float oz = p.z - S.zc, rr = p.xr * p.xr + oz * oz;
-        if (rr < S.r_o2) p.medium = (S.has_inner && rr < S.r_i2) ? MED_INNER : MED_OUTER;
-    }
-}
-
-// keep xr relative to the nearest capillary axis while travelling through the plate
-__device__ __forceinline__ void rebase_x(const DevScene& S, Photon& p) {
-    const int shift = (int)rintf(p.xr * S.inv_pitch);
-    int k = min(max(p.kc + shift, 0), max(S.n_ch - 1, 0));
-    p.xr -= (float)(k - p.kc) * S.pitch;
-    p.kc = k;
+    refresh_alphas(S, p);
+    const float ox = fmaf(-B.back_off, p.dx, ax), oy = fmaf(-B.back_off, p.dy, ay), oz = fmaf(-B.back_off, p.dz, az);
+    if (origin) { origin[0] = ox; origin[1] = oy; origin[2] = oz; }
+    return place_photon(S, p, ox, oy, oz, B.anchor_on_top && p.dz < 0.f, ax, ay);
 }
 
 // ------------------------------------------------------------------------------------------------
-// one iteration of follow() for a photon inside the plate assembly.
-// Returns -1 while the photon lives, otherwise its tally bin.  `ev`/`ev_node_medium` report what happened.
+// one iteration of follow().  `w_depth`, `u_surf`, `u_qy` are the iteration's random numbers.
+// Returns -1 while the photon lives, otherwise its tally bin.
 // ------------------------------------------------------------------------------------------------
 struct StepOut {
-    int event;       // EV_*
+    int event;       // EV_* (EV_NONE for a virtual cell crossing)
     int medium;      // container medium of the event (for node lookup by recorders)
     int ch;          // capillary index of the event
     int kind;        // surface kind for surface events
     int face;
 };
 
-__device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, Rng& rng, StepOut& out) {
-    if (++p.steps > MAXSTEPS) { out.event = EV_KILL; return BIN_KILL; }
-    const Hit h = find_hit(S, p);
-    const uint4 w = rng.next();
-    const float alpha = h.container == MED_PLATE ? p.a_plate : (h.container == MED_OUTER ? p.a_outer : p.a_inner);
-    const float depth = alpha <= ALPHA_ZERO ? LSCPM_INF : -logf(one_minus_u01(w.x)) / alpha;
+__device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, Rng& rng, uint32_t w_depth, float u_surf,
+                                           float u_qy, StepOut& out) {
+    Hit h;
+    if (p.medium == MED_AIR) {
+        h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.ch = p.kc;
+    } else {
+        h = compute_hit(S, p);
+    }
+    // a virtual crossing is not a follow() iteration
+    if (h.kind != SURF_CELL && ++p.steps > MAXSTEPS) { out.event = EV_KILL; return BIN_KILL; }
+    const float alpha = h.container == MED_PLATE ? p.a_plate
+                      : (h.container == MED_OUTER ? p.a_outer : (h.container == MED_INNER ? p.a_inner : 0.f));
+    const float depth = alpha <= ALPHA_ZERO ? LSCPM_INF : fdiv(-__logf(one_minus_u01(w_depth)), alpha);
     out.medium = h.container; out.ch = p.kc; out.kind = h.kind; out.face = h.face;
 
     if (depth < h.t) {
         // absorbed inside the container: move, choose the component ~ alpha_i, radiative test
         p.xr = fmaf(p.dx, depth, p.xr); p.y = fmaf(p.dy, depth, p.y); p.z = fmaf(p.dz, depth, p.z);
-        if (p.medium == MED_PLATE) rebase_x(S, p);
         const DevMedium& m = S.med[h.container];
-        const float pick = u01(w.y) * alpha;
+        const float pick = u_surf * alpha;
         float acc = 0.f;
         int index = m.n_comp - 1;
         bool found = false;
 #pragma unroll
         for (int c = 0; c < MAX_COMP; ++c) {
             if (c < m.n_comp) {
-                acc += component_alpha(S, m.comp[c], p.wl);
+                const DevComponent& cc = m.comp[c];
+                const float ac = cc.abs_table < 0 ? cc.coef
+                               : (m.single_tab == c ? alpha - m.const_sum : table_at(S, cc.abs_table, p.wl, S.tab_y));
+                acc += ac;
                 if (!found && pick < acc) { index = c; found = true; }
             }
         }
         const DevComponent& comp = m.comp[index];
-        if (comp.kind == COMP_LUMINOPHORE && u01(w.z) < comp.qy) {
+        if (comp.kind == COMP_LUMINOPHORE && u_qy < comp.qy) {
             const uint4 v = rng.next();
             float sp, cp;
             sincospif(2.f * u01(v.x), &sp, &cp);
             const float mu = 2.f * u01(v.y) - 1.f;
-            const float st = sqrtf(fmaxf(1.f - mu * mu, 0.f));
+            const float st = sqrtf(fmaxf(fmaf(-mu, mu, 1.f), 0.f));
             p.dx = st * cp; p.dy = st * sp; p.dz = mu;
-            const int lo = __ldg(S.tab_begin + comp.ems_table), n = __ldg(S.tab_begin + comp.ems_table + 1) - lo;
-            const float ev = HC_EV_NM / p.wl + 1.5f * KB_EV * 300.f;
-            const float p1 = interp(HC_EV_NM / ev, S.tab_x + lo, S.tab_cdf + lo, n);
+            const DevTable& T = S.tab[comp.ems_table];
+            const float ev = fdiv(HC_EV_NM, p.wl) + 1.5f * KB_EV * 300.f;
+            const float p1 = table_at(S, comp.ems_table, fdiv(HC_EV_NM, ev), S.tab_cdf);
             const float gamma = fmaf(1.f - p1, u01(v.z), p1);
-            p.wl = interp(gamma, S.tab_cdf + lo, S.tab_x + lo, n);
+            p.wl = inverse_cdf(gamma, S.tab_cdf + T.begin, S.tab_x + T.begin, T.n, S.tab_inv + T.inv_begin, INV_CDF_BUCKETS);
             refresh_alphas(S, p);
-            p.emitted = 1;
+            p.aux |= 256;
             out.event = EV_EMIT;
             return -1;
         }
@@ -525,32 +569,40 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, Rng& rn
 
     // reach the surface
     p.xr = fmaf(p.dx, h.t, p.xr); p.y = fmaf(p.dy, h.t, p.y); p.z = fmaf(p.dz, h.t, p.z);
+    if (h.kind == SURF_CELL) {
+        // step into the neighbouring cell; nothing physical happens here
+        p.kc += h.face;
+        p.xr = h.face > 0 ? -0.5f * S.pitch : 0.5f * S.pitch;
+        out.event = EV_NONE;
+        return -1;
+    }
     float nx, ny, nz;
     if (h.kind == SURF_BOX || h.kind == SURF_CAP) {
         box_normal(h.face, nx, ny, nz);
-        // snap the coordinate of the face that was hit
-        if (h.face < 2) { if (h.kind == SURF_BOX) { const float xa = (h.face & 1) ? S.hx : -S.hx; p.xr = xa - fmaf((float)p.kc, S.pitch, S.cx0); } }
-        else if (h.face < 4) p.y = (h.face & 1) ? S.hy : -S.hy;
-        else p.z = (h.face & 1) ? S.hz : -S.hz;
-    } else {
-        if (h.kind == SURF_OUTER && p.medium == MED_PLATE) {   // entering capillary h.ch from the plate
-            p.xr -= (float)(h.ch - p.kc) * S.pitch;
-            p.kc = h.ch;
+        if (p.medium != MED_AIR) {   // snap the coordinate of the face that was hit
+            if (h.face < 2) { if (h.kind == SURF_BOX) p.xr = (h.face & 1) ? S.cell_hi_last : S.cell_lo_first; }
+            else if (h.face < 4) p.y = (h.face & 1) ? S.hy : -S.hy;
+            else p.z = ((h.face & 1) ? S.hz : -S.hz) - S.zc;
         }
-        const float oz = p.z - S.zc;
-        const float inv = rsqrtf(p.xr * p.xr + oz * oz);
-        nx = p.xr * inv; ny = 0.f; nz = oz * inv;
+    } else {
+        const float inv = rsqrtf(fmaf(p.xr, p.xr, p.z * p.z));
+        nx = p.xr * inv; ny = 0.f; nz = p.z * inv;
+        if (h.kind == SURF_OUTER && p.medium == MED_OUTER) {
+            // leaving the tube wall: pvtrace's adjacent is whatever the straight continuation meets next
+            if (sibling_ahead(S, p.kc, p.xr, p.y, p.z, p.dx, p.dy, p.dz) >= 0) h.adj = MED_OUTER;
+        }
     }
-    const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, h.n1, h.n2);
-    ++p.n_surface;
-    out.ch = p.kc;
-    if (u01(w.y) < I.R) {
+    const float n1 = S.med[h.container].n, n2 = S.med[h.adj].n;
+    const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, n1, n2);
+    if (u_surf < I.R) {
         reflect_dir(p, I);
         out.event = EV_REFLECT;
+        if (p.medium == MED_AIR) return BIN_ENTRY_REFLECT;   // bounced off at first contact, leaves the scene
         return -1;
     }
-    refract_dir(p, I, h.n1, h.n2);
+    refract_dir(p, I);
     out.event = EV_TRANSMIT;
+    if (p.medium == MED_AIR) { p.medium = (p.aux >> 4) & 3; return -1; }
     if (h.kind == SURF_BOX || h.kind == SURF_CAP) {
         // left the plate assembly: the next follow() iteration meets only the world sphere -> EXIT
         p.medium = MED_AIR;
@@ -558,51 +610,6 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, Rng& rn
     }
     if (h.kind == SURF_OUTER) p.medium = (p.medium == MED_PLATE) ? MED_OUTER : MED_PLATE;
     else p.medium = (p.medium == MED_OUTER) ? MED_INNER : MED_OUTER;
-    if (p.medium == MED_PLATE) rebase_x(S, p);
-    return -1;
-}
-
-// Start of a photon history.  A ray whose origin lies inside the plate starts there without an entry
-// event (pvtrace finds the container geometrically); otherwise the first follow() iteration hits the
-// plate (or misses it) and does the Fresnel test at the entry face.
-// Returns -1 when the photon is alive inside the plate assembly, else its tally bin.
-__device__ __forceinline__ int photon_start(const DevScene& S, Photon& p, float ox, float oy, float oz,
-                                            bool have_anchor_entry, float ax, float ay, Rng& rng, StepOut& out) {
-    p.steps = 0; p.n_surface = 0; p.emitted = 0;
-    out.event = EV_GENERATE; out.medium = MED_AIR; out.kind = SURF_NONE; out.face = 0; out.ch = 0;
-    float t; int face;
-    float px, py, pz;
-    if (have_anchor_entry) { face = 5; px = ax; py = ay; pz = S.hz; }
-    else {
-        if (fabsf(ox) < S.hx && fabsf(oy) < S.hy && fabsf(oz) < S.hz) {
-            p.y = oy; p.z = oz;
-            locate_in_plate(S, p, ox);
-            return -1;
-        }
-        if (!box_enter(S, ox, oy, oz, p.dx, p.dy, p.dz, t, face)) { p.steps = 1; out.event = EV_EXIT; return BIN_MISS; }
-        px = fmaf(p.dx, t, ox); py = fmaf(p.dy, t, oy); pz = fmaf(p.dz, t, oz);
-        if (face < 2) px = (face & 1) ? S.hx : -S.hx; else if (face < 4) py = (face & 1) ? S.hy : -S.hy; else pz = (face & 1) ? S.hz : -S.hz;
-    }
-    p.steps = 1;
-    p.y = py; p.z = pz;
-    locate_in_plate(S, p, px);
-    const int inside_medium = p.medium;
-    float nx, ny, nz;
-    box_normal(face, nx, ny, nz);
-    const float n1 = S.med[MED_AIR].n, n2 = S.med[MED_PLATE].n;
-    const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, n1, n2);
-    const uint4 w = rng.next();
-    p.n_surface = 1;
-    out.medium = MED_AIR; out.kind = SURF_BOX; out.face = face; out.ch = p.kc;
-    if (u01(w.y) < I.R) {
-        reflect_dir(p, I);
-        p.medium = MED_AIR;
-        out.event = EV_REFLECT;
-        return BIN_ENTRY_REFLECT;
-    }
-    refract_dir(p, I, n1, n2);
-    p.medium = inside_medium;
-    out.event = EV_TRANSMIT;
     return -1;
 }
 
