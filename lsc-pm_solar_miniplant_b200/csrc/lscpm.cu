@@ -539,7 +539,6 @@ int lower_scene(const LscpmSceneDesc* d, LscpmScene* s) {
 
     DevScene& D = s->dev;
     memset(&D, 0, sizeof(D));
-    if (d->n_tables > MAX_TABLES) return fail(LSCPM_EUNSUPPORTED, "more than 8 spectrum tables in one scene");
     D.hx = (float)s->hx; D.hy = (float)s->hy; D.hz = (float)s->hz;
     D.has_caps = s->n_ch > 0;
     D.has_inner = s->has_inner;
@@ -708,37 +707,104 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
 
     std::vector<float> tx, ty, tc;
     std::vector<unsigned short> fwd, inv;
-    for (int t = 0; t < desc->n_tables; ++t) {
-        const int lo = desc->table_begin[t], n = desc->table_begin[t + 1] - lo;
-        if (n > 65000) return bail(fail(LSCPM_EUNSUPPORTED, "spectrum table with more than 65000 knots"));
-        const double* x = desc->table_x + lo;
+    int n_dev_tables = 0;
+    // Stores one knot table (resampled onto its regular grid when the knots sit on one) and returns its index.
+    auto add_table = [&](const std::vector<double>& x, const std::vector<double>& y, int* index) -> int {
+        const int n = (int)x.size();
+        if (n_dev_tables >= MAX_TABLES) return fail(LSCPM_EUNSUPPORTED, "too many spectrum tables in one scene");
         std::vector<double> cdf;
-        trapezoid_cdf(x, desc->table_y + lo, n, cdf);
-        DevTable& T = s->dev.tab[t];
-        T.begin = (int)tx.size(); T.n = n;
-        for (int i = 0; i < n; ++i) { tx.push_back((float)x[i]); ty.push_back((float)desc->table_y[lo + i]); tc.push_back((float)cdf[i]); }
-        // forward index: bucket width = smallest knot spacing (capped at 16384 buckets; table_at() then walks a little)
+        trapezoid_cdf(x.data(), y.data(), n, cdf);
         double wmin = x[n - 1] - x[0];
         for (int i = 1; i < n; ++i) wmin = std::min(wmin, x[i] - x[i - 1]);
         const double range = x[n - 1] - x[0];
-        int nb = (int)std::ceil(range / wmin);
-        nb = std::max(1, std::min(nb, 16384));
-        const double w = range / nb;
-        T.x0 = (float)x[0]; T.inv_w = (float)(1.0 / w); T.fwd_begin = (int)fwd.size(); T.fwd_n = nb;
-        int j = 0;
-        for (int b = 0; b < nb; ++b) {
-            const double start = x[0] + b * w;
-            while (j + 2 < n && x[j + 1] <= start) ++j;
-            fwd.push_back((unsigned short)j);
+        // regular grid?  every knot within 1e-6 of a multiple of the smallest spacing
+        bool regular = range / wmin < 60000.0;
+        for (int i = 0; regular && i < n; ++i) {
+            const double q = (x[i] - x[0]) / wmin;
+            if (std::fabs(q - std::round(q)) > 1e-6) regular = false;
         }
-        // inverse guide on the CDF: idx[b] = last knot (<= n-2) with cdf <= b / G
+        std::vector<double> gx, gy, gc;
+        if (regular) {
+            const int m = (int)std::llround(range / wmin) + 1;
+            int j = 0;
+            for (int i = 0; i < m; ++i) {
+                const double xi = i == m - 1 ? x[n - 1] : x[0] + i * wmin;
+                while (j + 2 < n && x[j + 1] <= xi) ++j;
+                const double f = (xi - x[j]) / (x[j + 1] - x[j]);
+                gx.push_back(xi); gy.push_back(y[j] + f * (y[j + 1] - y[j])); gc.push_back(cdf[j] + f * (cdf[j + 1] - cdf[j]));
+            }
+        } else { gx = x; gy = y; gc = cdf; }
+        const int m = (int)gx.size();
+        if (m > 65000) return fail(LSCPM_EUNSUPPORTED, "spectrum table with more than 65000 knots");
+        DevTable& T = s->dev.tab[n_dev_tables];
+        T.begin = (int)tx.size(); T.n = m; T.uniform = regular ? 1 : 0;
+        for (int i = 0; i < m; ++i) { tx.push_back((float)gx[i]); ty.push_back((float)gy[i]); tc.push_back((float)gc[i]); }
+        T.x0 = (float)gx[0]; T.fwd_begin = (int)fwd.size();
+        if (regular) { T.inv_w = (float)(1.0 / wmin); T.fwd_n = 0; }
+        else {
+            int nb = std::max(1, std::min((int)std::ceil(range / wmin), 16384));
+            const double w = range / nb;
+            T.inv_w = (float)(1.0 / w); T.fwd_n = nb;
+            int j = 0;
+            for (int bkt = 0; bkt < nb; ++bkt) {
+                const double start = gx[0] + bkt * w;
+                while (j + 2 < m && gx[j + 1] <= start) ++j;
+                fwd.push_back((unsigned short)j);
+            }
+        }
+        // inverse guide on the CDF: idx[b] = last knot (<= m-2) with cdf <= b / G
         T.inv_begin = (int)inv.size();
-        j = 0;
-        for (int b = 0; b <= INV_CDF_BUCKETS; ++b) {
-            const double level = (double)b / INV_CDF_BUCKETS;
-            while (j + 2 < n && cdf[j + 1] <= level) ++j;
+        int j = 0;
+        for (int bkt = 0; bkt <= INV_CDF_BUCKETS; ++bkt) {
+            const double level = (double)bkt / INV_CDF_BUCKETS;
+            while (j + 2 < m && gc[j + 1] <= level) ++j;
             inv.push_back((unsigned short)j);
         }
+        *index = n_dev_tables++;
+        return LSCPM_OK;
+    };
+    auto knots_of = [&](int t, std::vector<double>& x, std::vector<double>& y) {
+        const int lo = desc->table_begin[t], n = desc->table_begin[t + 1] - lo;
+        x.assign(desc->table_x + lo, desc->table_x + lo + n);
+        y.assign(desc->table_y + lo, desc->table_y + lo + n);
+    };
+    auto interp_clamped = [](const std::vector<double>& x, const std::vector<double>& y, double v) {
+        if (v <= x.front()) return y.front();
+        if (v >= x.back()) return y.back();
+        const size_t j = std::upper_bound(x.begin(), x.end(), v) - x.begin() - 1;
+        return y[j] + (v - x[j]) / (x[j + 1] - x[j]) * (y[j + 1] - y[j]);
+    };
+    for (int t = 0; t < desc->n_tables; ++t) {   // scene tables keep their indices
+        std::vector<double> x, y; int idx;
+        knots_of(t, x, y);
+        if ((rc = add_table(x, y, &idx))) return bail(rc);
+    }
+    // one total-attenuation table per medium: constants folded in, knots = union of the components' knots
+    for (int med = MED_PLATE; med <= MED_INNER; ++med) {
+        DevMedium& m = s->dev.med[med];
+        m.alpha_table = -1;
+        std::vector<double> ux;
+        for (int c = 0; c < m.n_comp; ++c)
+            if (m.comp[c].abs_table >= 0) {
+                std::vector<double> x, y; knots_of(m.comp[c].abs_table, x, y);
+                ux.insert(ux.end(), x.begin(), x.end());
+            }
+        if (ux.empty()) continue;
+        std::sort(ux.begin(), ux.end());
+        ux.erase(std::unique(ux.begin(), ux.end()), ux.end());
+        std::vector<double> uy(ux.size(), (double)0);
+        for (size_t i = 0; i < ux.size(); ++i) {
+            double total = 0;
+            const int mat_c0 = med == MED_PLATE ? desc->mat_comp_begin[desc->node_material[s->node_plate]]
+                             : med == MED_OUTER ? desc->mat_comp_begin[desc->node_material[s->node_outer[0]]]
+                                                : desc->mat_comp_begin[desc->node_material[s->node_inner[0]]];
+            for (int c = 0; c < m.n_comp; ++c) {
+                if (m.comp[c].abs_table < 0) total += desc->comp_coefficient[mat_c0 + c];
+                else { std::vector<double> x, y; knots_of(m.comp[c].abs_table, x, y); total += interp_clamped(x, y, ux[i]); }
+            }
+            uy[i] = total;
+        }
+        if ((rc = add_table(ux, uy, &m.alpha_table))) return bail(rc);
     }
     std::vector<int> abs_outer, abs_inner;
     for (int k = 0; k < s->n_ch; ++k) {

@@ -34,7 +34,7 @@
 namespace lscpm {
 
 constexpr int MAX_COMP = 4;
-constexpr int MAX_TABLES = 8;
+constexpr int MAX_TABLES = 12;           // scene tables + one total-attenuation table per medium
 constexpr int MED_AIR = 0, MED_PLATE = 1, MED_OUTER = 2, MED_INNER = 3;
 constexpr int COMP_ABSORBER = 0, COMP_LUMINOPHORE = 1, COMP_REACTOR = 2;
 constexpr int LIGHT_DIRECT = 0, LIGHT_DIFFUSE = 1;
@@ -62,6 +62,7 @@ struct DevMedium {
     float n;
     int n_comp;
     int single_tab;      // index of the only tabulated component (its alpha = total - const_sum), or -1
+    int alpha_table;     // table of the TOTAL attenuation (constants folded in) on the union of the knots, or -1
     float const_sum;     // sum of the constant coefficients
     DevComponent comp[MAX_COMP];
 };
@@ -69,7 +70,9 @@ struct DevMedium {
 // knot table with O(1) forward lookup (value at abscissa) and guided inverse-CDF lookup
 struct DevTable {
     int begin, n;        // knots [begin, begin+n) of tab_x / tab_y / tab_cdf
-    float x0, inv_w;     // bucket b covers x0 + [b, b+1) / inv_w; bucket width <= smallest knot spacing
+    int uniform;         // knots are equally spaced (tables whose knots sit on a regular grid are stored resampled
+                         // onto it — piecewise-linear interpolation is unchanged); lookup is then pure arithmetic
+    float x0, inv_w;     // uniform: knot spacing 1/inv_w.  otherwise bucket b covers x0 + [b, b+1) / inv_w
     int fwd_begin, fwd_n;// forward bucket index (uint16 knot numbers) in tab_fwd
     int inv_begin;       // inverse guide table (INV_CDF_BUCKETS + 1 entries) in tab_inv, or -1
 };
@@ -179,25 +182,33 @@ __device__ __forceinline__ float lerp_knots(float v, const float* __restrict__ x
     return den > 0.f ? fmaf(fdiv(f1 - f0, den), v - x0, f0) : f0;
 }
 
-// value of column `col` (tab_y or tab_cdf) at abscissa v
-__device__ __forceinline__ float table_at(const DevScene& S, int t, float v, const float* __restrict__ col) {
-    const DevTable& T = S.tab[t];
-    const float* xp = S.tab_x + T.begin;
-    const float* fp = col + T.begin;
+// value of column `col` (tab_y or tab_cdf) at abscissa v — irregular tables: bucket index + short walk
+__device__ __noinline__ float table_at_irregular(const DevTable T, const float* __restrict__ xp, const float* __restrict__ fp,
+                                                 const unsigned short* __restrict__ fwd, float v) {
     if (v <= __ldg(xp)) return __ldg(fp);
     if (v >= __ldg(xp + T.n - 1)) return __ldg(fp + T.n - 1);
     int b = (int)((v - T.x0) * T.inv_w);
     b = min(max(b, 0), T.fwd_n - 1);
-    int j = __ldg(S.tab_fwd + T.fwd_begin + b);
-    // the bucket is no wider than the smallest knot spacing: at most one knot boundary either side
-    if (j + 2 < T.n && v >= __ldg(xp + j + 1)) ++j;
-    if (j + 2 < T.n && v >= __ldg(xp + j + 1)) ++j;
-    if (j > 0 && v < __ldg(xp + j)) --j;
+    int j = __ldg(fwd + b);
+    while (j + 2 < T.n && v >= __ldg(xp + j + 1)) ++j;
+    while (j > 0 && v < __ldg(xp + j)) --j;
     return lerp_knots(v, xp, fp, j);
 }
 
+__device__ __forceinline__ float table_at(const DevScene& S, int t, float v, const float* __restrict__ col) {
+    const DevTable& T = S.tab[t];
+    if (T.uniform) {
+        float f = (v - T.x0) * T.inv_w;
+        f = fminf(fmaxf(f, 0.f), (float)(T.n - 1));      // numpy.interp clamps outside the table
+        const int j = min((int)f, T.n - 2);
+        const float y0 = __ldg(col + T.begin + j), y1 = __ldg(col + T.begin + j + 1);
+        return fmaf(f - (float)j, y1 - y0, y0);
+    }
+    return table_at_irregular(T, S.tab_x + T.begin, col + T.begin, S.tab_fwd + T.fwd_begin, v);
+}
+
 // inverse CDF through a guide table: bracket [idx[b], idx[b+1]+1] then a (usually empty) bisection
-__device__ __forceinline__ float inverse_cdf(float u, const float* __restrict__ cdf, const float* __restrict__ xs, int n,
+__device__ __noinline__ float inverse_cdf(float u, const float* __restrict__ cdf, const float* __restrict__ xs, int n,
                                              const unsigned short* __restrict__ guide, int buckets) {
     if (u <= __ldg(cdf)) return __ldg(xs);
     if (u >= __ldg(cdf + n - 1)) return __ldg(xs + n - 1);
@@ -216,17 +227,35 @@ __device__ __forceinline__ float component_alpha(const DevScene& S, const DevCom
 
 __device__ __forceinline__ float medium_alpha(const DevScene& S, int medium, float wl) {
     const DevMedium& m = S.med[medium];
-    float a = m.const_sum;
-#pragma unroll
-    for (int c = 0; c < MAX_COMP; ++c)
-        if (c < m.n_comp && m.comp[c].abs_table >= 0) a += table_at(S, m.comp[c].abs_table, wl, S.tab_y);
-    return a;
+    return m.alpha_table < 0 ? m.const_sum : table_at(S, m.alpha_table, wl, S.tab_y);
 }
 
 __device__ __forceinline__ void refresh_alphas(const DevScene& S, Photon& p) {
     p.a_plate = medium_alpha(S, MED_PLATE, p.wl);
     p.a_outer = S.has_caps ? medium_alpha(S, MED_OUTER, p.wl) : 0.f;
     p.a_inner = S.has_inner ? medium_alpha(S, MED_INNER, p.wl) : 0.f;
+}
+
+// component of medium `m` that absorbs, chosen with probability alpha_c / alpha (pvtrace Material.component)
+__device__ __noinline__ int pick_component_generic(const DevScene& S, int medium, float wl, float pick) {
+    const DevMedium& m = S.med[medium];
+    float acc = 0.f;
+    for (int c = 0; c < m.n_comp - 1; ++c) {
+        acc += component_alpha(S, m.comp[c], wl);
+        if (pick < acc) return c;
+    }
+    return m.n_comp - 1;
+}
+
+__device__ __forceinline__ int pick_component(const DevScene& S, int medium, float wl, float alpha, float pick) {
+    const DevMedium& m = S.med[medium];
+    if (m.n_comp == 1) return 0;
+    if (m.n_comp == 2 && (m.single_tab >= 0 || m.alpha_table < 0)) {
+        // one constant + one tabulated component (or two constants): no lookup needed
+        const float a0 = m.comp[0].abs_table < 0 ? m.comp[0].coef : alpha - m.const_sum;
+        return pick < a0 ? 0 : 1;
+    }
+    return pick_component_generic(S, medium, wl, pick);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -347,7 +376,7 @@ __device__ __noinline__ int sibling_ahead(const DevScene& S, int kc, float xr, f
 }
 
 // entry of the plate box for a ray starting outside it (slab test); false when it misses
-__device__ __forceinline__ bool box_enter(const DevScene& S, float ox, float oy, float oz, float dx, float dy, float dz,
+__device__ __noinline__ bool box_enter(const DevScene& S, float ox, float oy, float oz, float dx, float dy, float dz,
                                           float& t, int& face) {
     float tmin = -LSCPM_INF, tmax = LSCPM_INF;
     int fmin = -1;
@@ -461,6 +490,22 @@ __device__ __forceinline__ int place_photon(const DevScene& S, Photon& p, float 
     return -1;
 }
 
+// sky-diffuse direction (reference miniplant/utils.py:102-122): zenith ~ U(0,90) deg, azimuth ~ U(0,360) deg — uniform
+// in angle, not in solid angle — redrawn until the direction sees the plate's front face
+__device__ __noinline__ void sample_sky_direction(const DevScene& S, const DevBatch& B, Rng& rng, Photon& p) {
+    float sz, cz, sa, ca;
+    for (;;) {
+        const uint4 v = rng.next();
+        sincospif(2.f * u01(v.x), &sa, &ca);      // azimuth = 360 deg * u
+        sincospif(0.5f * u01(v.y), &sz, &cz);     // zenith  =  90 deg * u
+        if (B.cos_tilt * cz + B.sin_tilt * sz * ca >= 0.f) break;
+    }
+    const float wx = -sz * ca, wy = -sz * sa, wz = -cz;   // world direction = -sky
+    p.dx = S.w2l[0] * wx + S.w2l[1] * wy + S.w2l[2] * wz;
+    p.dy = S.w2l[3] * wx + S.w2l[4] * wy + S.w2l[5] * wz;
+    p.dz = S.w2l[6] * wx + S.w2l[7] * wy + S.w2l[8] * wz;
+}
+
 // ------------------------------------------------------------------------------------------------
 // photon generation (reference miniplant/utils.py:87-142, scene_creator.py:288-304).
 // Consumes the iteration's Philox draw `w` (x, y: mask point; z: wavelength) and leaves w.w for the entry
@@ -480,17 +525,7 @@ __device__ __forceinline__ int generate_photon(const DevScene& S, const DevBatch
     if (B.light_kind == LIGHT_DIRECT) {
         p.dx = B.dir[0]; p.dy = B.dir[1]; p.dz = B.dir[2];
     } else {
-        float sz, cz, sa, ca;
-        for (;;) {   // front-face rejection, uniform in (zenith, azimuth) angle
-            const uint4 v = rng.next();
-            sincospif(2.f * u01(v.x), &sa, &ca);      // azimuth = 360 deg * u
-            sincospif(0.5f * u01(v.y), &sz, &cz);     // zenith  =  90 deg * u
-            if (B.cos_tilt * cz + B.sin_tilt * sz * ca >= 0.f) break;
-        }
-        const float wx = -sz * ca, wy = -sz * sa, wz = -cz;   // world direction = -sky
-        p.dx = S.w2l[0] * wx + S.w2l[1] * wy + S.w2l[2] * wz;
-        p.dy = S.w2l[3] * wx + S.w2l[4] * wy + S.w2l[5] * wz;
-        p.dz = S.w2l[6] * wx + S.w2l[7] * wy + S.w2l[8] * wz;
+        sample_sky_direction(S, B, rng, p);
     }
     refresh_alphas(S, p);
     const float ox = fmaf(-B.back_off, p.dx, ax), oy = fmaf(-B.back_off, p.dy, ay), oz = fmaf(-B.back_off, p.dz, az);
@@ -529,20 +564,7 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, Rng& rn
         // absorbed inside the container: move, choose the component ~ alpha_i, radiative test
         p.xr = fmaf(p.dx, depth, p.xr); p.y = fmaf(p.dy, depth, p.y); p.z = fmaf(p.dz, depth, p.z);
         const DevMedium& m = S.med[h.container];
-        const float pick = u_surf * alpha;
-        float acc = 0.f;
-        int index = m.n_comp - 1;
-        bool found = false;
-#pragma unroll
-        for (int c = 0; c < MAX_COMP; ++c) {
-            if (c < m.n_comp) {
-                const DevComponent& cc = m.comp[c];
-                const float ac = cc.abs_table < 0 ? cc.coef
-                               : (m.single_tab == c ? alpha - m.const_sum : table_at(S, cc.abs_table, p.wl, S.tab_y));
-                acc += ac;
-                if (!found && pick < acc) { index = c; found = true; }
-            }
-        }
+        const int index = pick_component(S, h.container, p.wl, alpha, u_surf * alpha);
         const DevComponent& comp = m.comp[index];
         if (comp.kind == COMP_LUMINOPHORE && u_qy < comp.qy) {
             const uint4 v = rng.next();
