@@ -73,7 +73,9 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
     __syncwarp();
     int hbatch = -1;                        // warp-uniform: batch whose photons the shared row accumulates
 
-    unsigned long long cur = 0, end = 0;   // warp-uniform: photons [cur, end) of batch `cbatch` are unclaimed
+    // warp-uniform work item: photons chunk_base + [c_next, c_end) of batch `cbatch` are unclaimed
+    unsigned long long chunk_base = 0;
+    unsigned c_next = 0, c_end = 0;
     int cbatch = 0;
     bool more = true;                       // work items may remain in the global queue
 
@@ -84,75 +86,82 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
     unsigned n_events = 0;                  // low 16 bits: interaction events, high 16 bits: emissions
 
     for (;;) {
-        // ---- refill dead lanes ------------------------------------------------------------------
+        // ---- step every live photon ---------------------------------------------------------------
+        int status = -1;
+        if (alive) {
+            const uint4 w = rng.next();
+            StepOut so;
+            status = photon_step(S, p, w, so);
+            if (counts_as_event(so.event)) ++n_events;
+            if (so.event == EV_EMIT) n_events += 0x10000u;
+        }
+        // ---- tally the photons that ended -----------------------------------------------------------
+        if (status >= 0) {
+            if (batch == hbatch) {
+                atomicAdd(hist + status, 1u);
+                atomicAdd(hist + S.n_bins, n_events & 0xffffu);
+                if (n_events >> 16) atomicAdd(hist + S.n_bins + 1, n_events >> 16);
+            } else {
+                unsigned long long* row = A.tallies + (size_t)batch * stride;
+                atomicAdd(row + status, 1ULL);
+                atomicAdd(row + S.n_bins, (unsigned long long)(n_events & 0xffffu));
+                if (n_events >> 16) atomicAdd(row + S.n_bins + 1, (unsigned long long)(n_events >> 16));
+            }
+            alive = false;
+        }
+        // ---- refill dead lanes from the warp's work item --------------------------------------------
         bool want = !alive;
         bool fresh = false;
         while (true) {
             const unsigned pending = __ballot_sync(FULL_MASK, want);
             if (!pending) break;
-            if (cur >= end) {
+            if (c_next >= c_end) {
                 if (!more) break;
                 unsigned long long id = 0;
                 if (lane == 0) id = atomicAdd(A.work_counter, 1ULL);
                 id = __shfl_sync(FULL_MASK, id, 0);
                 if (id >= A.n_chunks) { more = false; break; }
                 cbatch = (int)(id / A.chunks_per_batch);
-                cur = (id % A.chunks_per_batch) * (unsigned long long)A.chunk;
-                end = min(cur + (unsigned long long)A.chunk, A.photon_count);
+                const unsigned long long first = (id % A.chunks_per_batch) * (unsigned long long)A.chunk;
+                chunk_base = A.photon_begin + first;
+                c_next = 0;
+                c_end = (unsigned)min((unsigned long long)A.chunk, A.photon_count - first);
                 if (cbatch != hbatch) {
                     if (hbatch >= 0) flush_row(hist, A.tallies + (size_t)hbatch * stride, stride, lane);
                     hbatch = cbatch;
                 }
             }
-            const unsigned long long avail = end - cur;
+            const unsigned avail = c_end - c_next;
             const unsigned rank = __popc(pending & lane_lt);
             if (want && rank < avail) {
-                const unsigned long long g = A.photon_begin + cur + rank;
+                const unsigned long long g = chunk_base + c_next + rank;
                 batch = cbatch;
                 rng.key = A.key; rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32);
                 rng.batch = A.batches[batch].batch_id; rng.calls = 0;
                 want = false;
                 fresh = true;
             }
-            cur += min((unsigned long long)__popc(pending), avail);
+            c_next += min((unsigned)__popc(pending), avail);
         }
-        const bool active = alive || fresh;
-        if (!__any_sync(FULL_MASK, active)) {
-            if (!more && cur >= end) break;
-            continue;
-        }
-        if (active) {
-            const uint4 w = rng.next();
-            float u_surf = u01(w.y);
+        // ---- source block: new photons and re-emissions ---------------------------------------------
+        if (fresh || status == STEP_EMIT) {
+            const uint4 v = rng.next();
+            WavelengthDraw wd;
             int bin = -1;
-            bool step_now = true;
             if (fresh) {
-                bin = generate_photon(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, w, p, nullptr);
-                alive = true;
+                bin = source_fresh(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr);
                 n_events = 0;
-                u_surf = u01(w.w);
-                step_now = p.medium == MED_AIR;     // born inside the plate: take fresh uniforms next iteration
+                alive = true;
+            } else {
+                source_emit(S, v, p, wd);
             }
-            if (bin < 0 && step_now) {
-                StepOut so;
-                bin = photon_step(S, p, rng, w.x, u_surf, u01(w.z), so);
-                if (counts_as_event(so.event)) ++n_events;
-                if (so.event == EV_EMIT) n_events += 0x10000u;
-            }
-            if (bin >= 0) {
-                if (batch == hbatch) {
-                    atomicAdd(hist + bin, 1u);
-                    atomicAdd(hist + S.n_bins, n_events & 0xffffu);
-                    if (n_events >> 16) atomicAdd(hist + S.n_bins + 1, n_events >> 16);
-                } else {
-                    unsigned long long* row = A.tallies + (size_t)batch * stride;
-                    atomicAdd(row + bin, 1ULL);
-                    atomicAdd(row + S.n_bins, (unsigned long long)(n_events & 0xffffu));
-                    if (n_events >> 16) atomicAdd(row + S.n_bins + 1, (unsigned long long)(n_events >> 16));
-                }
+            source_finish(S, p, wd);
+            if (bin >= 0) {   // the ray never touches the plate (rare): tally straight to global memory
+                atomicAdd(A.tallies + (size_t)batch * stride + bin, 1ULL);
                 alive = false;
             }
         }
+        if (!__any_sync(FULL_MASK, alive) && !more && c_next >= c_end) break;
     }
     if (hbatch >= 0) flush_row(hist, A.tallies + (size_t)hbatch * stride, stride, lane);
 }
@@ -165,10 +174,12 @@ __global__ void emit_kernel(const __grid_constant__ DevScene S, const DevBatch* 
     if (i >= n) return;
     const unsigned long long g = photon_begin + (unsigned long long)i;
     Rng rng; rng.key = key; rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32); rng.batch = batch->batch_id; rng.calls = 0;
-    const uint4 w = rng.next();
+    const uint4 v = rng.next();
     Photon p;
+    WavelengthDraw wd;
     float origin[3];
-    generate_photon(S, *batch, spec_x, spec_cdf, spec_guide, rng, w, p, origin);
+    source_fresh(S, *batch, spec_x, spec_cdf, spec_guide, rng, v, p, wd, origin);
+    source_finish(S, p, wd);
     float* o = out + 7 * i;
     o[0] = origin[0]; o[1] = origin[1]; o[2] = origin[2]; o[3] = p.dx; o[4] = p.dy; o[5] = p.dz; o[6] = p.wl;
 }
@@ -192,10 +203,10 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
     p.wl = 555.f; p.a_plate = p.a_outer = p.a_inner = 0.f; p.steps = 0; p.aux = 0;
     float nx, ny, nz;
     if (q.medium == MED_AIR) {
-        float t; int face;
-        if (!box_enter(S, abs_x(S, p), p.y, q.z, p.dx, p.dy, p.dz, t, face)) { out[i] = o; return; }
-        o.found = 1; o.t = t; o.kind = SURF_BOX; o.face = face; o.container = MED_AIR; o.adj = MED_PLATE; o.ch = 0;
-        box_normal(face, nx, ny, nz);
+        const Entry e = plate_entry(S.hx, S.hy, S.hz, abs_x(S, p), p.y, q.z, p.dx, p.dy, p.dz);
+        if (e.t < 0.f) { out[i] = o; return; }
+        o.found = 1; o.t = e.t; o.kind = SURF_BOX; o.face = e.face; o.container = MED_AIR; o.adj = MED_PLATE; o.ch = 0;
+        box_normal(e.face, nx, ny, nz);
     } else {
         // march over virtual cell crossings until a real interface
         float travelled = 0.f;
@@ -248,7 +259,14 @@ __global__ void follow_kernel(const __grid_constant__ DevScene S, const FollowIn
     while (bin < 0) {
         const uint4 w = rng.next();
         StepOut so;
-        bin = photon_step(S, p, rng, w.x, u01(w.y), u01(w.z), so);
+        bin = photon_step(S, p, w, so);
+        if (bin == STEP_EMIT) {
+            const uint4 v = rng.next();
+            WavelengthDraw wd;
+            source_emit(S, v, p, wd);
+            source_finish(S, p, wd);
+            bin = -1;
+        }
         if (so.event == EV_NONE) continue;
         if (k < max_steps) {
             FollowStep& s = steps[(size_t)i * max_steps + k];

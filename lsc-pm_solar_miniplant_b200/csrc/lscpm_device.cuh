@@ -26,7 +26,11 @@
 //     iteration tests exactly one capillary; crossing a cell boundary is a virtual, uncounted step (free paths
 //     are memoryless, so re-sampling the Beer-Lambert depth per sub-segment leaves the statistics unchanged);
 //   * table lookups are O(1) through bucket indices instead of binary searches;
-//   * a fresh photon shares the iteration's Philox call and its entry Fresnel test runs in the common step.
+//   * photon generation and luminophore re-emission share ONE "source" block at the end of the iteration (new
+//     direction + wavelength by inverse CDF + attenuation refresh), and a fresh photon's entry Fresnel test runs
+//     in the common step of the next iteration;
+//   * rare paths (sky-diffuse rejection loop, generic plate entry, sibling search, irregular tables) are out of line
+//     and exchange scalars only, so the photon state never leaves registers.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -135,6 +139,7 @@ struct Hit {
     int ch;                    // sibling capillary (probe only)
     int container;             // medium whose material governs the segment
     int adj;                   // medium on the far side of the interface (pvtrace's `adjacent`)
+    bool maybe_sibling;        // tube-wall exit whose continuation could reach a neighbouring capillary
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -307,42 +312,41 @@ __device__ __forceinline__ Hit compute_hit(const DevScene& S, const Photon& p) {
     if (!S.has_inner) i_near = LSCPM_INF;
 
     const int yface = p.dy > 0.f ? 3 : 2;
-    if (p.medium == MED_PLATE) {
-        h.container = MED_PLATE;
-        // box faces / cell boundary
-        float t = tz; int kind = SURF_BOX, face = p.dz > 0.f ? 5 : 4;
-        if (ty < t) { t = ty; face = yface; }
-        if (tx < t) {
-            t = tx;
-            const bool plate_face = p.dx > 0.f ? last : first;
-            kind = plate_face ? SURF_BOX : SURF_CELL;
-            face = plate_face ? (p.dx > 0.f ? 1 : 0) : (p.dx > 0.f ? 1 : -1);
-        }
-        h.adj = MED_AIR;
-        if (o_near < t) { t = o_near; kind = SURF_OUTER; face = 0; h.adj = MED_OUTER; }
-        h.t = fmaxf(t, 0.f); h.kind = kind; h.face = face;
-        return h;
+    // PLATE: box faces / cell boundary / the cell's capillary
+    float t_pl = tz; int k_pl = SURF_BOX, f_pl = p.dz > 0.f ? 5 : 4, adj_pl = MED_AIR;
+    if (ty < t_pl) { t_pl = ty; f_pl = yface; }
+    if (tx < t_pl) {
+        t_pl = tx;
+        const bool plate_face = p.dx > 0.f ? last : first;
+        k_pl = plate_face ? SURF_BOX : SURF_CELL;
+        f_pl = plate_face ? (p.dx > 0.f ? 1 : 0) : (p.dx > 0.f ? 1 : -1);
     }
-    if (p.medium == MED_OUTER) {
-        if (i_near < o_far && i_near < ty) {
-            h.t = i_near; h.kind = SURF_INNER; h.face = 0; h.container = MED_OUTER; h.adj = MED_INNER;
-        } else if (ty <= o_far) {
-            // cap coincides with the plate face; the plate sorts first and becomes container and hit node
-            h.t = fmaxf(ty, 0.f); h.kind = SURF_CAP; h.face = yface; h.container = MED_PLATE; h.adj = MED_OUTER;
-        } else {
-            h.t = o_far; h.kind = SURF_OUTER; h.face = 0; h.container = MED_OUTER;
-            h.adj = MED_PLATE;     // provisional: sibling_ahead() upgrades it to MED_OUTER
-        }
-        return h;
-    }
-    // MED_INNER
-    if (ty <= i_far) {
-        h.t = fmaxf(ty, 0.f); h.kind = SURF_CAP; h.face = yface; h.container = MED_PLATE; h.adj = MED_OUTER;
-    } else {
-        h.t = i_far; h.kind = SURF_INNER; h.face = 0; h.container = MED_INNER;
-        // adjacent = second intersection: the tube wall's outer surface, unless the cap (plate first) comes earlier
-        h.adj = (ty <= o_far) ? MED_PLATE : MED_OUTER;
-    }
+    if (o_near < t_pl) { t_pl = o_near; k_pl = SURF_OUTER; f_pl = 0; adj_pl = MED_OUTER; }
+    // OUTER: inner cylinder, else cap (coincides with the plate face: plate sorts first and becomes container and
+    // hit node), else the tube's own outer surface (adjacent provisional: sibling search may upgrade it)
+    const bool ou_inner = i_near < o_far && i_near < ty;
+    const bool ou_cap = !ou_inner && ty <= o_far;
+    const float t_ou = ou_inner ? i_near : (ou_cap ? ty : o_far);
+    const int k_ou = ou_inner ? SURF_INNER : (ou_cap ? SURF_CAP : SURF_OUTER);
+    const int c_ou = ou_cap ? MED_PLATE : MED_OUTER;
+    const int adj_ou = ou_inner ? MED_INNER : (ou_cap ? MED_OUTER : MED_PLATE);
+    // INNER: cap, else the inner surface with adjacent = second intersection (tube wall, unless the cap comes first)
+    const bool in_cap = ty <= i_far;
+    const float t_in = in_cap ? ty : i_far;
+    const int k_in = in_cap ? SURF_CAP : SURF_INNER;
+    const int c_in = in_cap ? MED_PLATE : MED_INNER;
+    const int adj_in = in_cap ? MED_OUTER : ((ty <= o_far) ? MED_PLATE : MED_OUTER);
+
+    const bool is_pl = p.medium == MED_PLATE, is_ou = p.medium == MED_OUTER;
+    h.t = fmaxf(is_pl ? t_pl : (is_ou ? t_ou : t_in), 0.f);
+    h.kind = is_pl ? k_pl : (is_ou ? k_ou : k_in);
+    h.face = is_pl ? f_pl : ((h.kind == SURF_CAP) ? yface : 0);
+    h.container = is_pl ? MED_PLATE : (is_ou ? c_ou : c_in);
+    h.adj = is_pl ? adj_pl : (is_ou ? adj_ou : adj_in);
+    // a tube-wall exit may have a sibling capillary ahead only if the straight continuation travels far enough in x
+    // before it leaves the plate through a y or z face (x faces can only come earlier)
+    h.maybe_sibling = is_ou && h.kind == SURF_OUTER &&
+                      fabsf(p.dx) * (fminf(ty, tz) - o_far) > (S.pitch - S.r_o - fabsf(fmaf(p.dx, o_far, p.xr)));
     return h;
 }
 
@@ -373,29 +377,6 @@ __device__ __noinline__ int sibling_ahead(const DevScene& S, int kc, float xr, f
         if (t > 0.f) return j;
     }
     return -1;
-}
-
-// entry of the plate box for a ray starting outside it (slab test); false when it misses
-__device__ __noinline__ bool box_enter(const DevScene& S, float ox, float oy, float oz, float dx, float dy, float dz,
-                                          float& t, int& face) {
-    float tmin = -LSCPM_INF, tmax = LSCPM_INF;
-    int fmin = -1;
-    const float h[3] = {S.hx, S.hy, S.hz}, o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
-#pragma unroll
-    for (int ax = 0; ax < 3; ++ax) {
-        if (d[ax] == 0.f) {
-            if (fabsf(o[ax]) > h[ax]) return false;
-            continue;
-        }
-        float tlo = (-h[ax] - o[ax]) / d[ax], thi = (h[ax] - o[ax]) / d[ax];
-        int flo = 2 * ax;
-        if (tlo > thi) { const float tt = tlo; tlo = thi; thi = tt; flo = 2 * ax + 1; }
-        if (tlo > tmin) { tmin = tlo; fmin = flo; }
-        tmax = fminf(tmax, thi);
-    }
-    if (tmin > tmax || tmin <= 0.f) return false;
-    t = tmin; face = fmin;
-    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -466,6 +447,59 @@ __device__ __forceinline__ void locate_in_plate(const DevScene& S, Photon& p, fl
     if (rr < S.r_o2) p.medium = (S.has_inner && rr < S.r_i2) ? MED_INNER : MED_OUTER;
 }
 
+// sky-diffuse direction (reference miniplant/utils.py:102-122): zenith ~ U(0,90) deg, azimuth ~ U(0,360) deg — uniform
+// in angle, not in solid angle — redrawn until the direction sees the plate's front face.  Returns the WORLD
+// direction of travel (= -sky) and the advanced Philox call counter.
+struct SkyDraw { float x, y, z; uint32_t calls; };
+__device__ __noinline__ SkyDraw sample_sky_direction(float cos_tilt, float sin_tilt, uint32_t k0, uint32_t k1, uint32_t p_lo,
+                                                     uint32_t p_hi, uint32_t batch, uint32_t calls) {
+    float sz, cz, sa, ca;
+    for (;;) {
+        const uint4 v = philox4x32_10(make_uint4(p_lo, p_hi, batch, calls++), make_uint2(k0, k1));
+        sincospif(2.f * u01(v.x), &sa, &ca);      // azimuth = 360 deg * u
+        sincospif(0.5f * u01(v.y), &sz, &cz);     // zenith  =  90 deg * u
+        if (cos_tilt * cz + sin_tilt * sz * ca >= 0.f) break;
+    }
+    SkyDraw d; d.x = -sz * ca; d.y = -sz * sa; d.z = -cz; d.calls = calls;
+    return d;
+}
+
+// generic plate entry for a ray that starts outside the box (scalars in, scalars out); t < 0: miss
+struct Entry { float t; int face; };
+__device__ __noinline__ Entry plate_entry(float hx, float hy, float hz, float ox, float oy, float oz, float dx, float dy, float dz) {
+    float tmin = -LSCPM_INF, tmax = LSCPM_INF;
+    int fmin = -1;
+    const float h[3] = {hx, hy, hz}, o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+    Entry e; e.t = -1.f; e.face = 0;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        if (d[ax] == 0.f) {
+            if (fabsf(o[ax]) > h[ax]) return e;
+            continue;
+        }
+        float tlo = (-h[ax] - o[ax]) / d[ax], thi = (h[ax] - o[ax]) / d[ax];
+        int flo = 2 * ax;
+        if (tlo > thi) { const float tt = tlo; tlo = thi; thi = tt; flo = 2 * ax + 1; }
+        if (tlo > tmin) { tmin = tlo; fmin = flo; }
+        tmax = fminf(tmax, thi);
+    }
+    if (tmin > tmax || tmin <= 0.f) return e;
+    e.t = tmin; e.face = fmin;
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the "source" block: photon generation (reference miniplant/utils.py:87-142, scene_creator.py:288-304) and
+// luminophore re-emission (pvtrace Luminophore.emit, method 'kT') both end in "wavelength by inverse CDF, then
+// refresh the attenuation coefficients"; they share that tail and one Philox draw `v`.
+// ------------------------------------------------------------------------------------------------
+struct WavelengthDraw {
+    const float* cdf; const float* xs; const unsigned short* guide;
+    int n, buckets;
+    float u;
+    float constant;      // used when n == 0
+};
+
 // put a ray that starts at plate-local (ox,oy,oz) on the plate: inside -> its medium, outside -> AIR on the entry
 // face (or BIN_MISS).  `anchored`: the entry point is already known to be (ax, ay) on the top face.
 __device__ __forceinline__ int place_photon(const DevScene& S, Photon& p, float ox, float oy, float oz, bool anchored,
@@ -478,9 +512,10 @@ __device__ __forceinline__ int place_photon(const DevScene& S, Photon& p, float 
             p.y = oy; locate_in_plate(S, p, ox, oz); p.aux = 0;
             return -1;
         }
-        float t;
-        if (!box_enter(S, ox, oy, oz, p.dx, p.dy, p.dz, t, face)) { p.steps = 1; return BIN_MISS; }
-        px = fmaf(p.dx, t, ox); py = fmaf(p.dy, t, oy); pz = fmaf(p.dz, t, oz);
+        const Entry e = plate_entry(S.hx, S.hy, S.hz, ox, oy, oz, p.dx, p.dy, p.dz);
+        if (e.t < 0.f) { p.steps = 1; return BIN_MISS; }
+        face = e.face;
+        px = fmaf(p.dx, e.t, ox); py = fmaf(p.dy, e.t, oy); pz = fmaf(p.dz, e.t, oz);
         if (face < 2) px = (face & 1) ? S.hx : -S.hx; else if (face < 4) py = (face & 1) ? S.hy : -S.hy; else pz = (face & 1) ? S.hz : -S.hz;
     }
     p.y = py;
@@ -490,53 +525,59 @@ __device__ __forceinline__ int place_photon(const DevScene& S, Photon& p, float 
     return -1;
 }
 
-// sky-diffuse direction (reference miniplant/utils.py:102-122): zenith ~ U(0,90) deg, azimuth ~ U(0,360) deg — uniform
-// in angle, not in solid angle — redrawn until the direction sees the plate's front face
-__device__ __noinline__ void sample_sky_direction(const DevScene& S, const DevBatch& B, Rng& rng, Photon& p) {
-    float sz, cz, sa, ca;
-    for (;;) {
-        const uint4 v = rng.next();
-        sincospif(2.f * u01(v.x), &sa, &ca);      // azimuth = 360 deg * u
-        sincospif(0.5f * u01(v.y), &sz, &cz);     // zenith  =  90 deg * u
-        if (B.cos_tilt * cz + B.sin_tilt * sz * ca >= 0.f) break;
-    }
-    const float wx = -sz * ca, wy = -sz * sa, wz = -cz;   // world direction = -sky
-    p.dx = S.w2l[0] * wx + S.w2l[1] * wy + S.w2l[2] * wz;
-    p.dy = S.w2l[3] * wx + S.w2l[4] * wy + S.w2l[5] * wz;
-    p.dz = S.w2l[6] * wx + S.w2l[7] * wy + S.w2l[8] * wz;
-}
-
-// ------------------------------------------------------------------------------------------------
-// photon generation (reference miniplant/utils.py:87-142, scene_creator.py:288-304).
-// Consumes the iteration's Philox draw `w` (x, y: mask point; z: wavelength) and leaves w.w for the entry
-// Fresnel test.  Returns -1 with the photon placed, or BIN_MISS when the ray never touches the plate.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int generate_photon(const DevScene& S, const DevBatch& B, const float* __restrict__ spec_x,
-                                               const float* __restrict__ spec_cdf, const unsigned short* __restrict__ spec_guide,
-                                               Rng& rng, const uint4 w, Photon& p, float* origin /* optional [3] */) {
-    const float mx = (2.f * u01(w.x) - 1.f) * B.mask_half[0];
-    const float my = (2.f * u01(w.y) - 1.f) * B.mask_half[1];
+// generation-specific half: anchor point, direction, placement; fills the wavelength draw.  Returns -1 or BIN_MISS.
+__device__ __forceinline__ int source_fresh(const DevScene& S, const DevBatch& B, const float* __restrict__ spec_x,
+                                            const float* __restrict__ spec_cdf, const unsigned short* __restrict__ spec_guide,
+                                            Rng& rng, const uint4 v, Photon& p, WavelengthDraw& wd, float* origin) {
+    const float mx = (2.f * u01(v.x) - 1.f) * B.mask_half[0];
+    const float my = (2.f * u01(v.y) - 1.f) * B.mask_half[1];
     const float ax = fmaf(B.A[0], mx, fmaf(B.A[1], my, B.A[3]));
     const float ay = fmaf(B.A[4], mx, fmaf(B.A[5], my, B.A[7]));
     const float az = fmaf(B.A[8], mx, fmaf(B.A[9], my, B.A[11]));
-    p.wl = B.spec_begin < 0 ? B.wavelength
-                            : inverse_cdf(u01(w.z), spec_cdf + B.spec_begin, spec_x + B.spec_begin, B.spec_n,
-                                          spec_guide + B.spec_guide, SPEC_BUCKETS);
+    wd.cdf = spec_cdf + max(B.spec_begin, 0); wd.xs = spec_x + max(B.spec_begin, 0); wd.guide = spec_guide + B.spec_guide;
+    wd.n = B.spec_begin < 0 ? 0 : B.spec_n; wd.buckets = SPEC_BUCKETS; wd.u = u01(v.z); wd.constant = B.wavelength;
     if (B.light_kind == LIGHT_DIRECT) {
         p.dx = B.dir[0]; p.dy = B.dir[1]; p.dz = B.dir[2];
     } else {
-        sample_sky_direction(S, B, rng, p);
+        const SkyDraw d = sample_sky_direction(B.cos_tilt, B.sin_tilt, rng.key.x, rng.key.y, rng.p_lo, rng.p_hi, rng.batch, rng.calls);
+        rng.calls = d.calls;
+        p.dx = S.w2l[0] * d.x + S.w2l[1] * d.y + S.w2l[2] * d.z;
+        p.dy = S.w2l[3] * d.x + S.w2l[4] * d.y + S.w2l[5] * d.z;
+        p.dz = S.w2l[6] * d.x + S.w2l[7] * d.y + S.w2l[8] * d.z;
     }
-    refresh_alphas(S, p);
     const float ox = fmaf(-B.back_off, p.dx, ax), oy = fmaf(-B.back_off, p.dy, ay), oz = fmaf(-B.back_off, p.dz, az);
     if (origin) { origin[0] = ox; origin[1] = oy; origin[2] = oz; }
     return place_photon(S, p, ox, oy, oz, B.anchor_on_top && p.dz < 0.f, ax, ay);
 }
 
+// emission-specific half: isotropic direction, kT-restricted CDF window of the luminophore stored in p.aux
+__device__ __forceinline__ void source_emit(const DevScene& S, const uint4 v, Photon& p, WavelengthDraw& wd) {
+    float sp, cp;
+    sincospif(2.f * u01(v.x), &sp, &cp);
+    const float mu = 2.f * u01(v.y) - 1.f;
+    const float st = sqrtf(fmaxf(fmaf(-mu, mu, 1.f), 0.f));
+    p.dx = st * cp; p.dy = st * sp; p.dz = mu;
+    const int t = (p.aux >> 16) & 0xff;
+    const DevTable& T = S.tab[t];
+    const float ev = fdiv(HC_EV_NM, p.wl) + 1.5f * KB_EV * 300.f;
+    const float p1 = table_at(S, t, fdiv(HC_EV_NM, ev), S.tab_cdf);
+    wd.cdf = S.tab_cdf + T.begin; wd.xs = S.tab_x + T.begin; wd.guide = S.tab_inv + T.inv_begin;
+    wd.n = T.n; wd.buckets = INV_CDF_BUCKETS; wd.u = fmaf(1.f - p1, u01(v.z), p1); wd.constant = p.wl;
+    p.aux = (p.aux & 0xffff) | 256;     // has emitted
+}
+
+__device__ __forceinline__ void source_finish(const DevScene& S, Photon& p, const WavelengthDraw& wd) {
+    p.wl = wd.n == 0 ? wd.constant : inverse_cdf(wd.u, wd.cdf, wd.xs, wd.n, wd.guide, wd.buckets);
+    refresh_alphas(S, p);
+}
+
 // ------------------------------------------------------------------------------------------------
-// one iteration of follow().  `w_depth`, `u_surf`, `u_qy` are the iteration's random numbers.
-// Returns -1 while the photon lives, otherwise its tally bin.
+// one iteration of follow() with the iteration's Philox draw `w` (x: free path, y: Fresnel / component pick,
+// z: quantum yield).  Returns -1 while the photon lives, STEP_EMIT when it was absorbed by a luminophore that
+// re-emits (the source block then gives it a new direction and wavelength), otherwise its tally bin.
 // ------------------------------------------------------------------------------------------------
+constexpr int STEP_EMIT = -2;
+
 struct StepOut {
     int event;       // EV_* (EV_NONE for a virtual cell crossing)
     int medium;      // container medium of the event (for node lookup by recorders)
@@ -545,43 +586,31 @@ struct StepOut {
     int face;
 };
 
-__device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, Rng& rng, uint32_t w_depth, float u_surf,
-                                           float u_qy, StepOut& out) {
-    Hit h;
+__device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const uint4 w, StepOut& out) {
+    Hit h = compute_hit(S, p);
     if (p.medium == MED_AIR) {
-        h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.ch = p.kc;
-    } else {
-        h = compute_hit(S, p);
+        h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false;
     }
     // a virtual crossing is not a follow() iteration
     if (h.kind != SURF_CELL && ++p.steps > MAXSTEPS) { out.event = EV_KILL; return BIN_KILL; }
     const float alpha = h.container == MED_PLATE ? p.a_plate
                       : (h.container == MED_OUTER ? p.a_outer : (h.container == MED_INNER ? p.a_inner : 0.f));
-    const float depth = alpha <= ALPHA_ZERO ? LSCPM_INF : fdiv(-__logf(one_minus_u01(w_depth)), alpha);
+    const float depth = alpha <= ALPHA_ZERO ? LSCPM_INF : fdiv(-__logf(one_minus_u01(w.x)), alpha);
+    const float u_surf = u01(w.y);
     out.medium = h.container; out.ch = p.kc; out.kind = h.kind; out.face = h.face;
+    const bool absorbed = depth < h.t;
+    const float travel = absorbed ? depth : h.t;
+    p.xr = fmaf(p.dx, travel, p.xr); p.y = fmaf(p.dy, travel, p.y); p.z = fmaf(p.dz, travel, p.z);
 
-    if (depth < h.t) {
-        // absorbed inside the container: move, choose the component ~ alpha_i, radiative test
-        p.xr = fmaf(p.dx, depth, p.xr); p.y = fmaf(p.dy, depth, p.y); p.z = fmaf(p.dz, depth, p.z);
+    if (absorbed) {
+        // absorbed inside the container: choose the component ~ alpha_i, radiative test
         const DevMedium& m = S.med[h.container];
         const int index = pick_component(S, h.container, p.wl, alpha, u_surf * alpha);
         const DevComponent& comp = m.comp[index];
-        if (comp.kind == COMP_LUMINOPHORE && u_qy < comp.qy) {
-            const uint4 v = rng.next();
-            float sp, cp;
-            sincospif(2.f * u01(v.x), &sp, &cp);
-            const float mu = 2.f * u01(v.y) - 1.f;
-            const float st = sqrtf(fmaxf(fmaf(-mu, mu, 1.f), 0.f));
-            p.dx = st * cp; p.dy = st * sp; p.dz = mu;
-            const DevTable& T = S.tab[comp.ems_table];
-            const float ev = fdiv(HC_EV_NM, p.wl) + 1.5f * KB_EV * 300.f;
-            const float p1 = table_at(S, comp.ems_table, fdiv(HC_EV_NM, ev), S.tab_cdf);
-            const float gamma = fmaf(1.f - p1, u01(v.z), p1);
-            p.wl = inverse_cdf(gamma, S.tab_cdf + T.begin, S.tab_x + T.begin, T.n, S.tab_inv + T.inv_begin, INV_CDF_BUCKETS);
-            refresh_alphas(S, p);
-            p.aux |= 256;
+        if (comp.kind == COMP_LUMINOPHORE && u01(w.z) < comp.qy) {
+            p.aux = (p.aux & 0xffff) | (comp.ems_table << 16);
             out.event = EV_EMIT;
-            return -1;
+            return STEP_EMIT;
         }
         out.event = comp.kind == COMP_REACTOR ? EV_REACT : EV_ABSORB;
         const int base = h.container == MED_PLATE ? S.abs_base_plate
@@ -589,8 +618,6 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, Rng& rn
         return base + index;
     }
 
-    // reach the surface
-    p.xr = fmaf(p.dx, h.t, p.xr); p.y = fmaf(p.dy, h.t, p.y); p.z = fmaf(p.dz, h.t, p.z);
     if (h.kind == SURF_CELL) {
         // step into the neighbouring cell; nothing physical happens here
         p.kc += h.face;
@@ -598,9 +625,10 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, Rng& rn
         out.event = EV_NONE;
         return -1;
     }
+    const bool flat = h.kind == SURF_BOX || h.kind == SURF_CAP;
     float nx, ny, nz;
-    if (h.kind == SURF_BOX || h.kind == SURF_CAP) {
-        box_normal(h.face, nx, ny, nz);
+    box_normal(h.face, nx, ny, nz);
+    if (flat) {
         if (p.medium != MED_AIR) {   // snap the coordinate of the face that was hit
             if (h.face < 2) { if (h.kind == SURF_BOX) p.xr = (h.face & 1) ? S.cell_hi_last : S.cell_lo_first; }
             else if (h.face < 4) p.y = (h.face & 1) ? S.hy : -S.hy;
@@ -609,23 +637,21 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, Rng& rn
     } else {
         const float inv = rsqrtf(fmaf(p.xr, p.xr, p.z * p.z));
         nx = p.xr * inv; ny = 0.f; nz = p.z * inv;
-        if (h.kind == SURF_OUTER && p.medium == MED_OUTER) {
-            // leaving the tube wall: pvtrace's adjacent is whatever the straight continuation meets next
-            if (sibling_ahead(S, p.kc, p.xr, p.y, p.z, p.dx, p.dy, p.dz) >= 0) h.adj = MED_OUTER;
-        }
+        // leaving the tube wall: pvtrace's adjacent is whatever the straight continuation meets next
+        if (h.maybe_sibling && sibling_ahead(S, p.kc, p.xr, p.y, p.z, p.dx, p.dy, p.dz) >= 0) h.adj = MED_OUTER;
     }
     const float n1 = S.med[h.container].n, n2 = S.med[h.adj].n;
     const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, n1, n2);
-    if (u_surf < I.R) {
-        reflect_dir(p, I);
-        out.event = EV_REFLECT;
-        if (p.medium == MED_AIR) return BIN_ENTRY_REFLECT;   // bounced off at first contact, leaves the scene
+    const bool reflected = u_surf < I.R;
+    if (reflected) reflect_dir(p, I); else refract_dir(p, I);
+    out.event = reflected ? EV_REFLECT : EV_TRANSMIT;
+    if (p.medium == MED_AIR) {
+        if (reflected) return BIN_ENTRY_REFLECT;   // bounced off at first contact, leaves the scene
+        p.medium = (p.aux >> 4) & 3;
         return -1;
     }
-    refract_dir(p, I);
-    out.event = EV_TRANSMIT;
-    if (p.medium == MED_AIR) { p.medium = (p.aux >> 4) & 3; return -1; }
-    if (h.kind == SURF_BOX || h.kind == SURF_CAP) {
+    if (reflected) return -1;
+    if (flat) {
         // left the plate assembly: the next follow() iteration meets only the world sphere -> EXIT
         p.medium = MED_AIR;
         return (p.steps + 1 > MAXSTEPS) ? BIN_KILL : S.exit_base_plate + h.face;
