@@ -127,6 +127,9 @@ typedef struct LscpmScene LscpmScene;
 /* ---- library ------------------------------------------------------------------------------- */
 int lscpm_abi_version(void);
 const char* lscpm_last_error(void);
+/* The counter-based generator the kernels use, evaluated on the host (Philox4x32-10; Random123 known-answer
+ * vectors apply): out = philox(counter, key).  Pure function, no device needed. */
+void lscpm_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]);
 /* number of visible CUDA devices (0 without a GPU); never fails */
 int lscpm_device_count(void);
 

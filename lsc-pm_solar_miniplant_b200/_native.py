@@ -161,6 +161,7 @@ _SIGNATURES = {
     "lscpm_abi_version": (C.c_int, []),
     "lscpm_last_error": (C.c_char_p, []),
     "lscpm_device_count": (C.c_int, []),
+    "lscpm_philox4x32_10": (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "lscpm_scene_create": (C.c_int, [C.POINTER(SceneDesc), C.c_int, C.POINTER(C.c_void_p)]),
     "lscpm_scene_destroy": (C.c_int, [C.c_void_p]),
     "lscpm_scene_n_bins": (C.c_int, [C.c_void_p]),

@@ -682,6 +682,11 @@ int lscpm_abi_version(void) { return LSCPM_ABI_VERSION; }
 const char* lscpm_last_error(void) { return g_error.c_str(); }
 uint64_t lscpm_launch_count(void) { return g_launches.load(); }
 
+void lscpm_philox4x32_10(const uint32_t counter[4], const uint32_t key[2], uint32_t out[4]) {
+    const uint4 r = philox4x32_10(make_uint4(counter[0], counter[1], counter[2], counter[3]), make_uint2(key[0], key[1]));
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
 int lscpm_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -176,7 +176,11 @@ struct Rng {
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-8f; }
 __device__ __forceinline__ float one_minus_u01(uint32_t x) { return (float)(((~x) >> 8) + 1u) * 5.9604644775390625e-8f; }
 
-__device__ __forceinline__ float fdiv(float a, float b) { return __fdividef(a, b); }
+// single-instruction SFU approximations (MUFU.RCP / MUFU.SQRT, ~1 ulp): the geometry is statistical, and the
+// per-ray parity test (1e-5 relative) passes with them
+__device__ __forceinline__ float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fsqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fdiv(float a, float b) { return a * frcp(b); }
 
 // ------------------------------------------------------------------------------------------------
 // table lookups with numpy.interp semantics (clamped; segment = last j with xp[j] <= v)
@@ -217,7 +221,10 @@ __device__ __noinline__ float inverse_cdf(float u, const float* __restrict__ cdf
                                              const unsigned short* __restrict__ guide, int buckets) {
     if (u <= __ldg(cdf)) return __ldg(xs);
     if (u >= __ldg(cdf + n - 1)) return __ldg(xs + n - 1);
-    const int b = min((int)(u * (float)buckets), buckets - 1);
+    // clamp in the float domain: nvcc 12.9 / sm_100a folded `min((int)(u * G), G - 1)` with a constant-propagated G
+    // into VIADDMNMX with a wrong immediate inside the out-of-line clone of this function (emit / follow kernels)
+    const float fb = (float)buckets;
+    const int b = (int)fminf(u * fb, fb - 1.f);
     int lo = __ldg(guide + b), hi = min((int)__ldg(guide + b + 1) + 1, n - 1);
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -274,7 +281,7 @@ __device__ __forceinline__ float abs_x(const DevScene& S, const Photon& p) { ret
 __device__ __forceinline__ void cylinder_roots(float a, float inv_a, float b, float cross2, float rr, float r2,
                                                float& t_near, float& t_far) {
     const float disc = fmaf(a, r2, -cross2);            // = b^2 - a*c without the cancellation
-    const float s = sqrtf(fmaxf(disc, 0.f));
+    const float s = fsqrt(fmaxf(disc, 0.f));
     const float c = rr - r2;
     const float q = s + fabsf(b);
     const float r1 = fdiv(c, q), r2_ = q * inv_a;
@@ -372,7 +379,7 @@ __device__ __noinline__ int sibling_ahead(const DevScene& S, int kc, float xr, f
         const float disc = fmaf(-cross, cross, ar2);
         if (disc <= 0.f) continue;
         const float c = fmaf(ox, ox, z * z) - S.r_o2;
-        const float t = fdiv(c, sqrtf(disc) - b);
+        const float t = fdiv(c, fsqrt(disc) - b);
         if (t >= t_box) return -1;
         if (t > 0.f) return j;
     }
@@ -403,7 +410,7 @@ __device__ __forceinline__ Interface interface_eval(float dx, float dy, float dz
     const float s2 = fmaxf(fmaf(-c, c, 1.f), 0.f);
     const float k2 = fmaf(-eta * eta, s2, 1.f);
     if (n2 < n1 && k2 < 0.f) { I.R = 1.f; I.k = 0.f; return I; }   // beyond the critical angle
-    const float k = sqrtf(fmaxf(k2, 0.f));
+    const float k = fsqrt(fmaxf(k2, 0.f));
     const float rs = fdiv(n1 * c - n2 * k, n1 * c + n2 * k);
     const float rp = fdiv(n1 * k - n2 * c, n1 * k + n2 * c);
     I.k = k;
@@ -555,7 +562,7 @@ __device__ __forceinline__ void source_emit(const DevScene& S, const uint4 v, Ph
     float sp, cp;
     sincospif(2.f * u01(v.x), &sp, &cp);
     const float mu = 2.f * u01(v.y) - 1.f;
-    const float st = sqrtf(fmaxf(fmaf(-mu, mu, 1.f), 0.f));
+    const float st = fsqrt(fmaxf(fmaf(-mu, mu, 1.f), 0.f));
     p.dx = st * cp; p.dy = st * sp; p.dz = mu;
     const int t = (p.aux >> 16) & 0xff;
     const DevTable& T = S.tab[t];
