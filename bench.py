@@ -63,7 +63,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -125,11 +125,18 @@ def cpu_oracle_throughput(arrays, photons: int, threads: int) -> tuple:
     oracle = c_oracle.COracle(nat, nat.PackedScene(arrays))
     batches, _ = backend.pack_batches([arrays.light])
     spectra = [arrays.light.spectrum] if arrays.light.spectrum is not None else None
-    oracle.trace(batches[0], spectra=spectra, photon_count=2000, seed=1, threads=threads)  # warm
+    if photons <= 0:
+        # bounded sample: calibrate, then size the run for about 10 s of CPU work
+        t0 = time.perf_counter()
+        oracle.trace(batches[0], spectra=spectra, photon_count=200_000, seed=1, threads=threads)
+        rate = 200_000 / max(time.perf_counter() - t0, 1e-6)
+        photons = int(min(max(rate * 10.0, 1_000_000), 200_000_000))
+    else:
+        oracle.trace(batches[0], spectra=spectra, photon_count=2000, seed=1, threads=threads)  # warm
     t0 = time.perf_counter()
     out = oracle.trace(batches[0], spectra=spectra, photon_count=photons, seed=2, threads=threads)
     dt = time.perf_counter() - t0
-    return photons / dt, dt, out
+    return photons / dt, dt, photons
 
 
 def run_reference(args) -> None:
@@ -138,9 +145,13 @@ def run_reference(args) -> None:
         return
     arrays = workload_scene()
     cores = os.cpu_count() or 1
+    # each step is a bounded sample of the workload; the whole run is sized to end within a few minutes
+    _, _, calibrated = cpu_oracle_throughput(arrays, args.cpu_photons, cores)
     sample = args.cpu_photons
+    if args.cpu_photons <= 0:   # ~10 s of CPU work per step, the whole run capped near one minute
+        sample = max(int(calibrated * min(1.0, 6.0 / max(args.steps + args.warmup, 1))), 200_000)
     for _ in range(max(args.warmup, 0)):
-        cpu_oracle_throughput(arrays, max(sample // 10, 1000), cores)
+        cpu_oracle_throughput(arrays, sample, cores)
     total, elapsed = 0, 0.0
     for _ in range(args.steps):
         rate, dt, _ = cpu_oracle_throughput(arrays, sample, cores)
@@ -288,9 +299,9 @@ def run_cuda(args) -> None:
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            rate, dt, _ = cpu_oracle_throughput(arrays, args.cpu_photons, cores)
+            rate, dt, n_cpu = cpu_oracle_throughput(arrays, args.cpu_photons, cores)
             line["cpu_baseline"] = {"value": rate, "unit": "photons/s", "cores": cores, "kind": "port",
-                                    "sample": f"{args.cpu_photons} photons of the same workload in {dt:.1f} s "
+                                    "sample": f"{n_cpu} photons of the same workload in {dt:.1f} s "
                                               f"(C float64 oracle, OpenMP {cores} threads)"}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -306,7 +317,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=("cuda", "reference"), default="cuda")
     ap.add_argument("--batches", type=int, default=64, help="batches (time points) per GPU per step")
     ap.add_argument("--photons", type=int, default=1_000_000, help="photons per batch")
-    ap.add_argument("--cpu-photons", type=int, default=2_000_000, help="photons of the bounded CPU sample")
+    ap.add_argument("--cpu-photons", type=int, default=0, help="photons of the bounded CPU sample (0: calibrate to ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -35,7 +35,8 @@ def init_process_group(backend: Optional[str] = None):
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        kwargs = {"device_id": torch.device(f"cuda:{local_rank}")} if backend == "nccl" else {}
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
     return rank, local_rank, world
 
 
