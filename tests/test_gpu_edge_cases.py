@@ -1,0 +1,132 @@
+"""Edge cases of the hot path on the GPU: empty and ragged inputs, many tiny batches, 64-bit photon indices, scene
+variants of the LSC-PM family (no capillaries, no inner cylinder, dense channel grid) against the generic oracle, and
+scenes outside the family (rejected loudly, never traced as something else)."""
+import numpy as np
+import pytest
+
+from helpers import assert_counts_agree, grouped, standard_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_row(arrays, native, n, seed=5):
+    import c_oracle
+    from lscpm_b200 import backend
+
+    oracle = c_oracle.COracle(native, native.PackedScene(arrays))
+    batches, _ = backend.pack_batches([arrays.light])
+    spectra = [arrays.light.spectrum] if arrays.light.spectrum is not None else None
+    return oracle.trace(batches[0], spectra=spectra, photon_count=n, seed=seed)
+
+
+def test_zero_and_tiny_photon_counts(built_library):
+    from lscpm_b200 import backend, flatten
+    from miniplant.simulation_runner import run_direct_simulation
+
+    arrays = flatten.flatten_scene(standard_scene())
+    for n in (1, 2, 31, 33, 120):
+        row = backend.trace_lights(arrays, [arrays.light], n, seed=n, device=0)[0]
+        assert row[:-2].sum() == n
+    assert run_direct_simulation(num_photons=0) == 0.0
+    assert 0.0 <= run_direct_simulation(num_photons=1, seed=3) <= 1.0
+
+
+def test_many_tiny_batches_like_the_yearly_driver(native, built_library):
+    """16 k time points x 120 photons (reference full_simulation.py:53): every row sums to 120; pooled tallies follow
+    the oracle."""
+    from lscpm_b200 import backend, flatten
+
+    arrays = flatten.flatten_scene(standard_scene(tilt=40, elevation=50, wavelength=555.0))
+    nb, ppb = 4000, 120
+    rows = backend.trace_lights(arrays, [arrays.light] * nb, ppb, seed=8, device=0)
+    names = arrays.bin_names()
+    assert rows.shape == (nb, len(names) + 2)
+    assert np.all(rows[:, :len(names)].sum(axis=1) == ppb)
+    assert len({tuple(r) for r in rows[:50]}) > 40            # distinct batch ids -> distinct random streams
+    pooled = rows.sum(axis=0)
+    ref = _oracle_row(arrays, native, nb * ppb)
+    g, r = grouped(names, pooled[:len(names)]), grouped(names, ref[:len(names)])
+    keys = sorted(set(g) | set(r))
+    assert_counts_agree(keys, [g.get(k, 0) for k in keys], [r.get(k, 0) for k in keys], label="tiny batches pooled")
+
+
+def test_photon_indices_beyond_32_bits(built_library):
+    from lscpm_b200 import backend, flatten
+
+    arrays = flatten.flatten_scene(standard_scene())
+    base = (1 << 33) + 12345
+    whole = backend.trace_lights(arrays, [arrays.light], 6000, seed=4, device=0, photon_begin=base)
+    parts = sum(backend.trace_lights(arrays, [arrays.light], 2000, seed=4, device=0, photon_begin=base + 2000 * i) for i in range(3))
+    assert np.array_equal(whole, parts)
+    low = backend.trace_lights(arrays, [arrays.light], 6000, seed=4, device=0, photon_begin=12345)
+    assert not np.array_equal(whole, low)                      # the high counter word matters
+
+
+def _custom_scene(n_channels, pitch, with_inner=True, r_outer=0.0015875, r_inner=0.00079375, tilt=0.0, wavelength=585.0,
+                  plate=(0.47, 0.47, 0.008)):
+    """A member of the LSC-PM family built with the same object API the reference uses."""
+    from lscpm_b200.compat import pvtrace_api as pv
+    from lscpm_b200.miniplant import scene_creator as sc
+    from lscpm_b200.miniplant.utils import LightPosition, VectorInverter
+    from lscpm_b200.workloads import ConstantWavelength
+
+    spectra = sc._spectra()
+    world = pv.Node(name="World (air)", geometry=pv.Sphere(radius=10.0, material=pv.Material(refractive_index=1.0)))
+    sun = pv.spherical_to_cart(np.deg2rad(20.0), np.deg2rad(15.0))
+    light = pv.Node(name="Solar Light", light=pv.Light(wavelength=ConstantWavelength(wavelength), direction=VectorInverter(sun),
+                                                       position=LightPosition(tilt_angle=tilt)), parent=world)
+    light.translate(sun)
+    dye = pv.Luminophore(coefficient=np.array(spectra["lr305_abs"]), emission=np.array(spectra["lr305_ems"]),
+                         quantum_yield=0.95, phase_function=pv.isotropic)
+    reactor = pv.Node(name="plate", geometry=pv.Box(size=plate, material=pv.Material(
+        refractive_index=1.48, components=[pv.Absorber(coefficient=0.1), dye])), parent=world)
+    mix = pv.Reactor(np.array(spectra["mb_abs"]))
+    tube_geom = pv.Cylinder(length=plate[1], radius=r_outer, material=pv.Material(refractive_index=1.34, components=[pv.Absorber(coefficient=0.1)]))
+    x0 = -0.5 * pitch * (n_channels - 1)
+    for k in range(n_channels):
+        tube = pv.Node(name=f"tube_{k}", geometry=tube_geom, parent=reactor)
+        if with_inner:
+            pv.Node(name=f"mix_{k}", geometry=pv.Cylinder(length=plate[1], radius=r_inner, material=pv.Material(
+                refractive_index=1.344, components=[mix])), parent=tube)
+        tube.rotate(np.radians(90), (1, 0, 0))
+        tube.translate((x0 + pitch * k, 0, 0))
+    reactor.rotate(np.radians(tilt), (0, 1, 0))
+    reactor.translate((-np.sin(np.deg2rad(tilt)) * 0.5 * plate[2], 0, -np.cos(np.deg2rad(tilt)) * 0.5 * plate[2]))
+    return pv.Scene(world)
+
+
+@pytest.mark.parametrize("label,kw", [
+    ("bare_plate", dict(n_channels=0, pitch=0.03)),
+    ("tubes_without_mixture", dict(n_channels=16, pitch=0.03, with_inner=False)),
+    ("single_capillary", dict(n_channels=1, pitch=0.03)),
+    ("dense_grid_46_channels", dict(n_channels=46, pitch=0.01, wavelength=555.0)),
+    ("fat_tubes_tilted", dict(n_channels=8, pitch=0.05, r_outer=0.003, r_inner=0.002, tilt=25.0)),
+])
+def test_scene_family_variants_match_oracle(label, kw, native, built_library):
+    from lscpm_b200 import backend, flatten
+
+    arrays = flatten.flatten_scene(_custom_scene(**kw))
+    n = 200_000
+    row = backend.trace_lights(arrays, [arrays.light], n, seed=21, device=0)[0]
+    ref = _oracle_row(arrays, native, n)
+    names = arrays.bin_names()
+    assert row[:len(names)].sum() == n
+    assert_counts_agree(names, row[:len(names)], ref[:len(names)], label=label)
+    assert abs(row[len(names)] - ref[len(names)]) / ref[len(names)] < 0.02
+
+
+def test_scenes_outside_the_family_are_rejected(native, built_library):
+    from lscpm_b200 import backend, flatten
+    from miniplant.simulation_runner import run_direct_simulation
+
+    with pytest.raises(native.LscpmError) as err:
+        run_direct_simulation(num_photons=10, add_bottom_PV=True)
+    assert err.value.code == -2 and "not supported" in str(err.value)
+    # capillaries shorter than the plate: caps inside the plate are a different topology
+    from lscpm_b200.compat import pvtrace_api as pv
+
+    scene = _custom_scene(n_channels=2, pitch=0.03)
+    for node in scene.root.children[1].children:
+        node.geometry = pv.Cylinder(length=0.4, radius=0.0015875, material=node.geometry.material)
+    with pytest.raises(native.LscpmError):
+        backend.trace_lights(flatten.flatten_scene(scene), [flatten.flatten_light(scene)], 10, seed=1, device=0)
