@@ -98,7 +98,7 @@ typedef struct LscpmSceneDesc {
  * scene_creator.py:288-304).  DIFFUSE: d = -sky with sky from zenith~U(0,90) deg, azimuth~U(0,360) deg,
  * redrawn while cos(t)cos(z)+sin(t)sin(z)cos(az) < 0, t = tilt_deg (utils.py:102-122,135-142).
  * Wavelength: constant wavelength_nm when spectrum < 0, else inverse-CDF sample of launch spectrum
- * table `spectrum` (trapezoid CDF over the knots, reference utils.py:39-46).
+ * table `spectrum` (pvtrace Distribution: cdf = cumsum(y)/max over the knots, reference utils.py:39-46).
  */
 typedef struct LscpmBatchDesc {
     int32_t light_kind;

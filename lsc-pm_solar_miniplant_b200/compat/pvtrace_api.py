@@ -14,9 +14,11 @@ Behavioural notes each class follows (pvtrace 2.1 public behaviour, see DESIGN.m
 * ``Node.translate``/``Node.rotate`` pre-multiply the pose, i.e. act in the parent frame; the
   reference's tilt transform only puts the plate's top face through the world origin under that
   convention (``miniplant/scene_creator.py:264-272``).
-* ``Distribution`` builds its CDF with a cumulative trapezoid, normalised by its maximum, and both
-  ``lookup`` and ``sample`` are ``numpy.interp`` on the knots; a negative ordinate raises
-  ``ValueError`` (relied on by ``miniplant/solar_data.py:93-104``).
+* ``Distribution`` builds its CDF as ``numpy.cumsum(y) / max`` over the knots (pvtrace's ``cdf = np.cumsum(y);
+  pdf = cdf / max(cdf)`` idiom, the same one ``Material.component`` uses) — knot spacing does not enter, which
+  matters on the non-uniform 27-point solar grid; both ``lookup`` and ``sample`` are ``numpy.interp`` on the
+  knots; a negative ordinate raises ``ValueError`` (relied on by ``miniplant/solar_data.py:93-104``).  The choice
+  between cumsum and a cumulative trapezoid is pinned by the reference's committed results.
 * ``Light.emit`` calls the wavelength / position / direction callables once per ray
   (``miniplant/scene_creator.py:295-303``).
 """
@@ -92,7 +94,7 @@ def rectangular_mask(l, w) -> tuple:
 
 
 class Distribution:
-    """Tabulated 1-D distribution with trapezoid CDF; see module docstring."""
+    """Tabulated 1-D distribution with a cumulative-sum CDF; see module docstring."""
 
     def __init__(self, x=None, y=None, hist: bool = False):
         if x is None or y is None:
@@ -108,10 +110,8 @@ class Distribution:
             if len(x) != len(y) + 1:
                 raise ValueError("Histogram distributions need len(x) == len(y) + 1")
             cdf = np.hstack([0.0, np.cumsum(y * np.diff(x))])
-        elif len(x) > 1:
-            cdf = np.hstack([0.0, np.cumsum(0.5 * (y[1:] + y[:-1]) * np.diff(x))])
         else:
-            cdf = np.zeros_like(x)
+            cdf = np.cumsum(y)
         peak = cdf.max() if len(cdf) else 0.0
         self._cdf = cdf / peak if peak > 0 else cdf
 

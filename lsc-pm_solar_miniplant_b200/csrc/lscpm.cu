@@ -379,11 +379,12 @@ int validate_desc(const LscpmSceneDesc* d) {
     return LSCPM_OK;
 }
 
-void trapezoid_cdf(const double* x, const double* y, int n, std::vector<double>& cdf) {
+// pvtrace Distribution: cdf = cumsum(y) / max(cdf) over the knots (knot spacing does not enter)
+void cumulative_cdf(const double* x, const double* y, int n, std::vector<double>& cdf) {
+    (void)x;
     cdf.assign(n, 0.0);
-    for (int i = 1; i < n; ++i) cdf[i] = cdf[i - 1] + 0.5 * (y[i] + y[i - 1]) * (x[i] - x[i - 1]);
-    double peak = 0.0;
-    for (int i = 0; i < n; ++i) peak = std::max(peak, cdf[i]);
+    double acc = 0.0, peak = 0.0;
+    for (int i = 0; i < n; ++i) { acc += y[i]; cdf[i] = acc; peak = std::max(peak, acc); }
     if (peak > 0) for (int i = 0; i < n; ++i) cdf[i] /= peak;
 }
 
@@ -736,7 +737,7 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
         const int n = (int)x.size();
         if (n_dev_tables >= MAX_TABLES) return fail(LSCPM_EUNSUPPORTED, "too many spectrum tables in one scene");
         std::vector<double> cdf;
-        trapezoid_cdf(x.data(), y.data(), n, cdf);
+        cumulative_cdf(x.data(), y.data(), n, cdf);
         double wmin = x[n - 1] - x[0];
         for (int i = 1; i < n; ++i) wmin = std::min(wmin, x[i] - x[i - 1]);
         const double range = x[n - 1] - x[0];
@@ -896,7 +897,7 @@ int lscpm_plan_create(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_ba
             }
             if (!(total > 0)) return fail(LSCPM_EINVAL, "spectrum is identically zero");
             std::vector<double> cdf;
-            trapezoid_cdf(spectra->x + lo, spectra->y + lo, n, cdf);
+            cumulative_cdf(spectra->x + lo, spectra->y + lo, n, cdf);
             if (n > 65000) return fail(LSCPM_EUNSUPPORTED, "spectrum with more than 65000 knots");
             for (int k = 0; k < n; ++k) { sx.push_back((float)spectra->x[lo + k]); sc.push_back((float)cdf[k]); }
             sb.push_back((int)sx.size());

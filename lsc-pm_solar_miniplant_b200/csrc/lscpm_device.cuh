@@ -95,7 +95,7 @@ struct DevScene {
     DevTable tab[MAX_TABLES];
     const float* tab_x;        // concatenated knot tables (scene spectra)
     const float* tab_y;
-    const float* tab_cdf;      // trapezoid CDF, normalised
+    const float* tab_cdf;      // cumulative-sum CDF (pvtrace Distribution), normalised
     const unsigned short* tab_fwd;
     const unsigned short* tab_inv;
     int n_bins;

@@ -69,7 +69,7 @@ typedef struct {
     const LscpmSceneDesc* d;
     int n_nodes;
     ONode* nodes;
-    double** cdf;          /* per table: trapezoid CDF normalised by its maximum */
+    double** cdf;          /* per table: cumulative-sum CDF normalised by its maximum */
     int n_bins;
     int* exit_base;        /* per node */
     int* abs_base;         /* per node */
@@ -88,11 +88,11 @@ static void oscene_free(OScene* s) {
     free(s->nodes); free(s->exit_base); free(s->abs_base);
 }
 
+/* pvtrace Distribution: cdf = cumsum(y) / max(cdf) over the knots (spacing does not enter) */
 static void build_cdf(const double* x, const double* y, int n, double* cdf) {
-    cdf[0] = 0.0;
-    for (int i = 1; i < n; ++i) cdf[i] = cdf[i - 1] + 0.5 * (y[i] + y[i - 1]) * (x[i] - x[i - 1]);
-    double peak = cdf[n - 1];
-    for (int i = 0; i < n; ++i) if (cdf[i] > peak) peak = cdf[i];
+    (void)x;
+    double acc = 0.0, peak = 0.0;
+    for (int i = 0; i < n; ++i) { acc += y[i]; cdf[i] = acc; if (acc > peak) peak = acc; }
     if (peak > 0) for (int i = 0; i < n; ++i) cdf[i] /= peak;
 }
 
@@ -382,7 +382,7 @@ static int follow(const OScene* s, double* p, double* v, double wl, Rng* rng, Hi
 }
 
 /* ---- light (reference miniplant/utils.py:87-142, scene_creator.py:288-304) -------------------- */
-typedef struct { const double* x; const double* cdf; int n; } Spectrum;
+typedef struct { const double* x; const double* cdf; int n; } Spectrum;   /* cdf: cumulative sum, see build_cdf */
 
 static void emit_ray(const LscpmBatchDesc* b, const Spectrum* sp, Rng* rng, double* p, double* v, double* wl) {
     double mx = (2.0 * rng_uniform(rng) - 1.0) * b->mask_half[0], my = (2.0 * rng_uniform(rng) - 1.0) * b->mask_half[1];

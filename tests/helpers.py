@@ -10,8 +10,7 @@ from lscpm_b200.workloads import (AM15_LIKE_W, SPECTRL2_SLICE_NM, ConstantWavele
                                   am15_like_photon_spectrum, standard_scene)
 
 
-def assert_counts_agree(names, a, b, z=Z_999, label=""):
-    """Two independent multinomial samples of equal size: every bin's difference inside the 99.9 % band."""
+def bins_outside_band(names, a, b, z=Z_999):
     a = np.asarray(a, dtype=np.int64)
     b = np.asarray(b, dtype=np.int64)
     assert a.sum() == b.sum(), (a.sum(), b.sum())
@@ -22,6 +21,19 @@ def assert_counts_agree(names, a, b, z=Z_999, label=""):
         allowed = z * np.sqrt(max(ca + cb, 4))
         if abs(int(ca) - int(cb)) > allowed:
             bad.append((name, int(ca), int(cb), round(float(allowed), 1)))
+    return bad
+
+
+def assert_counts_agree(names, a, b, z=Z_999, label="", resample=None):
+    """Two independent multinomial samples of equal size: every bin's difference inside the 99.9 % band.
+
+    With ~100 bins a 99.9 % band is left by chance in roughly one run out of ten, so a bin that falls outside may be
+    re-drawn ONCE with an independent seed (``resample() -> counts``): a real discrepancy fails both draws, a
+    fluctuation fails both with probability ~1e-6."""
+    bad = bins_outside_band(names, a, b, z)
+    if bad and resample is not None:
+        again = {name for name, *_ in bins_outside_band(names, resample(), b, z)}
+        bad = [entry for entry in bad if entry[0] in again]
     assert not bad, f"{label}: bins outside the 99.9% band: {bad}"
 
 
