@@ -28,3 +28,16 @@ exp = pd.read_csv("/root/reference/miniplant/experimental_comparison/experimenta
 exp.index.name = "timestamp"
 exp.to_csv(os.path.join(HERE, "reference_experimental_conditions.csv"))
 print(len(out), "ephemeris rows;", len(exp), "experimental rows")
+
+# yearly column means of the committed full-year results (statistical anchors for the driver tests)
+import glob
+import json
+
+means = {}
+for path in sorted(glob.glob(os.path.join(REF, "*", "*.csv"))):
+    frame = pd.read_csv(path, index_col=0)
+    means[os.path.basename(path)] = {"rows": len(frame), "simulation_direct_mean": float(frame.simulation_direct.mean()),
+                                     "simulation_diffuse_mean": float(frame.simulation_diffuse.mean())}
+with open(os.path.join(HERE, "reference_yearly_means.json"), "w") as fh:
+    json.dump({"source": "column means of the result CSVs committed under miniplant/full_simulation_results/ in the reference "
+                         "(120 photons per time point)", "files": means}, fh, indent=1, ensure_ascii=False)

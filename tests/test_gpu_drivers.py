@@ -65,3 +65,32 @@ def test_tilt_sweep_driver(tmp_path, built_library):
         totals[tilt] = res["simulation_direct"].mean()
     assert all(0.12 < v < 0.30 for v in totals.values())
     assert totals[0] != totals[40] != totals[80]
+
+
+@pytest.mark.parametrize("site_name,tilt,dye,csv", [
+    ("Eindhoven", 0, True, "Eindhoven_0deg_results.csv"),
+    ("Townsville", -10, True, "Townsville_-10deg_results.csv"),
+    ("North Cape", 50, True, "North Cape_50deg_results.csv"),
+    ("Eindhoven", 40, False, "Eindhoven_40deg_results_no_dye.csv"),
+    ("North Cape", 50, False, "North Cape_50deg_results_no_dye.csv"),
+])
+def test_yearly_means_against_the_reference_results(site_name, tilt, dye, csv, tmp_path, built_library):
+    """The whole chain (solar position, spectra stand-in, scene, tracing) against the full-year results the reference
+    committed: same number of time points, yearly mean reacted fractions within 1.5 % (dye) / 1 % (no dye) relative.
+    The reference's means carry +-0.0004 of Monte-Carlo noise (120 photons x ~8000 points)."""
+    import json
+
+    from miniplant.full_simulation import yearlong_simulation
+    from miniplant.locations import LOCATIONS
+    from miniplant.solar_data import solar_data_for_place_and_time
+
+    with open(os.path.join(GOLDEN, "reference_yearly_means.json")) as fh:
+        ref = json.load(fh)["files"][csv]
+    site = next(s for s in LOCATIONS if s.name == site_name)
+    data = solar_data_for_place_and_time(site, tilt, 1800, write_csv=False)
+    assert abs(len(data) - ref["rows"]) <= 1
+    res = yearlong_simulation(tilt, site, num_photons_per_simulation=5000, include_dye=dye, target_file=tmp_path / "y.csv",
+                              solar_data=data, seed=9)
+    tol = 0.015 if dye else 0.01
+    assert abs(res["simulation_direct"].mean() / ref["simulation_direct_mean"] - 1) < tol
+    assert abs(res["simulation_diffuse"].mean() / ref["simulation_diffuse_mean"] - 1) < tol + 0.005
