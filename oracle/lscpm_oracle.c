@@ -3,12 +3,13 @@
  * the reference drives (miniplant/simulation_runner.py:38-66) through pvtrace 2.1
  * (fork cambiegroup/pvtrace@22c90761e2ee2a9b9193051f40ee553bd4f527f8, reference requirements.txt:43).
  *
- * PARITY PIN STATUS: parity unpinned against real pvtrace output (pvtrace is not vendored in
- * /root/reference and not installable offline).  This file is the fast twin of
+ * PARITY PIN STATUS: per-ray values are parity unpinned against real pvtrace output (pvtrace is not vendored in
+ * /root/reference and not installable offline); tallies are pinned statistically on the full-year results the
+ * reference committed (tests/test_solar_stage.py).  This file is the fast twin of
  * oracle/pvtrace_oracle.py — the same generic algorithm (every geometry node intersected in its own
  * local frame, stable distance sort, container = nearest node hit exactly once, Beer-Lambert free
  * path, Fresnel reflect/refract, kT-restricted re-emission), working on the flattened description of
- * include/lscpm.h instead of the scene graph.  tests/test_oracle_c_vs_python.py checks the two against
+ * include/lscpm.h instead of the scene graph.  tests/test_oracle_golden.py checks the two against
  * each other ray by ray; the Python twin is checked against the reference's own test bands and the
  * analytic known-answer vectors.
  *

@@ -133,3 +133,28 @@ def test_evaluate_tilt_angle_schema_and_skip(tmp_path):
     assert all(0.05 < v < 0.45 for v in written["simulation_direct"].iloc[[0, 2]])
     assert np.allclose(written["direct_reacted"], written["simulation_direct"] * 2.0)
     assert aos.RAYS_PER_SIMULATIONS == 100 and aos.INCLUDE_DYE is True
+
+
+def test_oracle_against_the_reference_yearly_results():
+    """Pins the ORACLE on reference output: the full-year result CSVs the reference committed (column means in
+    tests/golden/reference_yearly_means.json).  Every 16th time point of the Eindhoven 40 deg year, 1500 photons each,
+    traced by the C oracle; yearly mean reacted fractions within 2.5 % (sub-sampling the year costs ~1 %)."""
+    import json
+
+    from lscpm_b200 import lights
+    from miniplant.full_simulation import trace_time_points
+    from miniplant.locations import EINDHOVEN
+    from miniplant.solar_data import solar_data_for_place_and_time
+
+    with open(os.path.join(GOLDEN, "reference_yearly_means.json")) as fh:
+        ref = json.load(fh)["files"]
+    data = solar_data_for_place_and_time(EINDHOVEN, 40, 1800, write_csv=False)
+    assert len(data) == ref["Eindhoven_40deg_results.csv"]["rows"]
+    rows = data.iloc[3::16]
+    for dye, key in ((True, "Eindhoven_40deg_results.csv"), (False, "Eindhoven_40deg_results_no_dye.csv")):
+        direct = [lights.direct_light(40, r["apparent_elevation"], r["azimuth"], r["direct_spectrum"]) for _, r in rows.iterrows()]
+        diffuse = [lights.diffuse_light(40, r["diffuse_spectrum"]) for _, r in rows.iterrows()]
+        frac = trace_time_points(40, direct + diffuse, 1500, include_dye=dye, seed=4, tracer=_oracle_tracer)
+        n = len(rows)
+        assert abs(frac[:n].mean() / ref[key]["simulation_direct_mean"] - 1) < 0.025, (dye, frac[:n].mean())
+        assert abs(frac[n:].mean() / ref[key]["simulation_diffuse_mean"] - 1) < 0.025, (dye, frac[n:].mean())
