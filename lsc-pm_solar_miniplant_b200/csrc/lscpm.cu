@@ -92,7 +92,7 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
             const uint4 w = rng.next();
             StepOut so;
             status = photon_step(S, p, w, so);
-            if (counts_as_event(so.event)) ++n_events;
+            if (counts_as_event(so.event)) n_events += 1u + (unsigned)so.extra;
             if (so.event == EV_EMIT) n_events += 0x10000u;
         }
         // ---- tally the photons that ended -----------------------------------------------------------
@@ -189,7 +189,7 @@ struct ProbeIn { float xr, y, z, dx, dy, dz; int kc, medium; };
 struct ProbeOut {
     float t, n1, n2, R, cosi;
     float nx, ny, nz, rx, ry, rz, tx, ty, tz;
-    int kind, face, ch, container, adj, found;
+    int kind, face, ch, container, adj, found, ext;
 };
 
 __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* in, ProbeOut* out, long long n) {
@@ -202,7 +202,15 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
     p.xr = q.xr; p.y = q.y; p.z = q.z - S.zc; p.dx = q.dx; p.dy = q.dy; p.dz = q.dz; p.kc = q.kc; p.medium = q.medium;
     p.wl = 555.f; p.a_plate = p.a_outer = p.a_inner = 0.f; p.steps = 0; p.aux = 0;
     float nx, ny, nz;
-    if (q.medium == MED_AIR) {
+    int ext_node = 0;      // probe bookkeeping: outside box hit (i+1) or lending its index as adjacent (-(i+1))
+    if (q.medium == MED_AIR && S.n_ext > 0) {
+        float t; int node, face;
+        const bool inside = outside_hit(S, abs_x(S, p), p.y, q.z, p.dx, p.dy, p.dz, t, node, face);
+        if (node < 0) { out[i] = o; return; }
+        o.found = inside ? 2 : 1; o.t = t; o.kind = SURF_BOX; o.face = face; o.container = MED_AIR; o.adj = MED_PLATE; o.ch = node;
+        ext_node = node;
+        box_normal(face, nx, ny, nz);
+    } else if (q.medium == MED_AIR) {
         const Entry e = plate_entry(S.hx, S.hy, S.hz, abs_x(S, p), p.y, q.z, p.dx, p.dy, p.dz);
         if (e.t < 0.f) { out[i] = o; return; }
         o.found = 1; o.t = e.t; o.kind = SURF_BOX; o.face = e.face; o.container = MED_AIR; o.adj = MED_PLATE; o.ch = 0;
@@ -219,8 +227,13 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
         }
         const float xr = fmaf(p.dx, h.t, p.xr), yy = fmaf(p.dy, h.t, p.y), zz = fmaf(p.dz, h.t, p.z);
         o.found = 1; o.t = travelled + h.t; o.kind = h.kind; o.face = h.face; o.ch = p.kc; o.container = h.container; o.adj = h.adj;
-        if (h.kind == SURF_BOX || h.kind == SURF_CAP) box_normal(h.face, nx, ny, nz);
-        else {
+        if (h.kind == SURF_BOX || h.kind == SURF_CAP) {
+            box_normal(h.face, nx, ny, nz);
+            if (S.n_ext > 0) {
+                const int e = ext_ahead(S, axis_x(S, p.kc) + xr, yy, zz + S.zc, p.dx, p.dy, p.dz);
+                if (e >= 0) ext_node = -(e + 1);
+            }
+        } else {
             const float inv = rsqrtf(xr * xr + zz * zz);
             nx = xr * inv; ny = 0.f; nz = zz * inv;
             if (h.kind == SURF_OUTER && p.medium == MED_OUTER) {
@@ -230,6 +243,9 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
         }
     }
     o.n1 = S.med[o.container].n; o.n2 = S.med[o.adj].n;
+    if (ext_node > 0) o.n2 = S.ext[ext_node - 1].n;
+    if (ext_node < 0) o.n2 = S.ext[-ext_node - 1].n;
+    o.ext = ext_node;
     const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, o.n1, o.n2);
     o.R = I.R; o.cosi = I.cosi; o.nx = I.nx; o.ny = I.ny; o.nz = I.nz;
     Photon r = p; reflect_dir(r, I);
@@ -414,7 +430,7 @@ struct LscpmScene {
     double hx = 0, hy = 0, hz = 0, cx0 = 0, pitch = 1, zc = 0, r_o = 0, r_i = 0;
     int n_ch = 0, has_inner = 0;
     int node_plate = 1;
-    std::vector<int> node_outer, node_inner;
+    std::vector<int> node_outer, node_inner, node_ext;
     BinLayout layout;
     std::vector<std::string> bin_names;
     // device allocations
@@ -495,11 +511,39 @@ int lower_scene(const LscpmSceneDesc* d, LscpmScene* s) {
 
     struct Channel { double x, z; int outer, inner; };
     std::vector<Channel> ch;
+    std::vector<Vec3> ext_centres, ext_halves;
     for (int i = 1; i < d->n_nodes; ++i) {
         if (i == plate || d->node_parent[i] != plate) continue;
+        if (d->node_geom[i] == LSCPM_GEOM_BOX) {
+            // a box in the plate's frame but outside its volume: the reference's photovoltaic absorbers
+            // (miniplant/scene_creator.py:99-206).  Opaque (alpha * thickness >> 1), axis-aligned, touching allowed.
+            const double* B = d->node_pose + 16 * i;
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    double rel = 0;
+                    for (int k = 0; k < 3; ++k) rel += P[4 * k + r] * B[4 * k + c];
+                    if (std::fabs(rel - (r == c ? 1.0 : 0.0)) > tol) return fail(LSCPM_EUNSUPPORTED, "outside boxes must be axis-aligned with the plate");
+                }
+            const Vec3 c = mul_rt(P, {B[3] - P[3], B[7] - P[7], B[11] - P[11]});
+            const double h[3] = {0.5 * d->node_size[3 * i], 0.5 * d->node_size[3 * i + 1], 0.5 * d->node_size[3 * i + 2]};
+            const double cc[3] = {c.x, c.y, c.z}, ph[3] = {s->hx, s->hy, s->hz};
+            bool outside = false;
+            for (int ax = 0; ax < 3; ++ax) if (std::fabs(cc[ax]) - h[ax] >= ph[ax] - tol) outside = true;
+            if (!outside) return fail(LSCPM_EUNSUPPORTED, std::string("box '") + d->node_name[i] + "' overlaps the plate");
+            const int m = d->node_material[i];
+            const int c0 = d->mat_comp_begin[m], nc = d->mat_comp_begin[m + 1] - c0;
+            const double thinnest = 2 * std::min(h[0], std::min(h[1], h[2]));
+            if (nc != 1 || d->comp_kind[c0] != LSCPM_COMP_ABSORBER || d->comp_abs_table[c0] >= 0 || !(d->comp_coefficient[c0] * thinnest > 50.0))
+                return fail(LSCPM_EUNSUPPORTED, std::string("box '") + d->node_name[i] + "' must be one opaque constant absorber");
+            for (int j = i + 1; j < d->n_nodes; ++j)
+                if (d->node_parent[j] == i) return fail(LSCPM_EUNSUPPORTED, "outside boxes cannot have children");
+            if ((int)s->node_ext.size() >= MAX_EXT) return fail(LSCPM_EUNSUPPORTED, "more than 6 boxes outside the plate");
+            s->node_ext.push_back(i);
+            ext_centres.push_back(c); ext_halves.push_back({h[0], h[1], h[2]});
+            continue;
+        }
         if (d->node_geom[i] != LSCPM_GEOM_CYLINDER)
-            return fail(LSCPM_EUNSUPPORTED, std::string("node '") + d->node_name[i] +
-                        "' is not a capillary cylinder (photovoltaic boxes are not supported by this build)");
+            return fail(LSCPM_EUNSUPPORTED, std::string("node '") + d->node_name[i] + "' is neither a capillary cylinder nor a box outside the plate");
         const double* C = d->node_pose + 16 * i;
         const Vec3 axis = mul_rt(P, {C[2], C[6], C[10]});                      // capillary z axis in plate coordinates
         const Vec3 centre = mul_rt(P, {C[3] - P[3], C[7] - P[7], C[11] - P[11]});
@@ -526,6 +570,7 @@ int lower_scene(const LscpmSceneDesc* d, LscpmScene* s) {
         const int par = d->node_parent[i];
         if (i == plate || par == plate) continue;
         if (par <= 0 || d->node_parent[par] != plate) return fail(LSCPM_EUNSUPPORTED, "unexpected node outside the plate hierarchy");
+        if (d->node_geom[par] != LSCPM_GEOM_CYLINDER) return fail(LSCPM_EUNSUPPORTED, "only capillaries may contain another node");
     }
     std::sort(ch.begin(), ch.end(), [](const Channel& a, const Channel& b) { return a.x < b.x; });
     s->n_ch = (int)ch.size();
@@ -589,6 +634,17 @@ int lower_scene(const LscpmSceneDesc* d, LscpmScene* s) {
     D.n_bins = s->layout.n_bins;
     D.exit_base_plate = s->layout.exit_base[plate];
     D.abs_base_plate = s->layout.abs_base[plate];
+    D.med[MED_OUT] = D.med[MED_AIR];
+    D.n_ext = (int)s->node_ext.size();
+    for (int e = 0; e < D.n_ext; ++e) {
+        DevExtBox& b = D.ext[e];
+        const int node = s->node_ext[e];
+        b.cx = (float)ext_centres[e].x; b.cy = (float)ext_centres[e].y; b.cz = (float)ext_centres[e].z;
+        b.hx = (float)ext_halves[e].x; b.hy = (float)ext_halves[e].y; b.hz = (float)ext_halves[e].z;
+        b.n = (float)d->mat_refractive_index[d->node_material[node]];
+        b.abs_bin = s->layout.abs_base[node];
+        b.exit_base = s->layout.exit_base[node];
+    }
     s->bin_names.resize(D.n_bins);
     for (int b = 0; b < D.n_bins; ++b) s->bin_names[b] = bin_name(d, b);
     return LSCPM_OK;
@@ -1106,9 +1162,13 @@ int lscpm_probe(LscpmScene* s, int64_t n, const double* pos, const double* dir, 
         }
         // node bookkeeping of pvtrace's next_hit for this interface
         int h_node, c_node, a_node;
-        if (q.medium == MED_AIR) { h_node = s->node_plate; c_node = 0; a_node = s->node_plate; }
-        else if (o.kind == SURF_BOX) { h_node = c_node = s->node_plate; a_node = 0; }
-        else if (o.kind == SURF_CAP) { h_node = c_node = s->node_plate; a_node = s->node_outer[q.kc]; }
+        if (q.medium == MED_AIR) {
+            h_node = o.ext > 0 ? s->node_ext[o.ext - 1] : s->node_plate;
+            if (o.found == 2) { c_node = h_node; a_node = 0; }      // already inside that box (zero-distance entry dropped)
+            else { c_node = 0; a_node = h_node; }
+        }
+        else if (o.kind == SURF_BOX) { h_node = c_node = s->node_plate; a_node = o.ext < 0 ? s->node_ext[-o.ext - 1] : 0; }
+        else if (o.kind == SURF_CAP) { h_node = c_node = s->node_plate; a_node = o.ext < 0 ? s->node_ext[-o.ext - 1] : s->node_outer[q.kc]; }
         else if (o.kind == SURF_OUTER) {
             if (q.medium == MED_PLATE) { h_node = a_node = s->node_outer[o.ch]; c_node = s->node_plate; }
             else { h_node = c_node = s->node_outer[q.kc]; a_node = o.adj == MED_OUTER ? s->node_outer[o.ch] : s->node_plate; }
@@ -1203,7 +1263,9 @@ int lscpm_follow(LscpmScene* s, int64_t n, const double* pos, const double* dir,
             if (step_node) {
                 // node of the event: the surface's node for surface events, the container for absorption events
                 int node = -1;
-                if (st.event == EV_REFLECT || st.event == EV_TRANSMIT) {
+                if (st.medium == MED_AIR && !s->node_ext.empty() && st.event != EV_EXIT && st.event != EV_KILL) {
+                    node = st.ch == 0 ? s->node_plate : s->node_ext[st.ch - 1];
+                } else if (st.event == EV_REFLECT || st.event == EV_TRANSMIT) {
                     if (st.kind == SURF_BOX || st.kind == SURF_CAP) node = s->node_plate;
                     else if (st.kind == SURF_OUTER) node = s->node_outer[st.ch];
                     else if (st.kind == SURF_INNER) node = s->node_inner[st.ch];

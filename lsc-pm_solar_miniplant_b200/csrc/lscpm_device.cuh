@@ -39,7 +39,9 @@ namespace lscpm {
 
 constexpr int MAX_COMP = 4;
 constexpr int MAX_TABLES = 12;           // scene tables + one total-attenuation table per medium
-constexpr int MED_AIR = 0, MED_PLATE = 1, MED_OUTER = 2, MED_INNER = 3;
+constexpr int MED_AIR = 0, MED_PLATE = 1, MED_OUTER = 2, MED_INNER = 3, MED_OUT = 4;
+constexpr int MAX_EXT = 6;                // boxes outside the plate (the reference's photovoltaic absorbers)
+constexpr float EXT_TOL = 1e-6f;          // metres: "distance is zero" for faces shared between the plate and an outside box
 constexpr int COMP_ABSORBER = 0, COMP_LUMINOPHORE = 1, COMP_REACTOR = 2;
 constexpr int LIGHT_DIRECT = 0, LIGHT_DIFFUSE = 1;
 constexpr int EV_GENERATE = 0, EV_REFLECT = 1, EV_TRANSMIT = 2, EV_ABSORB = 3, EV_EMIT = 4, EV_EXIT = 5, EV_KILL = 6,
@@ -81,6 +83,15 @@ struct DevTable {
     int inv_begin;       // inverse guide table (INV_CDF_BUCKETS + 1 entries) in tab_inv, or -1
 };
 
+// Opaque box outside the plate, axis-aligned in the plate frame (reference miniplant/scene_creator.py:99-206: the bottom
+// PV under an air gap, four side PVs sharing a face with the plate edges; n = 3.4, alpha = 1e10 m^-1)
+struct DevExtBox {
+    float cx, cy, cz, hx, hy, hz;   // centre and half extents, plate-local absolute coordinates
+    float n;
+    int abs_bin;                    // absorb/<node>/0
+    int exit_base;                  // exit/<node>/<face>
+};
+
 // Lowered scene, passed to every kernel by value (constant bank).
 struct DevScene {
     float hx, hy, hz;          // plate half extents
@@ -91,7 +102,9 @@ struct DevScene {
     int has_caps;              // capillaries present
     float r_o, r_i, r_o2, r_i2;
     int has_inner;
-    DevMedium med[4];          // indexed by MED_*; med[MED_AIR] carries the world's refractive index only
+    DevMedium med[5];          // indexed by MED_*; med[MED_AIR] and med[MED_OUT] carry the world's refractive index only
+    int n_ext;                 // outside boxes (0 for the standard scene: none of the MED_OUT code runs then)
+    DevExtBox ext[MAX_EXT];
     DevTable tab[MAX_TABLES];
     const float* tab_x;        // concatenated knot tables (scene spectra)
     const float* tab_y;
@@ -129,7 +142,10 @@ struct Photon {
     int kc;
     int medium;
     int steps;                 // follow-loop iterations so far
-    int aux;                   // AIR: entry face | inside medium << 4.   bit 8: has emitted
+    int aux;                   // bits 0-2 entry face, 4-5 medium behind it (fresh photon); bit 8 has emitted; 16-23 emission
+                               // table of a pending re-emission.  Scenes with outside boxes also track, for the EXIT
+                               // classification: bits 9-10 surface events (saturating), bit 11 first one was a reflection
+                               // in air, bits 12-14 node of the last surface event in air (0 plate, i+1 box i), 24-26 its face
 };
 
 struct Hit {
@@ -512,6 +528,11 @@ struct WavelengthDraw {
 __device__ __forceinline__ int place_photon(const DevScene& S, Photon& p, float ox, float oy, float oz, bool anchored,
                                             float ax, float ay) {
     p.steps = 0;
+    if (S.n_ext > 0 && !(fabsf(ox) < S.hx && fabsf(oy) < S.hy && fabsf(oz) < S.hz)) {
+        // outside boxes may shadow the plate: travel through the air from the true origin
+        p.kc = 0; p.xr = ox - axis_x(S, 0); p.y = oy; p.z = oz - S.zc; p.aux = 0; p.medium = MED_OUT;
+        return -1;
+    }
     int face; float px, py, pz;
     if (anchored) { face = 5; px = ax; py = ay; pz = S.hz; }
     else {
@@ -560,7 +581,7 @@ __device__ __forceinline__ int source_fresh(const DevScene& S, const DevBatch& B
 // emission-specific half: isotropic direction, kT-restricted CDF window of the luminophore stored in p.aux
 __device__ __forceinline__ void source_emit(const DevScene& S, const uint4 v, Photon& p, WavelengthDraw& wd) {
     float sp, cp;
-    sincospif(2.f * u01(v.x), &sp, &cp);
+    __sincosf(fmaf(6.2831853071795865f, u01(v.x), -3.1415926535897932f), &sp, &cp);   // phi - pi in [-pi, pi): SFU accuracy ~1e-6
     const float mu = 2.f * u01(v.y) - 1.f;
     const float st = fsqrt(fmaxf(fmaf(-mu, mu, 1.f), 0.f));
     p.dx = st * cp; p.dy = st * sp; p.dz = mu;
@@ -579,6 +600,129 @@ __device__ __forceinline__ void source_finish(const DevScene& S, Photon& p, cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// scenes with boxes outside the plate (photovoltaic absorbers): the air around the plate becomes a medium with
+// geometry of its own.  All of this is out of line and only runs when S.n_ext > 0.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void slab_interval(float cx, float cy, float cz, float hx, float hy, float hz, float ox, float oy,
+                                              float oz, float dx, float dy, float dz, float& tmin, float& tmax, int& fmin) {
+    tmin = -LSCPM_INF; tmax = LSCPM_INF; fmin = 0;
+    const float c[3] = {cx, cy, cz}, h[3] = {hx, hy, hz}, o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        const float rel = o[ax] - c[ax];
+        if (d[ax] == 0.f) {
+            if (fabsf(rel) > h[ax]) { tmin = LSCPM_INF; tmax = -LSCPM_INF; }
+            continue;
+        }
+        float tlo = (-h[ax] - rel) / d[ax], thi = (h[ax] - rel) / d[ax];
+        int flo = 2 * ax;
+        if (tlo > thi) { const float tt = tlo; tlo = thi; thi = tt; flo = 2 * ax + 1; }
+        if (tlo > tmin) { tmin = tlo; fmin = flo; }
+        tmax = fminf(tmax, thi);
+    }
+}
+
+// first outside box met by the straight line from (ox,oy,oz) along d, a box starting at distance ~0 included
+// (pvtrace's `adjacent = intersections[1]` for a photon leaving the plate: ties sort the plate first)
+__device__ __noinline__ int ext_ahead(const DevScene& S, float ox, float oy, float oz, float dx, float dy, float dz) {
+    int best = -1; float tbest = LSCPM_INF;
+    for (int i = 0; i < S.n_ext; ++i) {
+        const DevExtBox& b = S.ext[i];
+        float tmin, tmax; int f;
+        slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, ox, oy, oz, dx, dy, dz, tmin, tmax, f);
+        if (tmin <= tmax && tmax > EXT_TOL && tmin > -EXT_TOL && tmin < tbest) { tbest = tmin; best = i; }
+    }
+    return best;
+}
+
+// Nearest surface for a ray in the air around the plate: node 0 = plate, i+1 = outside box i, -1 = none.
+// Returns true when the ray starts on (within EXT_TOL of) a face of box `node` heading inwards.
+__device__ __forceinline__ bool outside_hit(const DevScene& S, float x, float y, float z, float dx, float dy, float dz,
+                                            float& t_best, int& node, int& face) {
+    t_best = LSCPM_INF; node = -1; face = 0;
+    for (int i = 0; i < S.n_ext; ++i) {
+        const DevExtBox& b = S.ext[i];
+        float tmin, tmax; int f;
+        slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, x, y, z, dx, dy, dz, tmin, tmax, f);
+        if (!(tmin <= tmax) || tmax <= EXT_TOL) continue;
+        if (tmin <= EXT_TOL) { t_best = 0.f; node = i + 1; face = f; return true; }
+        if (tmin < t_best) { t_best = tmin; node = i + 1; face = f; }
+    }
+    float tmin, tmax; int f;
+    slab_interval(0.f, 0.f, 0.f, S.hx, S.hy, S.hz, x, y, z, dx, dy, dz, tmin, tmax, f);
+    if (tmin <= tmax && tmin > EXT_TOL && tmin < t_best) { t_best = tmin; node = 0; face = f; }
+    return false;
+}
+
+struct OutState { float x, y, z, dx, dy, dz; int aux, steps; };
+struct OutResult { float x, y, z, dx, dy, dz; int aux, steps, bin, event, node, face, extra; bool entered; };
+
+__device__ __forceinline__ int exit_bin(const DevScene& S, int aux) {
+    const int n_surface = (aux >> 9) & 3;
+    if (n_surface == 0) return BIN_MISS;
+    if (n_surface == 1 && (aux & (1 << 11)) && !(aux & 256)) return BIN_ENTRY_REFLECT;
+    const int node = (aux >> 12) & 7, face = (aux >> 24) & 7;
+    return (node == 0 ? S.exit_base_plate : S.ext[node - 1].exit_base) + face;
+}
+
+__device__ __forceinline__ int note_surface(int aux, bool air_reflection, int node, int face, bool record) {
+    const int n_surface = (aux >> 9) & 3;
+    if (n_surface == 0 && air_reflection) aux |= 1 << 11;
+    aux = (aux & ~(3 << 9)) | (min(n_surface + 1, 2) << 9);
+    if (record) aux = (aux & ~((7 << 12) | (7 << 24))) | (node << 12) | (face << 24);
+    return aux;
+}
+
+// One follow() iteration of a photon travelling in the air around the plate: next hit among the plate and the outside
+// boxes (container = world, adjacent = hit), Fresnel test; an outside box that is entered absorbs at once (alpha ~1e10).
+__device__ __noinline__ OutResult outside_step(const DevScene& S, OutState q, float u_surf) {
+    OutResult r;
+    r.x = q.x; r.y = q.y; r.z = q.z; r.dx = q.dx; r.dy = q.dy; r.dz = q.dz; r.aux = q.aux; r.steps = q.steps + 1;
+    r.bin = -1; r.event = EV_NONE; r.node = 0; r.face = 0; r.extra = 0; r.entered = false;
+    if (r.steps > MAXSTEPS) { r.event = EV_KILL; r.bin = BIN_KILL; return r; }
+    float t_best; int node, face;
+    if (outside_hit(S, q.x, q.y, q.z, q.dx, q.dy, q.dz, t_best, node, face)) {
+        // the photon sits on a face of box `node`, heading in: the zero-distance entry is dropped, it is inside the box
+        r.event = EV_ABSORB; r.node = node; r.bin = S.ext[node - 1].abs_bin;
+        return r;
+    }
+    if (node < 0) {   // nothing but the world sphere ahead
+        r.event = EV_EXIT;
+        r.bin = exit_bin(S, q.aux);
+        return r;
+    }
+    r.x = fmaf(q.dx, t_best, q.x); r.y = fmaf(q.dy, t_best, q.y); r.z = fmaf(q.dz, t_best, q.z);
+    float nx, ny, nz;
+    box_normal(face, nx, ny, nz);
+    const float n1 = S.med[MED_AIR].n, n2 = node == 0 ? S.med[MED_PLATE].n : S.ext[node - 1].n;
+    const Interface I = interface_eval(q.dx, q.dy, q.dz, nx, ny, nz, n1, n2);
+    Photon tmp; tmp.dx = q.dx; tmp.dy = q.dy; tmp.dz = q.dz;
+    r.node = node; r.face = face;
+    if (u_surf < I.R) {
+        reflect_dir(tmp, I);
+        r.dx = tmp.dx; r.dy = tmp.dy; r.dz = tmp.dz;
+        r.event = EV_REFLECT;
+        r.aux = note_surface(q.aux, true, node, face, true);
+        return r;
+    }
+    refract_dir(tmp, I);
+    r.dx = tmp.dx; r.dy = tmp.dy; r.dz = tmp.dz;
+    r.event = EV_TRANSMIT;
+    r.aux = note_surface(q.aux, false, node, face, false);
+    if (node == 0) {
+        // snap onto the plate face; the caller locates the medium behind it
+        if (face < 2) r.x = (face & 1) ? S.hx : -S.hx; else if (face < 4) r.y = (face & 1) ? S.hy : -S.hy; else r.z = (face & 1) ? S.hz : -S.hz;
+        r.entered = true;
+        return r;
+    }
+    // transmitted into an opaque box: absorbed within nanometres (a second follow() iteration: ABSORB)
+    if (r.steps + 1 > MAXSTEPS) { r.event = EV_KILL; r.bin = BIN_KILL; return r; }
+    r.steps += 1; r.extra = 1;
+    r.bin = S.ext[node - 1].abs_bin;
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
 // one iteration of follow() with the iteration's Philox draw `w` (x: free path, y: Fresnel / component pick,
 // z: quantum yield).  Returns -1 while the photon lives, STEP_EMIT when it was absorbed by a luminophore that
 // re-emits (the source block then gives it a new direction and wavelength), otherwise its tally bin.
@@ -591,9 +735,21 @@ struct StepOut {
     int ch;          // capillary index of the event
     int kind;        // surface kind for surface events
     int face;
+    int extra;       // additional interaction events folded into this iteration (photon absorbed by an outside box)
 };
 
 __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const uint4 w, StepOut& out) {
+    out.extra = 0;
+    if (S.n_ext > 0 && p.medium == MED_OUT) {
+        OutState q;
+        q.x = abs_x(S, p); q.y = p.y; q.z = p.z + S.zc; q.dx = p.dx; q.dy = p.dy; q.dz = p.dz; q.aux = p.aux; q.steps = p.steps;
+        const OutResult r = outside_step(S, q, u01(w.y));
+        p.dx = r.dx; p.dy = r.dy; p.dz = r.dz; p.aux = r.aux; p.steps = r.steps;
+        out.event = r.event; out.medium = MED_AIR; out.ch = r.node; out.kind = SURF_BOX; out.face = r.face; out.extra = r.extra;
+        if (r.entered) { p.y = r.y; locate_in_plate(S, p, r.x, r.z); }
+        else { p.kc = 0; p.xr = r.x - axis_x(S, 0); p.y = r.y; p.z = r.z - S.zc; }
+        return r.bin;
+    }
     Hit h = compute_hit(S, p);
     if (p.medium == MED_AIR) {
         h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false;
@@ -647,7 +803,14 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
         // leaving the tube wall: pvtrace's adjacent is whatever the straight continuation meets next
         if (h.maybe_sibling && sibling_ahead(S, p.kc, p.xr, p.y, p.z, p.dx, p.dy, p.dz) >= 0) h.adj = MED_OUTER;
     }
-    const float n1 = S.med[h.container].n, n2 = S.med[h.adj].n;
+    float n2 = S.med[h.adj].n;
+    const bool leaving = flat && p.medium != MED_AIR;
+    if (S.n_ext > 0 && leaving) {
+        // adjacent = second intersection along the ray: an outside box straight ahead (even across an air gap) lends its index
+        const int e = ext_ahead(S, abs_x(S, p), p.y, p.z + S.zc, p.dx, p.dy, p.dz);
+        if (e >= 0) n2 = S.ext[e].n;
+    }
+    const float n1 = S.med[h.container].n;
     const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, n1, n2);
     const bool reflected = u_surf < I.R;
     if (reflected) reflect_dir(p, I); else refract_dir(p, I);
@@ -657,8 +820,15 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
         p.medium = (p.aux >> 4) & 3;
         return -1;
     }
+    if (S.n_ext > 0) p.aux = note_surface(p.aux, false, 0, h.face, leaving && !reflected);
     if (reflected) return -1;
     if (flat) {
+        if (S.n_ext > 0) {   // the air around the plate has geometry: keep following
+            const float xa = abs_x(S, p);
+            p.kc = 0; p.xr = xa - axis_x(S, 0);
+            p.medium = MED_OUT;
+            return -1;
+        }
         // left the plate assembly: the next follow() iteration meets only the world sphere -> EXIT
         p.medium = MED_AIR;
         return (p.steps + 1 > MAXSTEPS) ? BIN_KILL : S.exit_base_plate + h.face;

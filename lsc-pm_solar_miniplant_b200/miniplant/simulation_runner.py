@@ -49,8 +49,25 @@ def _common_simulation_runner(
     result = simulate_scene(scene, num_photons, seed=seed, device=device)
     reacted_fraction = result.reacted_fraction
     logger.debug(f"*** SIMULATION ENDED *** (Efficiency was {reacted_fraction:.3f})")
+
+    # The reference asks next_hit(scene, last_ray) which node the final ray is in / heading to and counts the PV names
+    # (:45-53).  A final ray points at a PV node exactly when the photon was absorbed inside it (an absorbed photon's
+    # last ray sits inside the opaque box; every other terminal ray faces the plate, a capillary or nothing).
+    counts = result.nonzero()
+    bottomPV_count = sum(c for name, c in counts.items() if name.startswith("absorb/bottomPV/"))
+    sidePV_count = sum(c for name, c in counts.items()
+                       if name.split("/")[0] == "absorb" and name.split("/")[1] in ("sidePV1", "sidePV2", "sidePV3", "sidePV4"))
+    if bottomPV_count > 0:
+        logger.info(f"Bottom PV absorbed {bottomPV_count} photons (i.e. {bottomPV_count/num_photons * 100 :.2f} %) ")
+    if sidePV_count > 0:
+        logger.info(f"The side PV absorbed {sidePV_count} photons (i.e. {sidePV_count / num_photons * 100 :.2f} %) ")
     if return_tallies:
         return reacted_fraction, result
+    # same polymorphic return as the reference (:77-80); photon histories are not kept for a bulk launch — use
+    # photon_tracer.follow(scene, ray) for individual paths
+    if bottomPV_count > 0 or sidePV_count > 0:
+        photon_path = []
+        return reacted_fraction, scene, photon_path, bottomPV_count, sidePV_count
     return reacted_fraction
 
 

@@ -120,12 +120,17 @@ def test_scenes_outside_the_family_are_rejected(native, built_library):
     from lscpm_b200 import backend, flatten
     from miniplant.simulation_runner import run_direct_simulation
 
-    with pytest.raises(native.LscpmError) as err:
-        run_direct_simulation(num_photons=10, add_bottom_PV=True)
-    assert err.value.code == -2 and "not supported" in str(err.value)
-    # capillaries shorter than the plate: caps inside the plate are a different topology
     from lscpm_b200.compat import pvtrace_api as pv
 
+    # a box that overlaps the plate is not an "outside box"
+    scene = _custom_scene(n_channels=2, pitch=0.03)
+    plate = scene.root.children[1]
+    pv.Node(name="intruder", geometry=pv.Box(size=(0.1, 0.1, 0.004), material=pv.Material(
+        refractive_index=3.4, components=[pv.Absorber(coefficient=1e10)])), parent=plate)
+    with pytest.raises(native.LscpmError) as err:
+        backend.trace_lights(flatten.flatten_scene(scene), [flatten.flatten_light(scene)], 10, seed=1, device=0)
+    assert err.value.code == -2 and "overlaps" in str(err.value)
+    # capillaries shorter than the plate: caps inside the plate are a different topology
     scene = _custom_scene(n_channels=2, pitch=0.03)
     for node in scene.root.children[1].children:
         node.geometry = pv.Cylinder(length=0.4, radius=0.0015875, material=node.geometry.material)

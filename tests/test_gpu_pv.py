@@ -1,0 +1,90 @@
+"""Row f3: the photovoltaic variants (reference miniplant/scene_creator.py:99-206, simulation_runner.py:45-53,68-79):
+boxes outside the plate make the surrounding air a medium with geometry.  Tallies and per-ray interfaces against the
+generic oracle, and the reference's polymorphic 5-tuple return."""
+import numpy as np
+import pytest
+
+from helpers import assert_counts_agree, grouped, standard_scene
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "bottom": dict(tilt=40, elevation=50, wavelength=555.0, add_bottom_PV=True),
+    "side": dict(tilt=40, elevation=50, wavelength=555.0, add_side_PV=True),
+    "both_585": dict(tilt=0, elevation=90, wavelength=585.0, add_bottom_PV=True, add_side_PV=True),
+    "both_backlit": dict(tilt=40, elevation=20, azimuth=0, wavelength=555.0, add_bottom_PV=True, add_side_PV=True),
+    "both_no_dye": dict(tilt=10, elevation=60, wavelength=610.0, include_dye=False, add_bottom_PV=True, add_side_PV=True),
+}
+
+
+def _oracle(arrays, native):
+    import c_oracle
+
+    return c_oracle.COracle(native, native.PackedScene(arrays))
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_pv_tallies_match_oracle(case, native, built_library):
+    from lscpm_b200 import backend, flatten
+
+    arrays = flatten.flatten_scene(standard_scene(**CASES[case]))
+    n = 300_000
+    row = backend.trace_lights(arrays, [arrays.light], n, seed=3, device=0)[0]
+    batches, _ = backend.pack_batches([arrays.light])
+    ref = _oracle(arrays, native).trace(batches[0], photon_count=n, seed=4)
+    names = arrays.bin_names()
+    nb = len(names)
+    assert row[:nb].sum() == n and ref[:nb].sum() == n
+    assert_counts_agree(names, row[:nb], ref[:nb], label=case, resample=lambda: backend.trace_lights(
+        arrays, [arrays.light], n, seed=5, device=0)[0][:nb])
+    g, r = grouped(names, row[:nb]), grouped(names, ref[:nb])
+    keys = sorted(set(g) | set(r))
+    assert_counts_agree(keys, [g.get(k, 0) for k in keys], [r.get(k, 0) for k in keys], label=case + " pooled")
+    assert abs(row[nb] - ref[nb]) / ref[nb] < 0.01           # interaction events (the absorbing box counts two)
+    if "backlit" not in case:
+        assert sum(c for name, c in zip(names, row) if "PV" in name and name.startswith("absorb/")) > 0.05 * n
+
+
+def test_pv_probe_matches_oracle(native, built_library):
+    import pvtrace_oracle as po
+    from lscpm_b200 import backend, flatten
+
+    scene = standard_scene(tilt=0, elevation=90, wavelength=585.0, add_bottom_PV=True, add_side_PV=True)
+    arrays = flatten.flatten_scene(scene)
+    result = po.run(scene, 300, seed=2, keep_histories=True)
+    pos, direc = [], []
+    for history in result.histories:
+        for step in history[:-1]:
+            pos.append(step.position)
+            direc.append(step.direction)
+    pos = np.array(pos).astype(np.float32).astype(np.float64)
+    direc = np.array(direc).astype(np.float32).astype(np.float64)
+    direc /= np.linalg.norm(direc, axis=1, keepdims=True)
+    ref = _oracle(arrays, native).probe(pos, direc)
+    gpu = backend.probe_rays(arrays, pos, direc, device=0)
+    clear = ref["distance"] > 1e-5
+    same = (gpu["hit"] == ref["hit"]) & (gpu["container"] == ref["container"]) & (gpu["adjacent"] == ref["adjacent"])
+    assert np.mean(same[clear]) > 0.99
+    in_air_to_pv = clear & same & np.isin(ref["hit"], [i for i, name in enumerate(arrays.node_name) if "PV" in name])
+    assert in_air_to_pv.sum() > 20
+    lending = clear & same & (ref["hit"] == 1) & np.isin(ref["adjacent"], [i for i, name in enumerate(arrays.node_name) if "PV" in name])
+    assert lending.sum() > 20                                  # plate faces whose adjacent is a PV box across the gap
+    ok = clear & same & (ref["hit"] > 0)
+    rel = np.abs(gpu["distance"][ok] - ref["distance"][ok]) / ref["distance"][ok]
+    assert np.quantile(rel, 0.99) < 1e-5
+    r_err = np.abs(gpu["reflectivity"][ok] - ref["reflectivity"][ok])
+    assert np.quantile(r_err[ref["reflectivity"][ok] < 1.0], 0.99) < 1e-4
+
+
+def test_runner_returns_the_reference_tuple(built_library):
+    """reference simulation_runner.py:127-139: res[-2] = bottom PV count, res[-1] = side PV count."""
+    from miniplant.simulation_runner import run_direct_simulation
+
+    res = run_direct_simulation(tilt_angle=40, solar_elevation=50, solar_azimuth=180, add_bottom_PV=True, add_side_PV=True,
+                                num_photons=20_000, seed=1)
+    assert isinstance(res, tuple) and len(res) == 5
+    fraction, scene, photon_path, bottom, side = res
+    assert 0.08 < fraction < 0.18 and 0.35 * 20_000 < bottom < 0.46 * 20_000 and 0.05 * 20_000 < side < 0.11 * 20_000
+    assert hasattr(scene, "light_nodes") and photon_path == []
+    plain = run_direct_simulation(tilt_angle=40, solar_elevation=50, solar_azimuth=180, num_photons=2000, seed=1)
+    assert isinstance(plain, float)
