@@ -1173,7 +1173,7 @@ int lscpm_probe(LscpmScene* s, int64_t n, const double* pos, const double* dir, 
             if (q.medium == MED_PLATE) { h_node = a_node = s->node_outer[o.ch]; c_node = s->node_plate; }
             else { h_node = c_node = s->node_outer[q.kc]; a_node = o.adj == MED_OUTER ? s->node_outer[o.ch] : s->node_plate; }
         } else {
-            if (q.medium == MED_OUTER) { h_node = a_node = s->node_inner[q.kc]; c_node = s->node_outer[q.kc]; }
+            if (q.medium == MED_OUTER) { h_node = a_node = s->node_inner[q.kc]; c_node = o.container == MED_PLATE ? s->node_plate : s->node_outer[q.kc]; }
             else { h_node = c_node = s->node_inner[q.kc]; a_node = o.adj == MED_PLATE ? s->node_plate : s->node_outer[q.kc]; }
         }
         hit[i] = h_node; container[i] = c_node; adjacent[i] = a_node;

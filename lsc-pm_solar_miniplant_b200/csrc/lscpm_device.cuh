@@ -16,8 +16,10 @@
 // including the literal consequences of pvtrace's adjacency rule (DESIGN.md "literal quirks"):
 //   * leaving a tube wall with a sibling capillary ahead takes n2 from the sibling (adjacent = intersections[1]);
 //   * leaving the inner cylinder when the straight continuation reaches a cap first takes n2 from the plate;
-//   * a segment that ends on a cap (coincident with the plate's +-y face; ties resolve in scene-graph order,
-//     plate first) is traced with the plate as container: plate material for absorption, n1 = plate, n2 = tube.
+//   * the capillary caps coincide with the plate's +-y faces; ties resolve in scene-graph order, plate first.  A photon
+//     in a tube wall whose straight line leaves the tube through the cap therefore has the PLATE as container (the
+//     nearest node hit exactly once): plate material for absorption and n1 = plate, whether the segment ends on the
+//     cap (n2 = tube) or on the inner cylinder first (n2 = mixture); likewise a mixture segment that ends on the cap.
 //
 // Divergence control (what the ncu profile of the first version asked for):
 //   * ONE code path computes every candidate distance (three slabs, near/far roots of both cylinders about
@@ -194,9 +196,17 @@ __device__ __forceinline__ float one_minus_u01(uint32_t x) { return (float)(((~x
 
 // single-instruction SFU approximations (MUFU.RCP / MUFU.SQRT, ~1 ulp): the geometry is statistical, and the
 // per-ray parity test (1e-5 relative) passes with them
+#ifdef LSCPM_PRECISE   // diagnostic build: IEEE division / square root / logarithm
+__device__ __forceinline__ float frcp(float x) { return 1.f / x; }
+__device__ __forceinline__ float fsqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
+__device__ __forceinline__ float flog(float x) { return logf(x); }
+#else
 __device__ __forceinline__ float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fsqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fdiv(float a, float b) { return a * frcp(b); }
+__device__ __forceinline__ float flog(float x) { return __logf(x); }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // table lookups with numpy.interp semantics (clamped; segment = last j with xp[j] <= v)
@@ -347,11 +357,15 @@ __device__ __forceinline__ Hit compute_hit(const DevScene& S, const Photon& p) {
     if (o_near < t_pl) { t_pl = o_near; k_pl = SURF_OUTER; f_pl = 0; adj_pl = MED_OUTER; }
     // OUTER: inner cylinder, else cap (coincides with the plate face: plate sorts first and becomes container and
     // hit node), else the tube's own outer surface (adjacent provisional: sibling search may upgrade it)
+    // Container: whenever the straight line leaves the tube through its CAP (ty <= o_far) the tube's only remaining
+    // intersection ties with the plate face, the plate sorts first and is the nearest node hit exactly once — also
+    // when the inner cylinder is hit before the cap (then n1 is the plate's index at the inner surface).
     const bool ou_inner = i_near < o_far && i_near < ty;
-    const bool ou_cap = !ou_inner && ty <= o_far;
+    const bool ou_exit_cap = ty <= o_far;
+    const bool ou_cap = !ou_inner && ou_exit_cap;
     const float t_ou = ou_inner ? i_near : (ou_cap ? ty : o_far);
     const int k_ou = ou_inner ? SURF_INNER : (ou_cap ? SURF_CAP : SURF_OUTER);
-    const int c_ou = ou_cap ? MED_PLATE : MED_OUTER;
+    const int c_ou = ou_exit_cap ? MED_PLATE : MED_OUTER;
     const int adj_ou = ou_inner ? MED_INNER : (ou_cap ? MED_OUTER : MED_PLATE);
     // INNER: cap, else the inner surface with adjacent = second intersection (tube wall, unless the cap comes first)
     const bool in_cap = ty <= i_far;
@@ -758,7 +772,7 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
     if (h.kind != SURF_CELL && ++p.steps > MAXSTEPS) { out.event = EV_KILL; return BIN_KILL; }
     const float alpha = h.container == MED_PLATE ? p.a_plate
                       : (h.container == MED_OUTER ? p.a_outer : (h.container == MED_INNER ? p.a_inner : 0.f));
-    const float depth = alpha <= ALPHA_ZERO ? LSCPM_INF : fdiv(-__logf(one_minus_u01(w.x)), alpha);
+    const float depth = alpha <= ALPHA_ZERO ? LSCPM_INF : fdiv(-flog(one_minus_u01(w.x)), alpha);
     const float u_surf = u01(w.y);
     out.medium = h.container; out.ch = p.kc; out.kind = h.kind; out.face = h.face;
     const bool absorbed = depth < h.t;

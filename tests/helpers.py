@@ -53,3 +53,19 @@ def grouped(names, counts) -> dict:
             key = name
         groups[key] = groups.get(key, 0) + int(c)
     return groups
+
+
+def assert_tallies_agree(names, a, b, label="", resample=None, z=Z_999):
+    """Per-bin AND pooled-family agreement of two tally rows with the single re-draw rule of assert_counts_agree."""
+    def failing(row):
+        bad = {("bin", e[0]): e for e in bins_outside_band(names, row, b, z)}
+        g, r = grouped(names, row), grouped(names, b)
+        keys = sorted(set(g) | set(r))
+        bad.update({("family", e[0]): e for e in bins_outside_band(keys, [g.get(k, 0) for k in keys], [r.get(k, 0) for k in keys], z)})
+        return bad
+
+    bad = failing(np.asarray(a, dtype=np.int64))
+    if bad and resample is not None:
+        again = failing(np.asarray(resample(), dtype=np.int64))
+        bad = {k: v for k, v in bad.items() if k in again}
+    assert not bad, f"{label}: outside the 99.9% band (also after one independent re-draw): {sorted(bad.values())}"

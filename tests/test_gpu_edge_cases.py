@@ -4,7 +4,7 @@ scenes outside the family (rejected loudly, never traced as something else)."""
 import numpy as np
 import pytest
 
-from helpers import assert_counts_agree, grouped, standard_scene
+from helpers import assert_counts_agree, assert_tallies_agree, grouped, standard_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -111,8 +111,8 @@ def test_scene_family_variants_match_oracle(label, kw, native, built_library):
     ref = _oracle_row(arrays, native, n)
     names = arrays.bin_names()
     assert row[:len(names)].sum() == n
-    assert_counts_agree(names, row[:len(names)], ref[:len(names)], label=label,
-                        resample=lambda: backend.trace_lights(arrays, [arrays.light], n, seed=22, device=0)[0][:len(names)])
+    assert_tallies_agree(names, row[:len(names)], ref[:len(names)], label=label,
+                         resample=lambda: backend.trace_lights(arrays, [arrays.light], n, seed=22, device=0)[0][:len(names)])
     assert abs(row[len(names)] - ref[len(names)]) / ref[len(names)] < 0.02
 
 

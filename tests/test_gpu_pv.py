@@ -4,7 +4,7 @@ generic oracle, and the reference's polymorphic 5-tuple return."""
 import numpy as np
 import pytest
 
-from helpers import assert_counts_agree, grouped, standard_scene
+from helpers import assert_counts_agree, assert_tallies_agree, grouped, standard_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -35,11 +35,8 @@ def test_pv_tallies_match_oracle(case, native, built_library):
     names = arrays.bin_names()
     nb = len(names)
     assert row[:nb].sum() == n and ref[:nb].sum() == n
-    assert_counts_agree(names, row[:nb], ref[:nb], label=case, resample=lambda: backend.trace_lights(
+    assert_tallies_agree(names, row[:nb], ref[:nb], label=case, resample=lambda: backend.trace_lights(
         arrays, [arrays.light], n, seed=5, device=0)[0][:nb])
-    g, r = grouped(names, row[:nb]), grouped(names, ref[:nb])
-    keys = sorted(set(g) | set(r))
-    assert_counts_agree(keys, [g.get(k, 0) for k in keys], [r.get(k, 0) for k in keys], label=case + " pooled")
     assert abs(row[nb] - ref[nb]) / ref[nb] < 0.01           # interaction events (the absorbing box counts two)
     if "backlit" not in case:
         assert sum(c for name, c in zip(names, row) if "PV" in name and name.startswith("absorb/")) > 0.05 * n
@@ -64,7 +61,7 @@ def test_pv_probe_matches_oracle(native, built_library):
     gpu = backend.probe_rays(arrays, pos, direc, device=0)
     clear = ref["distance"] > 1e-5
     same = (gpu["hit"] == ref["hit"]) & (gpu["container"] == ref["container"]) & (gpu["adjacent"] == ref["adjacent"])
-    assert np.mean(same[clear]) > 0.99
+    assert np.mean(same[clear]) > 0.999
     in_air_to_pv = clear & same & np.isin(ref["hit"], [i for i, name in enumerate(arrays.node_name) if "PV" in name])
     assert in_air_to_pv.sum() > 20
     lending = clear & same & (ref["hit"] == 1) & np.isin(ref["adjacent"], [i for i, name in enumerate(arrays.node_name) if "PV" in name])

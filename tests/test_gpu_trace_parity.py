@@ -3,7 +3,7 @@
 import numpy as np
 import pytest
 
-from helpers import am15_like_photon_spectrum, assert_counts_agree, grouped, standard_scene
+from helpers import am15_like_photon_spectrum, assert_counts_agree, assert_tallies_agree, grouped, standard_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -41,11 +41,8 @@ def test_tallies_match_oracle(case, native, built_library):
     names, gpu, ref = _both(standard_scene(**CASES[case]), n, native)
     nb = len(names)
     assert gpu[:nb].sum() == n and ref[:nb].sum() == n  # integer tallies: every photon lands in exactly one bin
-    assert_counts_agree(names, gpu[:nb], ref[:nb], label=case,
-                        resample=lambda: _both(standard_scene(**CASES[case]), n, native, seed_gpu=4048)[1][:nb])
-    g, r = grouped(names, gpu[:nb]), grouped(names, ref[:nb])
-    keys = sorted(set(g) | set(r))
-    assert_counts_agree(keys, [g.get(k, 0) for k in keys], [r.get(k, 0) for k in keys], label=case + " (pooled)")
+    assert_tallies_agree(names, gpu[:nb], ref[:nb], label=case,
+                         resample=lambda: _both(standard_scene(**CASES[case]), n, native, seed_gpu=4048)[1][:nb])
     # interaction events per photon agree to a fraction of a percent
     assert abs(gpu[nb] / n - ref[nb] / n) < 0.02 * ref[nb] / n + 0.02
     assert abs(gpu[nb + 1] / n - ref[nb + 1] / n) < 0.02 * max(ref[nb + 1] / n, 0.05) + 0.01
@@ -57,11 +54,8 @@ def test_config2_spectrum_1e6(native, built_library):
     names, gpu, ref = _both(standard_scene(tilt=0, elevation=90, spectrum=am15_like_photon_spectrum()), n, native)
     nb = len(names)
     assert gpu[:nb].sum() == n
-    assert_counts_agree(names, gpu[:nb], ref[:nb], label="config2", resample=lambda: _both(
+    assert_tallies_agree(names, gpu[:nb], ref[:nb], label="config2", resample=lambda: _both(
         standard_scene(tilt=0, elevation=90, spectrum=am15_like_photon_spectrum()), n, native, seed_gpu=4048)[1][:nb])
-    g, r = grouped(names, gpu[:nb]), grouped(names, ref[:nb])
-    keys = sorted(set(g) | set(r))
-    assert_counts_agree(keys, [g.get(k, 0) for k in keys], [r.get(k, 0) for k in keys], label="config2 pooled")
 
 
 def test_partition_invariance(native, built_library):
@@ -77,3 +71,49 @@ def test_partition_invariance(native, built_library):
     assert np.array_equal(whole, again)
     other = backend.trace_lights(arrays, [arrays.light], 40_000, seed=6, device=0)
     assert not np.array_equal(whole, other)
+
+
+def test_high_statistics_2e7(native, built_library):
+    """2e7 photons resolve discrepancies of a few 1e-4 (this is how a wrong container for tube-wall segments near the
+    capillary ends was found: 0.4 % of the +-y exits).  Every bin within 4 sigma, with the single re-draw rule."""
+    from lscpm_b200 import backend, flatten
+    import c_oracle
+
+    arrays = flatten.flatten_scene(standard_scene(tilt=0, elevation=90, wavelength=585.0))
+    n = 20_000_000
+    names = arrays.bin_names()
+    nb = len(names)
+    gpu = backend.trace_lights(arrays, [arrays.light], n, seed=31, device=0)[0]
+    batches, _ = backend.pack_batches([arrays.light])
+    ref = c_oracle.COracle(native, native.PackedScene(arrays)).trace(batches[0], photon_count=n, seed=32)
+    assert_tallies_agree(names, gpu[:nb], ref[:nb], label="2e7 photons", z=4.0,
+                         resample=lambda: backend.trace_lights(arrays, [arrays.light], n, seed=33, device=0)[0][:nb])
+    assert abs(gpu[nb] / n - ref[nb] / n) < 0.004           # interaction events per photon (sigma ~ 0.002)
+
+
+def test_probe_large_population(native, built_library):
+    """Interface bookkeeping (hit, container, adjacent) on ~4e5 rays harvested from oracle histories: no mismatch
+    beyond float-ambiguous origins."""
+    from lscpm_b200 import backend, flatten
+    import c_oracle
+
+    arrays = flatten.flatten_scene(standard_scene(tilt=0, elevation=25, azimuth=100, wavelength=585.0))
+    oracle = c_oracle.COracle(native, native.PackedScene(arrays))
+    batches, _ = backend.pack_batches([arrays.light])
+    pos, direc, wl = oracle.emit(batches[0], 50_000, seed=5)
+    hist = oracle.follow(pos, direc, wl, seed=6, max_steps=48)
+    rays_p, rays_d = [], []
+    for i in range(len(pos)):
+        k = min(hist["n_steps"][i], 48)
+        keep = np.isin(hist["event"][i, :k - 1], (0, 1, 2, 4))
+        rays_p.append(hist["pos"][i, :k - 1][keep])
+        rays_d.append(hist["dir"][i, :k - 1][keep])
+    p = np.concatenate(rays_p).astype(np.float32).astype(np.float64)
+    d = np.concatenate(rays_d).astype(np.float32).astype(np.float64)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    ref = oracle.probe(p, d)
+    gpu = backend.probe_rays(arrays, p, d, device=0)
+    clear = ref["distance"] > 1e-6
+    same = (gpu["hit"] == ref["hit"]) & (gpu["container"] == ref["container"]) & (gpu["adjacent"] == ref["adjacent"])
+    assert clear.sum() > 250_000
+    assert (clear & ~same).sum() <= 3, f"{(clear & ~same).sum()} interface mismatches"
