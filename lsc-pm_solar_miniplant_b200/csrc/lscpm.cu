@@ -209,6 +209,18 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
         if (node < 0) { out[i] = o; return; }
         o.found = inside ? 2 : 1; o.t = t; o.kind = SURF_BOX; o.face = face; o.container = MED_AIR; o.adj = MED_PLATE; o.ch = node;
         ext_node = node;
+        if (inside) {
+            // the photon is inside box `node` (its zero-distance entry is dropped): pvtrace reports the box's exit face
+            const DevExtBox& b = S.ext[node - 1];
+            const float c[3] = {b.cx, b.cy, b.cz}, hh[3] = {b.hx, b.hy, b.hz}, oo[3] = {abs_x(S, p), p.y, q.z}, dd[3] = {p.dx, p.dy, p.dz};
+            float tmax = LSCPM_INF; int fmax = 0;
+            for (int ax = 0; ax < 3; ++ax) {
+                if (dd[ax] == 0.f) continue;
+                const float te = ((dd[ax] > 0.f ? hh[ax] : -hh[ax]) - (oo[ax] - c[ax])) / dd[ax];
+                if (te < tmax) { tmax = te; fmax = 2 * ax + (dd[ax] > 0.f ? 1 : 0); }
+            }
+            o.t = tmax; o.face = face = fmax;
+        }
         box_normal(face, nx, ny, nz);
     } else if (q.medium == MED_AIR) {
         const Entry e = plate_entry(S.hx, S.hy, S.hz, abs_x(S, p), p.y, q.z, p.dx, p.dy, p.dz);
@@ -244,6 +256,7 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
     }
     o.n1 = S.med[o.container].n; o.n2 = S.med[o.adj].n;
     if (ext_node > 0) o.n2 = S.ext[ext_node - 1].n;
+    if (ext_node > 0 && o.found == 2) { o.n1 = S.ext[ext_node - 1].n; o.n2 = S.med[MED_AIR].n; }
     if (ext_node < 0) o.n2 = S.ext[-ext_node - 1].n;
     o.ext = ext_node;
     const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, o.n1, o.n2);
