@@ -275,6 +275,12 @@ def run_cuda(args) -> None:
         events_per_s_gpu = nb * ppb * events_per_photon / (ms_kernel * 1e-3)      # one GPU's kernel
         peak_lane = n_sm * 128 * sm_clock * 1e6
         achieved_lane = events_per_s_gpu * I_EVT
+        traffic, ncu = None, None
+        prof = os.path.join(ROOT, "profiles", "r1_final_metrics.json")
+        if os.path.exists(prof):
+            with open(prof) as fh:
+                ncu = json.load(fh)
+            traffic = ncu["dram__bytes_read.sum"] + ncu["dram__bytes_write.sum"]
         line = {
             "metric": METRIC, "value": value, "unit": "photons/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -289,7 +295,12 @@ def run_cuda(args) -> None:
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp32_issue", "achieved": achieved_lane / 1e12, "peak": peak_lane / 1e12,
-                         "unit": "Tlane-instr/s", "frac": achieved_lane / peak_lane, "traffic": None,
+                         "unit": "Tlane-instr/s", "frac": achieved_lane / peak_lane, "traffic": traffic,
+                         "traffic_note": "DRAM bytes per launch from profiles/r1_final_metrics.json (ncu --set full): photon state stays in registers",
+                         "executed": None if ncu is None else {
+                             "issue_slot_utilisation": ncu["sm__issue_active.avg.pct_of_peak_sustained_elapsed"] / 100.0,
+                             "active_lanes_per_warp_instruction": ncu["smsp__thread_inst_executed_per_inst_executed.ratio"],
+                             "source": "profiles/r1_final_metrics.json"},
                          "kernel": "trace_kernel", "ms_per_launch": ms_kernel,
                          "how": f"events/s/GPU x {I_EVT} lane-instr/event (SURVEY 8d) / (n_SM {n_sm} x 128 x {sm_clock:.0f} MHz sampled)"},
             "roofline_hbm": {"bound": "hbm", "achieved": events_per_s_gpu * BYTES_PER_EVENT / 1e9, "peak": peaks["hbm_gbs"],

@@ -62,6 +62,9 @@ __device__ __forceinline__ void flush_row(unsigned int* hist, unsigned long long
     __syncwarp();
 }
 
+// EXT: the scene has boxes outside the plate (photovoltaic variants); the standard scene runs the EXT = false
+// instantiation, which contains none of that code.
+template <bool EXT>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceArgs A) {
     extern __shared__ unsigned int smem_rows[];
@@ -91,7 +94,7 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
         if (alive) {
             const uint4 w = rng.next();
             StepOut so;
-            status = photon_step(S, p, w, so);
+            status = photon_step<EXT>(S, p, w, so);
             if (counts_as_event(so.event)) n_events += 1u + (unsigned)so.extra;
             if (so.event == EV_EMIT) n_events += 0x10000u;
         }
@@ -149,7 +152,7 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
             WavelengthDraw wd;
             int bin = -1;
             if (fresh) {
-                bin = source_fresh(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr);
+                bin = source_fresh<EXT>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr);
                 n_events = 0;
                 alive = true;
             } else {
@@ -178,7 +181,8 @@ __global__ void emit_kernel(const __grid_constant__ DevScene S, const DevBatch* 
     Photon p;
     WavelengthDraw wd;
     float origin[3];
-    source_fresh(S, *batch, spec_x, spec_cdf, spec_guide, rng, v, p, wd, origin);
+    if (S.n_ext > 0) source_fresh<true>(S, *batch, spec_x, spec_cdf, spec_guide, rng, v, p, wd, origin);
+    else source_fresh<false>(S, *batch, spec_x, spec_cdf, spec_guide, rng, v, p, wd, origin);
     source_finish(S, p, wd);
     float* o = out + 7 * i;
     o[0] = origin[0]; o[1] = origin[1]; o[2] = origin[2]; o[3] = p.dx; o[4] = p.dy; o[5] = p.dz; o[6] = p.wl;
@@ -284,11 +288,12 @@ __global__ void follow_kernel(const __grid_constant__ DevScene S, const FollowIn
     p.kc = 0; p.xr = 0.f; p.y = 0.f; p.z = 0.f; p.medium = MED_AIR; p.aux = 0;
     refresh_alphas(S, p);
     int k = 0;
-    int bin = place_photon(S, p, q.ox, q.oy, q.oz, false, 0.f, 0.f);
+    const bool ext = S.n_ext > 0;
+    int bin = ext ? place_photon<true>(S, p, q.ox, q.oy, q.oz, false, 0.f, 0.f) : place_photon<false>(S, p, q.ox, q.oy, q.oz, false, 0.f, 0.f);
     while (bin < 0) {
         const uint4 w = rng.next();
         StepOut so;
-        bin = photon_step(S, p, w, so);
+        bin = ext ? photon_step<true>(S, p, w, so) : photon_step<false>(S, p, w, so);
         if (bin == STEP_EMIT) {
             const uint4 v = rng.next();
             WavelengthDraw wd;
@@ -918,9 +923,11 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
     s->trace_smem = (size_t)(TRACE_THREADS / 32) * (size_t)(s->dev.n_bins + LSCPM_N_COUNTERS) * sizeof(unsigned int);
     if (s->trace_smem > 200 * 1024) return bail(fail(LSCPM_EUNSUPPORTED, "too many tally bins for the per-warp shared rows"));
     if (s->trace_smem > 48 * 1024 &&
-        (e = cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->trace_smem)) != cudaSuccess)
+        (e = cudaFuncSetAttribute(s->dev.n_ext > 0 ? trace_kernel<true> : trace_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->trace_smem)) != cudaSuccess)
         return bail(cuda_fail(e, "cudaFuncSetAttribute"));
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, trace_kernel, TRACE_THREADS, s->trace_smem)) != cudaSuccess)
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, s->dev.n_ext > 0 ? trace_kernel<true> : trace_kernel<false>,
+                                                           TRACE_THREADS, s->trace_smem)) != cudaSuccess)
         return bail(cuda_fail(e, "occupancy query (is the library built for this GPU's architecture?)"));
     if (s->blocks_per_sm < 1) return bail(fail(LSCPM_ECUDA, "trace kernel does not fit on an SM"));
     *out = s;
@@ -1029,7 +1036,8 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
     int rc = pick_counter(s, stream, &a.work_counter);
     if (rc) return rc;
     const int blocks = (int)std::min<unsigned long long>((unsigned long long)grid, (a.n_chunks + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32));
-    trace_kernel<<<std::max(blocks, 1), TRACE_THREADS, s->trace_smem, stream>>>(s->dev, a);
+    if (s->dev.n_ext > 0) trace_kernel<true><<<std::max(blocks, 1), TRACE_THREADS, s->trace_smem, stream>>>(s->dev, a);
+    else trace_kernel<false><<<std::max(blocks, 1), TRACE_THREADS, s->trace_smem, stream>>>(s->dev, a);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return LSCPM_OK;

@@ -539,10 +539,11 @@ struct WavelengthDraw {
 
 // put a ray that starts at plate-local (ox,oy,oz) on the plate: inside -> its medium, outside -> AIR on the entry
 // face (or BIN_MISS).  `anchored`: the entry point is already known to be (ax, ay) on the top face.
+template <bool EXT>
 __device__ __forceinline__ int place_photon(const DevScene& S, Photon& p, float ox, float oy, float oz, bool anchored,
                                             float ax, float ay) {
     p.steps = 0;
-    if (S.n_ext > 0 && !(fabsf(ox) < S.hx && fabsf(oy) < S.hy && fabsf(oz) < S.hz)) {
+    if (EXT && !(fabsf(ox) < S.hx && fabsf(oy) < S.hy && fabsf(oz) < S.hz)) {
         // outside boxes may shadow the plate: travel through the air from the true origin
         p.kc = 0; p.xr = ox - axis_x(S, 0); p.y = oy; p.z = oz - S.zc; p.aux = 0; p.medium = MED_OUT;
         return -1;
@@ -568,6 +569,7 @@ __device__ __forceinline__ int place_photon(const DevScene& S, Photon& p, float 
 }
 
 // generation-specific half: anchor point, direction, placement; fills the wavelength draw.  Returns -1 or BIN_MISS.
+template <bool EXT>
 __device__ __forceinline__ int source_fresh(const DevScene& S, const DevBatch& B, const float* __restrict__ spec_x,
                                             const float* __restrict__ spec_cdf, const unsigned short* __restrict__ spec_guide,
                                             Rng& rng, const uint4 v, Photon& p, WavelengthDraw& wd, float* origin) {
@@ -589,7 +591,7 @@ __device__ __forceinline__ int source_fresh(const DevScene& S, const DevBatch& B
     }
     const float ox = fmaf(-B.back_off, p.dx, ax), oy = fmaf(-B.back_off, p.dy, ay), oz = fmaf(-B.back_off, p.dz, az);
     if (origin) { origin[0] = ox; origin[1] = oy; origin[2] = oz; }
-    return place_photon(S, p, ox, oy, oz, B.anchor_on_top && p.dz < 0.f, ax, ay);
+    return place_photon<EXT>(S, p, ox, oy, oz, B.anchor_on_top && p.dz < 0.f, ax, ay);
 }
 
 // emission-specific half: isotropic direction, kT-restricted CDF window of the luminophore stored in p.aux
@@ -752,9 +754,10 @@ struct StepOut {
     int extra;       // additional interaction events folded into this iteration (photon absorbed by an outside box)
 };
 
+template <bool EXT>
 __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const uint4 w, StepOut& out) {
     out.extra = 0;
-    if (S.n_ext > 0 && p.medium == MED_OUT) {
+    if (EXT && p.medium == MED_OUT) {
         OutState q;
         q.x = abs_x(S, p); q.y = p.y; q.z = p.z + S.zc; q.dx = p.dx; q.dy = p.dy; q.dz = p.dz; q.aux = p.aux; q.steps = p.steps;
         const OutResult r = outside_step(S, q, u01(w.y));
@@ -819,7 +822,7 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
     }
     float n2 = S.med[h.adj].n;
     const bool leaving = flat && p.medium != MED_AIR;
-    if (S.n_ext > 0 && leaving) {
+    if (EXT && leaving) {
         // adjacent = second intersection along the ray: an outside box straight ahead (even across an air gap) lends its index
         const int e = ext_ahead(S, abs_x(S, p), p.y, p.z + S.zc, p.dx, p.dy, p.dz);
         if (e >= 0) n2 = S.ext[e].n;
@@ -834,10 +837,10 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
         p.medium = (p.aux >> 4) & 3;
         return -1;
     }
-    if (S.n_ext > 0) p.aux = note_surface(p.aux, false, 0, h.face, leaving && !reflected);
+    if (EXT) p.aux = note_surface(p.aux, false, 0, h.face, leaving && !reflected);
     if (reflected) return -1;
     if (flat) {
-        if (S.n_ext > 0) {   // the air around the plate has geometry: keep following
+        if (EXT) {   // the air around the plate has geometry: keep following
             const float xa = abs_x(S, p);
             p.kc = 0; p.xr = xa - axis_x(S, 0);
             p.medium = MED_OUT;
