@@ -1,67 +1,55 @@
-"""The reference's scene-construction tests (reference tests/test_scene_creator.py:19-87), against the mirrored
-scene_creator: same imports, same assertions (including the plain anytree.Node light and light_nodes.pop())."""
+"""Scene construction through the mirrored ``scene_creator`` with the reference's own imports and checks (reference
+tests/test_scene_creator.py:19-87): one light node carrying a ``Light``; the first ``Box`` has a ``Luminophore`` exactly
+when the dye is requested (default: yes); the diffuse scene's light is a ``MyLight``; a plain ``anytree.Node`` works
+as the light holder and ``scene.light_nodes`` is a list."""
+import numpy as np
+import pytest
 from anytree import LevelOrderIter, Node
 from miniplant.scene_creator import _create_scene_common, create_diffuse_scene, create_direct_scene
 from miniplant.utils import MyLight
 from pvtrace import Box, Light, Luminophore, Scene
 
 
-def get_light_node() -> Node:
+def plain_anytree_light() -> Node:
     return Node(name="Test Light", light=Light(), parent=None)
 
 
-def scene_is_valid(scene: Scene):
+def check_valid(scene):
     assert isinstance(scene, Scene)
-    assert len(scene.light_nodes) == 1
-    light = scene.light_nodes[0]
-    assert isinstance(light.light, Light)
+    lights = scene.light_nodes
+    assert len(lights) == 1 and isinstance(lights[0].light, Light)
 
 
-def scene_has_dye(scene: Scene):
-    for node in LevelOrderIter(scene.root):
-        if hasattr(node, "geometry") and isinstance(node.geometry, Box):
-            return any(isinstance(x, Luminophore) for x in node.geometry.material.components)
+def has_dye(scene) -> bool:
+    plate = next(n for n in LevelOrderIter(scene.root) if isinstance(getattr(n, "geometry", None), Box))
+    return any(isinstance(component, Luminophore) for component in plate.geometry.material.components)
 
 
-def test__create_scene_common():
-    scene = _create_scene_common(tilt_angle=0, light_source=get_light_node())
-    scene_is_valid(scene)
-    assert scene_has_dye(scene)
+@pytest.mark.parametrize("include_dye,expected", [(None, True), (True, True), (False, False)])
+def test__create_scene_common(include_dye, expected):
+    kwargs = {} if include_dye is None else {"include_dye": include_dye}
+    scene = _create_scene_common(tilt_angle=0, light_source=plain_anytree_light(), **kwargs)
+    check_valid(scene)
+    assert has_dye(scene) is expected
 
 
-def test__create_scene_common_w_dye():
-    assert scene_has_dye(_create_scene_common(tilt_angle=0, light_source=get_light_node(), include_dye=True))
+@pytest.mark.parametrize("kwargs,expected", [({}, True), ({"include_dye": False}, False)])
+def test_create_direct_scene_defaults(kwargs, expected):
+    scene = create_direct_scene(**kwargs)
+    check_valid(scene)
+    assert has_dye(scene) is expected
 
 
-def test__create_scene_common_wo_dye():
-    assert not scene_has_dye(_create_scene_common(tilt_angle=0, light_source=get_light_node(), include_dye=False))
-
-
-def test_create_diffuse_scene():
-    scene = create_direct_scene()
-    scene_is_valid(scene)
-    assert scene_has_dye(scene)
-
-
-def test_create_diffuse_scene_wo_dye():
-    scene = create_direct_scene(include_dye=False)
-    scene_is_valid(scene)
-    assert not scene_has_dye(scene)
-
-
-def test_create_direct_scene():
+def test_create_diffuse_scene_light_is_mylight():
     scene = create_diffuse_scene()
     assert isinstance(scene, Scene)
     assert len(scene.light_nodes) == 1
-    light = scene.light_nodes.pop()
-    assert isinstance(light.light, MyLight)
+    assert isinstance(scene.light_nodes.pop().light, MyLight)     # light_nodes is a fresh list
 
 
 def test_scene_graph_matches_reference_layout():
     """34 geometry nodes, shared PFA geometry, per-tube reaction cylinders sharing one Reactor component,
     capillaries at x_k = -0.225 + 0.03 k (reference scene_creator.py:216-262)."""
-    import numpy as np
-
     scene = create_direct_scene(tilt_angle=0)
     nodes = [n for n in LevelOrderIter(scene.root) if getattr(n, "geometry", None) is not None]
     assert len(nodes) == 34
@@ -75,3 +63,12 @@ def test_scene_graph_matches_reference_layout():
     assert np.allclose(xs, -0.225 + 0.03 * np.arange(16))
     plate = next(n for n in nodes if n.name.startswith("LSC-PM"))
     assert np.allclose(plate.world_pose()[:3, 3], [0, 0, -0.004])     # top face through the world origin
+
+
+def test_pv_kwargs_add_the_reference_boxes():
+    scene = create_direct_scene(tilt_angle=0, add_bottom_PV=True, add_side_PV=True)
+    names = [n.name for n in LevelOrderIter(scene.root)]
+    assert "bottomPV" in names and {"sidePV1", "sidePV2", "sidePV3", "sidePV4"} <= set(names)
+    bottom = next(n for n in LevelOrderIter(scene.root) if n.name == "bottomPV")
+    assert bottom.geometry.material.refractive_index == 3.4
+    assert np.allclose(bottom.world_pose()[:3, 3], [0, 0, -0.004 - 0.025])
