@@ -100,6 +100,7 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
         }
         // ---- tally the photons that ended -----------------------------------------------------------
         if (status >= 0) {
+            LSCPM_CHECK(status < S.n_bins);
             if (batch == hbatch) {
                 atomicAdd(hist + status, 1u);
                 atomicAdd(hist + S.n_bins, n_events & 0xffffu);

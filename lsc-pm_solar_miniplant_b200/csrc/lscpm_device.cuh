@@ -58,6 +58,15 @@ constexpr int INV_CDF_BUCKETS = 1024;     // guide-table resolution for inverse-
 constexpr int SPEC_BUCKETS = 32;          // guide-table resolution for the per-batch solar spectra
 #define LSCPM_INF __int_as_float(0x7f800000)
 
+// Bounds checks of every computed table / tally / cell index (compute-sanitizer is closed on this GPU pool):
+// build with -DLSCPM_BOUNDS_CHECK and run the GPU tests; a violated check prints its location and traps the kernel.
+#ifdef LSCPM_BOUNDS_CHECK
+#include <cstdio>
+#define LSCPM_CHECK(cond) do { if (!(cond)) { printf("LSCPM_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); __trap(); } } while (0)
+#else
+#define LSCPM_CHECK(cond) do { } while (0)
+#endif
+
 struct DevComponent {
     int kind;
     int abs_table;   // -1: constant coefficient
@@ -225,6 +234,7 @@ __device__ __noinline__ float table_at_irregular(const DevTable T, const float* 
     int b = (int)((v - T.x0) * T.inv_w);
     b = min(max(b, 0), T.fwd_n - 1);
     int j = __ldg(fwd + b);
+    LSCPM_CHECK(j >= 0 && j + 1 < T.n);
     while (j + 2 < T.n && v >= __ldg(xp + j + 1)) ++j;
     while (j > 0 && v < __ldg(xp + j)) --j;
     return lerp_knots(v, xp, fp, j);
@@ -236,6 +246,7 @@ __device__ __forceinline__ float table_at(const DevScene& S, int t, float v, con
         float f = (v - T.x0) * T.inv_w;
         f = fminf(fmaxf(f, 0.f), (float)(T.n - 1));      // numpy.interp clamps outside the table
         const int j = min((int)f, T.n - 2);
+        LSCPM_CHECK(j >= 0 && j + 1 < T.n);
         const float y0 = __ldg(col + T.begin + j), y1 = __ldg(col + T.begin + j + 1);
         return fmaf(f - (float)j, y1 - y0, y0);
     }
@@ -251,7 +262,9 @@ __device__ __noinline__ float inverse_cdf(float u, const float* __restrict__ cdf
     // into VIADDMNMX with a wrong immediate inside the out-of-line clone of this function (emit / follow kernels)
     const float fb = (float)buckets;
     const int b = (int)fminf(u * fb, fb - 1.f);
+    LSCPM_CHECK(b >= 0 && b < buckets);
     int lo = __ldg(guide + b), hi = min((int)__ldg(guide + b + 1) + 1, n - 1);
+    LSCPM_CHECK(lo >= 0 && lo < n - 1 && hi > lo && hi <= n - 1);
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (__ldg(cdf + mid) <= u) lo = mid; else hi = mid;
@@ -793,6 +806,7 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
             return STEP_EMIT;
         }
         out.event = comp.kind == COMP_REACTOR ? EV_REACT : EV_ABSORB;
+        LSCPM_CHECK(p.kc >= 0 && p.kc < S.n_ch && index >= 0 && index < m.n_comp);
         const int base = h.container == MED_PLATE ? S.abs_base_plate
                        : (h.container == MED_OUTER ? __ldg(S.abs_base_outer + p.kc) : __ldg(S.abs_base_inner + p.kc));
         return base + index;
@@ -801,6 +815,7 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
     if (h.kind == SURF_CELL) {
         // step into the neighbouring cell; nothing physical happens here
         p.kc += h.face;
+        LSCPM_CHECK(p.kc >= 0 && p.kc < S.n_ch);
         p.xr = h.face > 0 ? -0.5f * S.pitch : 0.5f * S.pitch;
         out.event = EV_NONE;
         return -1;
