@@ -37,6 +37,9 @@ BYTES_PER_EVENT = 96   # algorithmic bytes per event if photon state round-tripp
 METRIC = "photons/sec traced to termination"
 
 
+WORKLOAD = "config2"
+
+
 def workload_scene():
     import lscpm_b200
 
@@ -44,7 +47,10 @@ def workload_scene():
     from lscpm_b200 import flatten
     from lscpm_b200.workloads import am15_like_photon_spectrum, standard_scene
 
-    scene = standard_scene(tilt=0, elevation=90, azimuth=180, spectrum=am15_like_photon_spectrum())
+    extra = {}
+    if WORKLOAD == "config5":     # scaled mini-plant: every batch is one plate of the array, dense channel grid
+        extra = dict(capillary_count=46, capillary_pitch=0.01)
+    scene = standard_scene(tilt=0, elevation=90, azimuth=180, spectrum=am15_like_photon_spectrum(), **extra)
     return flatten.flatten_scene(scene)
 
 
@@ -172,6 +178,9 @@ def run_reference(args) -> None:
 
 
 def workload_name(args) -> str:
+    if WORKLOAD == "config5":
+        return (f"BASELINE configs[4]: scaled mini-plant, array of LSC-PM plates with a dense channel grid (46 capillaries at "
+                f"10 mm), one plate per batch; {args.batches} plates x {args.photons} photons per GPU per step")
     return (f"BASELINE configs[1]: standard LSC-PM scene (LR305 plate + 16 MB capillaries), tilt 0 / sun at zenith, "
             f"AM1.5G-like 27-knot SPECTRL2-slice spectrum; {args.batches} batches x {args.photons} photons per GPU per step")
 
@@ -330,7 +339,11 @@ def main() -> None:
     ap.add_argument("--photons", type=int, default=1_000_000, help="photons per batch")
     ap.add_argument("--cpu-photons", type=int, default=0, help="photons of the bounded CPU sample (0: calibrate to ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=("config2", "config5"), default="config2",
+                    help="config2 (default, the bench contract line) or config5 (dense-grid plate array)")
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -146,7 +146,14 @@ def _create_scene_common(tilt_angle, light_source, include_dye=None, **kwargs) -
     )
     pfa_cil.color, pfa_cil.transparency, pfa_cil.opacity = 0xEEEEEE, True, 0.5
 
-    for capillary_num in range(N_CAPILLARIES):
+    # Extension for the scaled mini-plant (BASELINE config 5, dense channel grids): `capillary_count` / `capillary_pitch`
+    # keyword arguments; the defaults reproduce the reference's 16 capillaries at 30 mm starting 10 mm from the edge.
+    capillary_count = int(kwargs.get("capillary_count", N_CAPILLARIES))
+    capillary_pitch = float(kwargs.get("capillary_pitch", CAPILLARY_PITCH))
+    first_x = CAPILLARY_FIRST_X if (capillary_count, capillary_pitch) == (N_CAPILLARIES, CAPILLARY_PITCH) \
+        else -0.5 * capillary_pitch * (capillary_count - 1)
+
+    for capillary_num in range(capillary_count):
         tube = Node(name=f"Capillary_PFA_{capillary_num}", geometry=pfa_cil, parent=reactor)
         reaction_cil = Cylinder(
             length=0.47,
@@ -158,7 +165,7 @@ def _create_scene_common(tilt_angle, light_source, include_dye=None, **kwargs) -
 
         # cylinder axis z -> y, then slide to its slot in the plate (reference :259-262)
         tube.rotate(np.radians(90), (1, 0, 0))
-        tube.translate((CAPILLARY_FIRST_X + CAPILLARY_PITCH * capillary_num, 0, 0))
+        tube.translate((first_x + capillary_pitch * capillary_num, 0, 0))
 
     # Tilt about +y, then drop by half the thickness along the tilted normal so that the top face
     # contains the world origin (reference :264-272)
