@@ -264,6 +264,26 @@ def simulate_scene(scene, num_photons: int, seed: Optional[int] = None, device=N
     return _tally.TallyResult(handle.bin_names, counts, 0, 0)
 
 
+def capture_paths(scene, num_paths: int, seed: Optional[int] = None, device=None, max_steps: int = 256) -> list:
+    """Photon paths for visual debugging (reference ``photon_path`` / ``renderer.add_ray_path``,
+    ``miniplant/simulation_runner.py:34-43,55``): the first ``num_paths`` rays of the scene's light, followed on the
+    GPU with per-step records.  Each path is a tuple of ``Ray`` objects, GENERATE ray first."""
+    arrays = _flatten.flatten_scene(scene, with_light=False)
+    rays = list(scene.emit(int(num_paths)))
+    if not rays:
+        return []
+    out = trace_rays(arrays, [r.position for r in rays], [r.direction for r in rays], [r.wavelength for r in rays],
+                     seed=seed, device=device, max_steps=max_steps)
+    paths = []
+    for i, ray in enumerate(rays):
+        steps = [ray]
+        for k in range(min(int(out["n_steps"][i]), max_steps)):
+            steps.append(_api.Ray(position=tuple(out["pos"][i, k]), direction=tuple(out["dir"][i, k]),
+                                  wavelength=float(out["wavelength"][i, k]), source=getattr(ray, "source", None)))
+        paths.append(tuple(steps))
+    return paths
+
+
 def simulate_final_events(scene, num_rays: int, **kwargs) -> list:
     """``Scene.simulate`` shape: one history per photon whose last entry carries the terminal ``Event``
     (the reference reads only ``photon[-1][1]``, ``miniplant/simulation_runner.py:63``)."""

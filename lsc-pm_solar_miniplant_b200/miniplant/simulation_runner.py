@@ -11,7 +11,7 @@ from __future__ import annotations
 import logging
 from typing import Callable
 
-from ..backend import simulate_scene
+from ..backend import capture_paths, simulate_scene
 from ..compat import pvtrace_namespace
 from .scene_creator import create_direct_scene, create_diffuse_scene
 
@@ -32,6 +32,7 @@ def _common_simulation_runner(
     seed: int = None,
     device=None,
     return_tallies: bool = False,
+    capture: int = 0,
 ):
     """Trace ``num_photons`` photons through ``scene`` and return the fraction absorbed by the reaction
     mixture, ``count[Event.REACT] / num_photons`` (reference ``:65-66``).
@@ -63,10 +64,10 @@ def _common_simulation_runner(
         logger.info(f"The side PV absorbed {sidePV_count} photons (i.e. {sidePV_count / num_photons * 100 :.2f} %) ")
     if return_tallies:
         return reacted_fraction, result
-    # same polymorphic return as the reference (:77-80); photon histories are not kept for a bulk launch — use
-    # photon_tracer.follow(scene, ray) for individual paths
+    # same polymorphic return as the reference (:77-80).  A bulk launch keeps no histories; `capture=N` follows N
+    # rays of the same light with per-step records for the photon_path slot (reference :55).
     if bottomPV_count > 0 or sidePV_count > 0:
-        photon_path = []
+        photon_path = capture_paths(scene, capture, seed=seed, device=device) if capture else []
         return reacted_fraction, scene, photon_path, bottomPV_count, sidePV_count
     return reacted_fraction
 
@@ -84,7 +85,7 @@ def run_direct_simulation(
 ):
     """Create a scene for direct irradiation with the provided parameters and run a simulation on it
     (reference ``:83-105``)."""
-    runner_kwargs = {k: kwargs.pop(k) for k in ("seed", "device", "return_tallies") if k in kwargs}
+    runner_kwargs = {k: kwargs.pop(k) for k in ("seed", "device", "return_tallies", "capture") if k in kwargs}
     scene = create_direct_scene(
         tilt_angle=tilt_angle,
         solar_elevation=solar_elevation,

@@ -85,3 +85,21 @@ def test_runner_returns_the_reference_tuple(built_library):
     assert hasattr(scene, "light_nodes") and photon_path == []
     plain = run_direct_simulation(tilt_angle=40, solar_elevation=50, solar_azimuth=180, num_photons=2000, seed=1)
     assert isinstance(plain, float)
+
+
+def test_photon_path_capture(built_library):
+    """Row f4: photon paths for the reference's photon_path slot / renderer (simulation_runner.py:34-43,55)."""
+    from lscpm_b200 import backend
+    from lscpm_b200.compat.pvtrace_api import Ray
+    from miniplant.scene_creator import create_direct_scene
+    from miniplant.simulation_runner import run_direct_simulation
+
+    res = run_direct_simulation(tilt_angle=0, solar_elevation=90, add_bottom_PV=True, num_photons=5000, seed=2, capture=25)
+    paths = res[2]
+    assert len(paths) == 25 and all(isinstance(step, Ray) for path in paths for step in path)
+    assert all(len(path) >= 2 for path in paths)
+    first = paths[0]
+    assert abs(first[0].position[2] - 1.0) < 1e-9 and abs(first[1].position[2]) < 1e-6     # 1 m above, then on the top face
+    scene = create_direct_scene(tilt_angle=0, solar_elevation=90)
+    plain = backend.capture_paths(scene, 10, seed=3)
+    assert len(plain) == 10
