@@ -336,13 +336,17 @@ __device__ __forceinline__ void cylinder_roots(float a, float inv_a, float b, fl
 __device__ __forceinline__ Hit compute_hit(const DevScene& S, const Photon& p) {
     Hit h;
     h.ch = p.kc;
-    // slabs
-    const float ty = p.dy > 0.f ? fdiv(S.hy - p.y, p.dy) : (p.dy < 0.f ? fdiv(-S.hy - p.y, p.dy) : LSCPM_INF);
-    const float tz = p.dz > 0.f ? fdiv(S.hz - S.zc - p.z, p.dz) : (p.dz < 0.f ? fdiv(-S.hz - S.zc - p.z, p.dz) : LSCPM_INF);
+    // slabs, branch-free: distance to the face the ray is heading to; a zero direction component gives +INF
+    // (rcp(0) = +INF times a positive gap)
     const bool first = p.kc == 0, last = p.kc == S.n_ch - 1;
     const float half = 0.5f * S.pitch;
     const float x_hi = last ? S.cell_hi_last : half, x_lo = first ? S.cell_lo_first : -half;
-    const float tx = p.dx > 0.f ? fdiv(x_hi - p.xr, p.dx) : (p.dx < 0.f ? fdiv(x_lo - p.xr, p.dx) : LSCPM_INF);
+    const float gap_y = copysignf(S.hy, p.dy) - p.y;
+    const float gap_z = copysignf(S.hz, p.dz) - S.zc - p.z;
+    const float gap_x = (p.dx >= 0.f ? x_hi : x_lo) - p.xr;
+    const float ty = p.dy != 0.f ? gap_y * frcp(p.dy) : LSCPM_INF;
+    const float tz = p.dz != 0.f ? gap_z * frcp(p.dz) : LSCPM_INF;
+    const float tx = p.dx != 0.f ? gap_x * frcp(p.dx) : LSCPM_INF;
     // cylinders about the current axis
     const float a = fmaf(p.dx, p.dx, p.dz * p.dz);
     const bool has_a = a > 1e-30f;
@@ -786,8 +790,11 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
     }
     // a virtual crossing is not a follow() iteration
     if (h.kind != SURF_CELL && ++p.steps > MAXSTEPS) { out.event = EV_KILL; return BIN_KILL; }
-    const float alpha = h.container == MED_PLATE ? p.a_plate
-                      : (h.container == MED_OUTER ? p.a_outer : (h.container == MED_INNER ? p.a_inner : 0.f));
+    // branch-free select of the container's attenuation (the compiler turned the ternary chain into a jump table)
+    float alpha = 0.f;
+    alpha = h.container == MED_PLATE ? p.a_plate : alpha;
+    alpha = h.container == MED_OUTER ? p.a_outer : alpha;
+    alpha = h.container == MED_INNER ? p.a_inner : alpha;
     const float depth = alpha <= ALPHA_ZERO ? LSCPM_INF : fdiv(-flog(one_minus_u01(w.x)), alpha);
     const float u_surf = u01(w.y);
     out.medium = h.container; out.ch = p.kc; out.kind = h.kind; out.face = h.face;
