@@ -210,11 +210,13 @@ __device__ __forceinline__ float frcp(float x) { return 1.f / x; }
 __device__ __forceinline__ float fsqrt(float x) { return sqrtf(x); }
 __device__ __forceinline__ float fdiv(float a, float b) { return a / b; }
 __device__ __forceinline__ float flog(float x) { return logf(x); }
+__device__ __forceinline__ float frsqrt(float x) { return rsqrtf(x); }
 #else
 __device__ __forceinline__ float frcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fsqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float fdiv(float a, float b) { return a * frcp(b); }
 __device__ __forceinline__ float flog(float x) { return __logf(x); }
+__device__ __forceinline__ float frsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #endif
 
 // ------------------------------------------------------------------------------------------------
@@ -466,7 +468,7 @@ __device__ __forceinline__ Interface interface_eval(float dx, float dy, float dz
 }
 
 __device__ __forceinline__ void normalise(float& x, float& y, float& z) {
-    const float s = rsqrtf(x * x + y * y + z * z);
+    const float s = frsqrt(x * x + y * y + z * z);
     x *= s; y *= s; z *= s;
 }
 
@@ -789,7 +791,8 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
         h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false;
     }
     // a virtual crossing is not a follow() iteration
-    if (h.kind != SURF_CELL && ++p.steps > MAXSTEPS) { out.event = EV_KILL; return BIN_KILL; }
+    p.steps += h.kind != SURF_CELL ? 1 : 0;
+    if (p.steps > MAXSTEPS) { out.event = EV_KILL; return BIN_KILL; }
     // branch-free select of the container's attenuation (the compiler turned the ternary chain into a jump table)
     float alpha = 0.f;
     alpha = h.container == MED_PLATE ? p.a_plate : alpha;
@@ -837,7 +840,7 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
             else p.z = ((h.face & 1) ? S.hz : -S.hz) - S.zc;
         }
     } else {
-        const float inv = rsqrtf(fmaf(p.xr, p.xr, p.z * p.z));
+        const float inv = frsqrt(fmaf(p.xr, p.xr, p.z * p.z));
         nx = p.xr * inv; ny = 0.f; nz = p.z * inv;
         // leaving the tube wall: pvtrace's adjacent is whatever the straight continuation meets next
         if (h.maybe_sibling && sibling_ahead(S, p.kc, p.xr, p.y, p.z, p.dx, p.dy, p.dz) >= 0) h.adj = MED_OUTER;
