@@ -210,7 +210,7 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
     int ext_node = 0;      // probe bookkeeping: outside box hit (i+1) or lending its index as adjacent (-(i+1))
     if (q.medium == MED_AIR && S.n_ext > 0) {
         float t; int node, face;
-        const bool inside = outside_hit(S, abs_x(S, p), p.y, q.z, p.dx, p.dy, p.dz, t, node, face);
+        const bool inside = outside_hit(S, abs_x(S, p), p.y, q.z, p.dx, p.dy, p.dz, -1, t, node, face);
         if (node < 0) { out[i] = o; return; }
         o.found = inside ? 2 : 1; o.t = t; o.kind = SURF_BOX; o.face = face; o.container = MED_AIR; o.adj = MED_PLATE; o.ch = node;
         ext_node = node;

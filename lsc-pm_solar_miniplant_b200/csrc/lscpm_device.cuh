@@ -43,7 +43,7 @@ constexpr int MAX_COMP = 4;
 constexpr int MAX_TABLES = 12;           // scene tables + one total-attenuation table per medium
 constexpr int MED_AIR = 0, MED_PLATE = 1, MED_OUTER = 2, MED_INNER = 3, MED_OUT = 4;
 constexpr int MAX_EXT = 6;                // boxes outside the plate (the reference's photovoltaic absorbers)
-constexpr float EXT_TOL = 1e-6f;          // metres: "distance is zero" for faces shared between the plate and an outside box
+constexpr float EXT_TOL = 2e-7f;          // metres along a face normal: "distance is zero" for faces shared between the plate and an outside box
 constexpr int COMP_ABSORBER = 0, COMP_LUMINOPHORE = 1, COMP_REACTOR = 2;
 constexpr int LIGHT_DIRECT = 0, LIGHT_DIFFUSE = 1;
 constexpr int EV_GENERATE = 0, EV_REFLECT = 1, EV_TRANSMIT = 2, EV_ABSORB = 3, EV_EMIT = 4, EV_EXIT = 5, EV_KILL = 6,
@@ -639,8 +639,9 @@ __device__ __forceinline__ void source_finish(const DevScene& S, Photon& p, cons
 // geometry of its own.  All of this is out of line and only runs when S.n_ext > 0.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void slab_interval(float cx, float cy, float cz, float hx, float hy, float hz, float ox, float oy,
-                                              float oz, float dx, float dy, float dz, float& tmin, float& tmax, int& fmin) {
-    tmin = -LSCPM_INF; tmax = LSCPM_INF; fmin = 0;
+                                              float oz, float dx, float dy, float dz, float& tmin, float& tmax, int& fmin,
+                                              int& fmax) {
+    tmin = -LSCPM_INF; tmax = LSCPM_INF; fmin = 0; fmax = 0;
     const float c[3] = {cx, cy, cz}, h[3] = {hx, hy, hz}, o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
@@ -650,11 +651,16 @@ __device__ __forceinline__ void slab_interval(float cx, float cy, float cz, floa
             continue;
         }
         float tlo = (-h[ax] - rel) / d[ax], thi = (h[ax] - rel) / d[ax];
-        int flo = 2 * ax;
-        if (tlo > thi) { const float tt = tlo; tlo = thi; thi = tt; flo = 2 * ax + 1; }
+        int flo = 2 * ax, fhi = 2 * ax + 1;
+        if (tlo > thi) { const float tt = tlo; tlo = thi; thi = tt; flo = 2 * ax + 1; fhi = 2 * ax; }
         if (tlo > tmin) { tmin = tlo; fmin = flo; }
-        tmax = fminf(tmax, thi);
+        if (thi < tmax) { tmax = thi; fmax = fhi; }
     }
+}
+
+// spatial gap (metres, along the face normal) that the ray parameter t corresponds to for face f
+__device__ __forceinline__ float normal_gap(float t, int f, float dx, float dy, float dz) {
+    return t * fabsf(f < 2 ? dx : (f < 4 ? dy : dz));
 }
 
 // first outside box met by the straight line from (ox,oy,oz) along d, a box starting at distance ~0 included
@@ -663,29 +669,38 @@ __device__ __noinline__ int ext_ahead(const DevScene& S, float ox, float oy, flo
     int best = -1; float tbest = LSCPM_INF;
     for (int i = 0; i < S.n_ext; ++i) {
         const DevExtBox& b = S.ext[i];
-        float tmin, tmax; int f;
-        slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, ox, oy, oz, dx, dy, dz, tmin, tmax, f);
-        if (tmin <= tmax && tmax > EXT_TOL && tmin > -EXT_TOL && tmin < tbest) { tbest = tmin; best = i; }
+        float tmin, tmax; int f, fx;
+        slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, ox, oy, oz, dx, dy, dz, tmin, tmax, f, fx);
+        if (tmin <= tmax && tmax > 0.f && normal_gap(tmin, f, dx, dy, dz) > -EXT_TOL && tmin < tbest) {
+            tbest = tmin; best = i;
+        }
     }
     return best;
 }
 
 // Nearest surface for a ray in the air around the plate: node 0 = plate, i+1 = outside box i, -1 = none.
+// `skip` is the convex body the photon has just left or bounced off (0 plate, i+1 box i, -1 none): it cannot be met
+// again before another interaction, so it is excluded by logic rather than by a distance tolerance (a tolerance on the
+// exit parameter would let photons that clip a box corner within that tolerance escape).
 // Returns true when the ray starts on (within EXT_TOL of) a face of box `node` heading inwards.
-__device__ __forceinline__ bool outside_hit(const DevScene& S, float x, float y, float z, float dx, float dy, float dz,
+__device__ __forceinline__ bool outside_hit(const DevScene& S, float x, float y, float z, float dx, float dy, float dz, int skip,
                                             float& t_best, int& node, int& face) {
     t_best = LSCPM_INF; node = -1; face = 0;
     for (int i = 0; i < S.n_ext; ++i) {
+        if (i + 1 == skip) continue;
         const DevExtBox& b = S.ext[i];
-        float tmin, tmax; int f;
-        slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, x, y, z, dx, dy, dz, tmin, tmax, f);
-        if (!(tmin <= tmax) || tmax <= EXT_TOL) continue;
-        if (tmin <= EXT_TOL) { t_best = 0.f; node = i + 1; face = f; return true; }
+        float tmin, tmax; int f, fx;
+        slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, x, y, z, dx, dy, dz, tmin, tmax, f, fx);
+        if (!(tmin <= tmax) || !(tmax > 0.f)) continue;
+        // on its face (gap along the face normal within EXT_TOL: coincident faces differ by float rounding), heading in
+        if (normal_gap(tmin, f, dx, dy, dz) <= EXT_TOL) { t_best = 0.f; node = i + 1; face = f; return true; }
         if (tmin < t_best) { t_best = tmin; node = i + 1; face = f; }
     }
-    float tmin, tmax; int f;
-    slab_interval(0.f, 0.f, 0.f, S.hx, S.hy, S.hz, x, y, z, dx, dy, dz, tmin, tmax, f);
-    if (tmin <= tmax && tmin > EXT_TOL && tmin < t_best) { t_best = tmin; node = 0; face = f; }
+    if (skip != 0) {
+        float tmin, tmax; int f, fx;
+        slab_interval(0.f, 0.f, 0.f, S.hx, S.hy, S.hz, x, y, z, dx, dy, dz, tmin, tmax, f, fx);
+        if (tmin <= tmax && tmax > 0.f && normal_gap(tmin, f, dx, dy, dz) > EXT_TOL && tmin < t_best) { t_best = tmin; node = 0; face = f; }
+    }
     return false;
 }
 
@@ -716,7 +731,8 @@ __device__ __noinline__ OutResult outside_step(const DevScene& S, OutState q, fl
     r.bin = -1; r.event = EV_NONE; r.node = 0; r.face = 0; r.extra = 0; r.entered = false;
     if (r.steps > MAXSTEPS) { r.event = EV_KILL; r.bin = BIN_KILL; return r; }
     float t_best; int node, face;
-    if (outside_hit(S, q.x, q.y, q.z, q.dx, q.dy, q.dz, t_best, node, face)) {
+    const int skip = ((q.aux >> 9) & 3) ? ((q.aux >> 12) & 7) : -1;
+    if (outside_hit(S, q.x, q.y, q.z, q.dx, q.dy, q.dz, skip, t_best, node, face)) {
         // the photon sits on a face of box `node`, heading in: the zero-distance entry is dropped, it is inside the box
         r.event = EV_ABSORB; r.node = node; r.bin = S.ext[node - 1].abs_bin;
         return r;
