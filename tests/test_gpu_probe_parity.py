@@ -46,7 +46,7 @@ def test_probe_matches_oracle(tilt, elevation, native, built_library):
     ok = clear & same_iface & (ref["hit"] > 0)
     assert ok.sum() > 1000
     d_rel = np.abs(gpu["distance"][ok] - ref["distance"][ok]) / ref["distance"][ok]
-    tol = REL if tilt == 0 else 1e-4   # a tilted plate adds the float rounding of the world->plate rotation
+    tol = REL   # holds for the tilted plate too: the world->plate rotation is applied in double on the host
     assert np.quantile(d_rel, 0.99) < tol, f"distance rel err p99 {np.quantile(d_rel, 0.99):.2e}"
     assert np.median(d_rel) < 2e-6
     r_err = np.abs(gpu["reflectivity"][ok] - ref["reflectivity"][ok])
