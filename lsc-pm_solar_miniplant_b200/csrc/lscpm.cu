@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -170,6 +171,276 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
     if (hbatch >= 0) flush_row(hist, A.tallies + (size_t)hbatch * stride, stride, lane);
 }
 
+// K2s: block-sorted persistent photon kernel.  Photons in a warp stop doing the same thing after the common half of
+// an iteration (advance): some meet a flat face, some a tube wall, some are absorbed, some need a new photon.  Left in
+// place they serialise (the lane-per-photon kernel above averages 15.6 of 32 active lanes).  Here every iteration the
+// whole block re-deals its photons through shared memory so that each warp holds (mostly) one class of pending work:
+// a counting sort over N_CLS classes (warp match -> per-warp 16-bit counts -> one packed 2-entries-per-lane scan that
+// every warp repeats for itself), a scatter of the 20-word photon record to its sorted slot, a linear read back.
+// New photon indices go to the FRESH class by rank from a double-buffered block-level work cursor (current + prefetched
+// work item, refilled by thread 0 with one global atomic per item); the tally of a photon that ended is made by the
+// FRESH class as well, warp-aggregated, into one shared-memory row per block for the batch of the current work item.
+#ifndef SORT_BLOCK
+#define SORT_BLOCK 256
+#endif
+constexpr int SORT_THREADS = SORT_BLOCK;
+#ifndef SORT_MIN_BLOCKS
+#define SORT_MIN_BLOCKS (1024 / SORT_BLOCK)
+#endif
+
+#ifdef SORT_TIMING   // diagnostic build: where do the warps of a block spend an iteration?
+__device__ unsigned long long g_sort_timing[64];
+#endif
+
+struct WorkCursor {
+    unsigned long long cur_base, nxt_base;
+    unsigned cur_left, nxt_left;
+    int cur_batch, nxt_batch;
+    int more, pad;
+};
+
+template <int BLOCK>
+struct SortShared {
+    uint4 x[5][BLOCK];
+    unsigned short counts[64];
+    WorkCursor cursor[2];
+};
+
+__device__ __forceinline__ void claim_item(const TraceArgs& A, unsigned long long& base, unsigned& left, int& batch, int& more) {
+    left = 0;
+    if (!more) return;
+    const unsigned long long id = atomicAdd(A.work_counter, 1ULL);
+    if (id >= A.n_chunks) { more = 0; return; }
+    batch = (int)(id / A.chunks_per_batch);
+    const unsigned long long first = (id % A.chunks_per_batch) * (unsigned long long)A.chunk;
+    base = A.photon_begin + first;
+    left = (unsigned)min((unsigned long long)A.chunk, A.photon_count - first);
+}
+
+template <bool EXT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, SORT_MIN_BLOCKS)
+trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceArgs A) {
+    constexpr int NW = BLOCK / 32;
+    static_assert(N_CLS * NW <= 64, "class table must fit two 16-bit entries per lane");
+    __shared__ SortShared<BLOCK> sm;
+    extern __shared__ unsigned int hist[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lane_lt = (1u << lane) - 1u;
+    const int stride = S.n_bins + LSCPM_N_COUNTERS;
+    for (int b = tid; b < stride; b += BLOCK) hist[b] = 0u;
+    if (tid < 64) sm.counts[tid] = 0;
+    if (tid == 0) {
+        WorkCursor c;
+        c.more = 1; c.cur_batch = c.nxt_batch = 0; c.cur_base = c.nxt_base = 0; c.pad = 0;
+        claim_item(A, c.cur_base, c.cur_left, c.cur_batch, c.more);
+        claim_item(A, c.nxt_base, c.nxt_left, c.nxt_batch, c.more);
+        sm.cursor[0] = c;
+    }
+    __syncthreads();
+    int hbatch = -1;                        // block-uniform: batch whose photons the shared row accumulates
+    int it = 0;                             // iteration parity selects the cursor copy
+
+    Photon p;
+    p.xr = p.y = p.z = p.dx = p.dy = p.dz = p.wl = p.a_plate = p.a_outer = p.a_inner = 0.f;
+    p.kc = p.medium = p.steps = p.aux = 0;
+    Rng rng;
+    rng.key = A.key; rng.p_lo = rng.p_hi = rng.batch = rng.calls = 0;
+    int batch = 0;
+    unsigned n_events = 0;                  // low 16 bits: interaction events, high 16 bits: emissions
+    unsigned pend = CLS_FRESH;              // pending interaction (class in the low 4 bits)
+    float u_surf = 0.f;
+    uint32_t w_z = 0;
+    int pbin = -1;                          // FRESH class: tally bin of the photon this lane has just finished
+
+#ifdef SORT_TIMING
+    long long t_work = 0, t_wait = 0, t_sort = 0, t_mark = clock64(), n_it = 0;
+    long long t_cls[N_CLS] = {0}, n_cls[N_CLS] = {0}, t_mixed = 0, n_mixed = 0;   // g_sort_timing[8 + 2c], [9 + 2c]; mixed at [30], [31]
+    int wcls = -1;
+#endif
+    for (;; it ^= 1) {
+        int cls = pend & 15;
+        // ---- counting sort of the block's photons by class ------------------------------------------
+        const unsigned mine = __match_any_sync(FULL_MASK, cls);
+#ifdef SORT_TIMING
+        { const long long now = clock64(); const long long d = now - t_mark; t_work += d; t_mark = now; ++n_it;
+          if (wcls >= 0) { t_cls[wcls] += d; ++n_cls[wcls]; } else if (wcls == -2) { t_mixed += d; ++n_mixed; } }
+#endif
+        if (lane < N_CLS) sm.counts[lane * NW + warp] = 0;
+        __syncwarp();
+        if ((mine & lane_lt) == 0u) sm.counts[cls * NW + warp] = (unsigned short)__popc(mine);
+        __syncthreads();
+#ifdef SORT_TIMING
+        { const long long now = clock64(); t_wait += now - t_mark; t_mark = now; }
+#endif
+        // packed exclusive scan of the class-major table: lane L owns entries 2L (low half) and 2L+1 (high half)
+        const unsigned word = reinterpret_cast<const unsigned*>(sm.counts)[lane];
+        const unsigned lo = word & 0xffffu, pair = lo + (word >> 16);
+        unsigned incl = pair;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned t = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const unsigned pre = (incl - pair) | ((incl - pair + lo) << 16);
+        const int entry = cls * NW + warp;
+        const unsigned base_word = __shfl_sync(FULL_MASK, pre, entry >> 1);
+        const int dest = (int)((entry & 1) ? base_word >> 16 : base_word & 0xffffu) + __popc(mine & lane_lt);
+        constexpr int E_FRESH = CLS_FRESH * NW, E_AFTER = (CLS_FRESH + 1) * NW, E_IDLE = CLS_IDLE * NW;
+        const unsigned w_fresh = __shfl_sync(FULL_MASK, pre, E_FRESH >> 1), w_after = __shfl_sync(FULL_MASK, pre, E_AFTER >> 1);
+        const unsigned w_idle = __shfl_sync(FULL_MASK, pre, E_IDLE >> 1);
+        const int fresh_begin = (int)((E_FRESH & 1) ? w_fresh >> 16 : w_fresh & 0xffffu);
+        const int fresh_end = (int)((E_AFTER & 1) ? w_after >> 16 : w_after & 0xffffu);
+        const int idle_begin = (int)((E_IDLE & 1) ? w_idle >> 16 : w_idle & 0xffffu);
+        if (idle_begin == 0) break;                      // every lane of the block is out of work
+        LSCPM_CHECK(dest >= 0 && dest < BLOCK);
+        // ---- the shared tally row follows the batch of the current work item --------------------------
+        const int target = sm.cursor[it].cur_batch;
+        if (target != hbatch) {
+            if (hbatch >= 0) {
+                unsigned long long* row = A.tallies + (size_t)hbatch * stride;
+                for (int b = tid; b < stride; b += BLOCK) {
+                    const unsigned int v = hist[b];
+                    if (v) { atomicAdd(row + b, (unsigned long long)v); hist[b] = 0u; }
+                }
+            }
+            hbatch = target;
+        }
+        // ---- re-deal --------------------------------------------------------------------------------
+        sm.x[0][dest] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z), __float_as_uint(p.dx));
+        sm.x[1][dest] = make_uint4(__float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl), __float_as_uint(p.a_plate));
+        sm.x[2][dest] = make_uint4(__float_as_uint(p.a_outer), __float_as_uint(p.a_inner),
+                                   (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16), (unsigned)p.aux);
+        sm.x[3][dest] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.calls);
+        sm.x[4][dest] = make_uint4(n_events, pend, cls == CLS_FRESH ? (unsigned)pbin : __float_as_uint(u_surf), w_z);
+        __syncthreads();
+        {
+            const uint4 q0 = sm.x[0][tid], q1 = sm.x[1][tid], q2 = sm.x[2][tid], q3 = sm.x[3][tid], q4 = sm.x[4][tid];
+            p.xr = __uint_as_float(q0.x); p.y = __uint_as_float(q0.y); p.z = __uint_as_float(q0.z); p.dx = __uint_as_float(q0.w);
+            p.dy = __uint_as_float(q1.x); p.dz = __uint_as_float(q1.y); p.wl = __uint_as_float(q1.z); p.a_plate = __uint_as_float(q1.w);
+            p.a_outer = __uint_as_float(q2.x); p.a_inner = __uint_as_float(q2.y);
+            p.kc = q2.z & 0xfff; p.medium = (q2.z >> 12) & 15; p.steps = q2.z >> 16; p.aux = (int)q2.w;
+            rng.p_lo = q3.x; rng.p_hi = q3.y; batch = (int)q3.z; rng.calls = q3.w;
+            n_events = q4.x; pend = q4.y; u_surf = __uint_as_float(q4.z); w_z = q4.w;
+            pbin = (int)q4.z;
+        }
+        cls = pend & 15;
+#ifdef SORT_TIMING
+        { const long long now = clock64(); t_sort += now - t_mark; t_mark = now;
+          const unsigned same = __match_any_sync(FULL_MASK, cls); wcls = same == FULL_MASK ? cls : -2; }
+#endif
+        const WorkCursor& cur = sm.cursor[it];
+        if (tid == 0) {
+            // next iteration's cursor: consume the indices the FRESH class takes below, keep two work items in hand
+            WorkCursor c = cur;
+            unsigned n = (unsigned)(fresh_end - fresh_begin);
+            unsigned take = min(n, c.cur_left); c.cur_base += take; c.cur_left -= take; n -= take;
+            take = min(n, c.nxt_left); c.nxt_base += take; c.nxt_left -= take;
+            while (c.cur_left == 0u && (c.nxt_left > 0u || c.more)) {
+                c.cur_base = c.nxt_base; c.cur_left = c.nxt_left; c.cur_batch = c.nxt_batch;
+                claim_item(A, c.nxt_base, c.nxt_left, c.nxt_batch, c.more);
+            }
+            sm.cursor[it ^ 1] = c;
+        }
+        // ---- tallies of the photons that ended, warp-aggregated (the FRESH class holds them) -----------
+        {
+            const bool have = cls == CLS_FRESH && pbin >= 0;
+            if (__any_sync(FULL_MASK, have)) {
+                LSCPM_CHECK(!have || pbin < S.n_bins);
+                const bool local = have && batch == hbatch;
+                const unsigned grp = __match_any_sync(FULL_MASK, local ? pbin : -1);
+                if (local && (grp & lane_lt) == 0u) atomicAdd(hist + pbin, (unsigned)__popc(grp));
+                const unsigned ev = __reduce_add_sync(FULL_MASK, local ? (n_events & 0xffffu) : 0u);
+                const unsigned em = __reduce_add_sync(FULL_MASK, local ? (n_events >> 16) : 0u);
+                if (lane == 0) {
+                    if (ev) atomicAdd(hist + S.n_bins, ev);
+                    if (em) atomicAdd(hist + S.n_bins + 1, em);
+                }
+                if (have && !local) {
+                    unsigned long long* row = A.tallies + (size_t)batch * stride;
+                    atomicAdd(row + pbin, 1ULL);
+                    atomicAdd(row + S.n_bins, (unsigned long long)(n_events & 0xffffu));
+                    if (n_events >> 16) atomicAdd(row + S.n_bins + 1, (unsigned long long)(n_events >> 16));
+                }
+            }
+        }
+        // ---- the pending interaction, one class per warp (mostly) ------------------------------------
+        int bin = -1;
+        bool fly = false, source = false, fresh = false;
+        if (cls == CLS_FRESH) {
+            pbin = -1;
+            const unsigned r = (unsigned)(tid - fresh_begin);
+            unsigned long long g = 0; int nb = -1;
+            if (r < cur.cur_left) { g = cur.cur_base + r; nb = cur.cur_batch; }
+            else if (r - cur.cur_left < cur.nxt_left) { g = cur.nxt_base + (r - cur.cur_left); nb = cur.nxt_batch; }
+            if (nb >= 0) {
+                batch = nb;
+                rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32); rng.calls = 0;
+                n_events = 0;
+                source = fresh = true;
+            } else if (!cur.more && cur.cur_left + cur.nxt_left == 0u) {
+                pend = CLS_IDLE;
+            }
+        } else if (cls == CLS_ABSORB) {
+            n_events += 1u;
+            bin = interact_absorb(S, p, pend, u_surf, w_z);
+            if (bin < 0) { n_events += 0x10000u; source = true; }   // re-emitted by the luminophore
+        } else if (cls == CLS_FLAT || cls == CLS_CYL) {
+            n_events += 1u;
+            bin = interact_surface<EXT>(S, p, pend, u_surf);
+            fly = bin < 0;
+        } else if (cls == CLS_CELL) {
+            fly = true;
+        } else if (EXT && cls == CLS_OUT) {
+            OutState q;
+            q.x = abs_x(S, p); q.y = p.y; q.z = p.z + S.zc; q.dx = p.dx; q.dy = p.dy; q.dz = p.dz; q.aux = p.aux; q.steps = p.steps;
+            const OutResult r = outside_step(S, q, u_surf);
+            p.dx = r.dx; p.dy = r.dy; p.dz = r.dz; p.aux = r.aux; p.steps = r.steps;
+            if (counts_as_event(r.event)) n_events += 1u + (unsigned)r.extra;
+            if (r.entered) { p.y = r.y; locate_in_plate(S, p, r.x, r.z); }
+            else { p.kc = 0; p.xr = r.x - axis_x(S, 0); p.y = r.y; p.z = r.z - S.zc; }
+            bin = r.bin;
+            fly = bin < 0;
+        }
+        // ---- source: a new photon or a re-emission --------------------------------------------------------
+        if (source) {
+            rng.batch = A.batches[batch].batch_id;
+            const uint4 v = rng.next();
+            WavelengthDraw wd;
+            if (fresh) bin = source_fresh<EXT>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr);
+            else source_emit(S, v, p, wd);
+            source_finish(S, p, wd);
+#ifdef SORT_SPLIT_SOURCE   // the advance of a (re-)emitted photon waits for the next deal: +1..4 % on the standard scene, -25 % with outside boxes
+            if (bin < 0) pend = CLS_CELL;
+#else
+            fly = bin < 0;
+#endif
+        }
+        // ---- common half of the next iteration ---------------------------------------------------------
+        if (fly) {
+            rng.batch = A.batches[batch].batch_id;
+            const uint4 w = rng.next();
+            u_surf = u01(w.y); w_z = w.z;
+            bin = advance<EXT>(S, p, w.x, pend);
+        }
+        if (bin >= 0) { pend = CLS_FRESH; pbin = bin; }
+    }
+    if (hbatch >= 0) {
+        unsigned long long* row = A.tallies + (size_t)hbatch * stride;
+        for (int b = tid; b < stride; b += BLOCK) {
+            const unsigned int v = hist[b];
+            if (v) atomicAdd(row + b, (unsigned long long)v);
+        }
+    }
+#ifdef SORT_TIMING
+    if (lane == 0) {
+        atomicAdd(&g_sort_timing[0], (unsigned long long)t_work); atomicAdd(&g_sort_timing[1], (unsigned long long)t_wait);
+        atomicAdd(&g_sort_timing[2], (unsigned long long)t_sort); atomicAdd(&g_sort_timing[3], (unsigned long long)n_it);
+        for (int c = 0; c < N_CLS; ++c) { atomicAdd(&g_sort_timing[8 + 2 * c], (unsigned long long)t_cls[c]); atomicAdd(&g_sort_timing[9 + 2 * c], (unsigned long long)n_cls[c]); }
+        atomicAdd(&g_sort_timing[40], (unsigned long long)t_mixed); atomicAdd(&g_sort_timing[41], (unsigned long long)n_mixed);
+    }
+#endif
+}
+
 // K1 (debug/emit): the rays a batch generates, in plate-local coordinates
 __global__ void emit_kernel(const __grid_constant__ DevScene S, const DevBatch* batch, const float* spec_x,
                             const float* spec_cdf, const unsigned short* spec_guide, unsigned long long photon_begin,
@@ -247,7 +518,7 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
         if (h.kind == SURF_BOX || h.kind == SURF_CAP) {
             box_normal(h.face, nx, ny, nz);
             if (S.n_ext > 0) {
-                const int e = ext_ahead(S, axis_x(S, p.kc) + xr, yy, zz + S.zc, p.dx, p.dy, p.dz);
+                const int e = ext_ahead(S, h.face, axis_x(S, p.kc) + xr, yy, zz + S.zc, p.dx, p.dy, p.dz);
                 if (e >= 0) ext_node = -(e + 1);
             }
         } else {
@@ -460,6 +731,10 @@ struct LscpmScene {
     std::atomic<unsigned> next_counter{0};
     int n_sm = 0, blocks_per_sm = 0;
     size_t trace_smem = 0;
+    bool sorted = false;                 // block-sorted kernel or the lane-per-photon kernel
+    bool sorted_forced = false;
+    int sort_blocks_per_sm = 0;
+    size_t sort_smem = 0;
 };
 constexpr int COUNTER_RING = 256;
 
@@ -663,6 +938,16 @@ int lower_scene(const LscpmSceneDesc* d, LscpmScene* s) {
         b.n = (float)d->mat_refractive_index[d->node_material[node]];
         b.abs_bin = s->layout.abs_base[node];
         b.exit_base = s->layout.exit_base[node];
+    }
+    for (int f = 0; f < 6; ++f) {
+        D.ext_beyond[f] = 0u;
+        const double plate_half[3] = {(double)D.hx, (double)D.hy, (double)D.hz};
+        const int ax = f / 2;
+        for (int e = 0; e < D.n_ext; ++e) {
+            const double c[3] = {ext_centres[e].x, ext_centres[e].y, ext_centres[e].z}, h[3] = {ext_halves[e].x, ext_halves[e].y, ext_halves[e].z};
+            const bool beyond = (f & 1) ? (c[ax] + h[ax] > plate_half[ax] + (double)EXT_TOL) : (c[ax] - h[ax] < -plate_half[ax] - (double)EXT_TOL);
+            if (beyond) D.ext_beyond[f] |= 1u << e;
+        }
     }
     s->bin_names.resize(D.n_bins);
     for (int b = 0; b < D.n_bins; ++b) s->bin_names[b] = bin_name(d, b);
@@ -931,6 +1216,23 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
                                                            TRACE_THREADS, s->trace_smem)) != cudaSuccess)
         return bail(cuda_fail(e, "occupancy query (is the library built for this GPU's architecture?)"));
     if (s->blocks_per_sm < 1) return bail(fail(LSCPM_ECUDA, "trace kernel does not fit on an SM"));
+    // The block-sorted kernel wins where photons do very different amounts of work per iteration (scenes with outside
+    // boxes: +40..60 %); on the standard scene the two are within a few per cent and the lane kernel has no barriers.
+    // LSCPM_TRACE_KERNEL=lanes|sorted forces one (the tallies are bit-identical either way).
+    const char* which = getenv("LSCPM_TRACE_KERNEL");
+    s->sorted = s->dev.n_ext > 0;
+    if (which && strcmp(which, "lanes") == 0) s->sorted = false;
+    if (which && strcmp(which, "sorted") == 0) s->sorted = true;
+    s->sorted_forced = which && strcmp(which, "sorted") == 0;
+    s->sort_smem = (size_t)(s->dev.n_bins + LSCPM_N_COUNTERS) * sizeof(unsigned int);
+    if (s->sort_smem > 24 * 1024) s->sorted = false;    // static exchange buffer + row must stay under 48 KB
+    if (s->sorted) {
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                 &s->sort_blocks_per_sm, s->dev.n_ext > 0 ? trace_sorted_kernel<true, SORT_THREADS> : trace_sorted_kernel<false, SORT_THREADS>,
+                 SORT_THREADS, s->sort_smem)) != cudaSuccess)
+            return bail(cuda_fail(e, "occupancy query (sorted kernel)"));
+        if (s->sort_blocks_per_sm < 1) return bail(fail(LSCPM_ECUDA, "sorted trace kernel does not fit on an SM"));
+    }
     *out = s;
     return LSCPM_OK;
 }
@@ -1023,24 +1325,52 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
     TraceArgs a{};
     a.batches = p->d_batches; a.spec_x = p->d_spec_x; a.spec_cdf = p->d_spec_cdf; a.spec_guide = p->d_spec_guide;
     a.photon_begin = photon_begin; a.photon_count = photon_count;
-    const int grid = s->n_sm * s->blocks_per_sm;
-    const unsigned long long n_warps = (unsigned long long)grid * (TRACE_THREADS / 32);
+    a.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    a.tallies = (unsigned long long*)tallies_dev;
     const unsigned long long total = photon_count * (unsigned long long)p->n_batches;
-    unsigned long long chunk = total / (n_warps * 8ULL);
-    chunk = std::min<unsigned long long>(std::max<unsigned long long>(chunk, 32ULL), 4096ULL);
+    // launches too small to fill the sorted kernel's blocks a few times over go to the lane kernel
+    const bool sorted = s->sorted && (s->sorted_forced || total >= 4ULL * (unsigned long long)(s->n_sm * s->sort_blocks_per_sm) * SORT_THREADS);
+    const int per_sm = sorted ? s->sort_blocks_per_sm : s->blocks_per_sm;
+    const int grid = s->n_sm * per_sm;
+    // work items: claimed by a block (sorted kernel) or by a warp (lane kernel); ~8 items per claimer, within a batch
+    const unsigned long long claimers = sorted ? (unsigned long long)grid : (unsigned long long)grid * (TRACE_THREADS / 32);
+    const unsigned long long lo = sorted ? (unsigned long long)SORT_THREADS : 32ULL, hi = sorted ? 16384ULL : 4096ULL;
+    unsigned long long chunk = total / (claimers * 8ULL);
+    chunk = std::min<unsigned long long>(std::max<unsigned long long>(chunk, lo), hi);
     chunk = std::min<unsigned long long>((chunk + 31ULL) / 32ULL * 32ULL, std::max<unsigned long long>(photon_count, 1ULL));
     a.chunk = (unsigned)chunk;
     a.chunks_per_batch = (photon_count + chunk - 1) / chunk;
     a.n_chunks = a.chunks_per_batch * (unsigned long long)p->n_batches;
-    a.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    a.tallies = (unsigned long long*)tallies_dev;
     int rc = pick_counter(s, stream, &a.work_counter);
     if (rc) return rc;
-    const int blocks = (int)std::min<unsigned long long>((unsigned long long)grid, (a.n_chunks + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32));
-    if (s->dev.n_ext > 0) trace_kernel<true><<<std::max(blocks, 1), TRACE_THREADS, s->trace_smem, stream>>>(s->dev, a);
-    else trace_kernel<false><<<std::max(blocks, 1), TRACE_THREADS, s->trace_smem, stream>>>(s->dev, a);
+    if (sorted) {
+        // a block drinks from two work items at a time; tiny launches need fewer blocks than the grid
+        const unsigned long long want = (total + SORT_THREADS - 1) / SORT_THREADS;
+        const int blocks = (int)std::max<unsigned long long>(1ULL, std::min<unsigned long long>((unsigned long long)grid, want));
+        if (s->dev.n_ext > 0) trace_sorted_kernel<true, SORT_THREADS><<<blocks, SORT_THREADS, s->sort_smem, stream>>>(s->dev, a);
+        else trace_sorted_kernel<false, SORT_THREADS><<<blocks, SORT_THREADS, s->sort_smem, stream>>>(s->dev, a);
+    } else {
+        const int blocks = (int)std::min<unsigned long long>((unsigned long long)grid, (a.n_chunks + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32));
+        if (s->dev.n_ext > 0) trace_kernel<true><<<std::max(blocks, 1), TRACE_THREADS, s->trace_smem, stream>>>(s->dev, a);
+        else trace_kernel<false><<<std::max(blocks, 1), TRACE_THREADS, s->trace_smem, stream>>>(s->dev, a);
+    }
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
+#ifdef SORT_TIMING
+    if (sorted) {
+        unsigned long long t[64];
+        cudaStreamSynchronize(stream);
+        cudaMemcpyFromSymbol(t, g_sort_timing, sizeof(t));
+        fprintf(stderr, "[sort timing] warp-iterations %llu: work %.0f wait %.0f sort %.0f cycles/iteration\n", t[3],
+                (double)t[0] / t[3], (double)t[1] / t[3], (double)t[2] / t[3]);
+        const char* names[] = {"flat", "cyl", "cell", "absorb", "fresh", "out", "idle"};
+        for (int c = 0; c < N_CLS; ++c)
+            if (t[9 + 2 * c]) fprintf(stderr, "  pure %-6s warps: %5.1f%% of warp-iterations, %.0f cycles\n", names[c], 100.0 * t[9 + 2 * c] / t[3], (double)t[8 + 2 * c] / t[9 + 2 * c]);
+        if (t[41]) fprintf(stderr, "  mixed       warps: %5.1f%% of warp-iterations, %.0f cycles\n", 100.0 * t[41] / t[3], (double)t[40] / t[41]);
+        memset(t, 0, sizeof(t));
+        cudaMemcpyToSymbol(g_sort_timing, t, sizeof(t));
+    }
+#endif
     return LSCPM_OK;
 }
 

@@ -116,6 +116,7 @@ struct DevScene {
     DevMedium med[5];          // indexed by MED_*; med[MED_AIR] and med[MED_OUT] carry the world's refractive index only
     int n_ext;                 // outside boxes (0 for the standard scene: none of the MED_OUT code runs then)
     DevExtBox ext[MAX_EXT];
+    unsigned ext_beyond[6];    // per plate face: bit i set when outside box i reaches beyond that face's plane
     DevTable tab[MAX_TABLES];
     const float* tab_x;        // concatenated knot tables (scene spectra)
     const float* tab_y;
@@ -638,11 +639,19 @@ __device__ __forceinline__ void source_finish(const DevScene& S, Photon& p, cons
 // scenes with boxes outside the plate (photovoltaic absorbers): the air around the plate becomes a medium with
 // geometry of its own.  All of this is out of line and only runs when S.n_ext > 0.
 // ------------------------------------------------------------------------------------------------
+// the ray's reciprocal direction is computed once per ray (RayInv) and shared by every box tested
+struct RayInv { float ix, iy, iz; };
+__device__ __forceinline__ RayInv ray_inverse(float dx, float dy, float dz) {
+    RayInv r;
+    r.ix = dx != 0.f ? frcp(dx) : 0.f; r.iy = dy != 0.f ? frcp(dy) : 0.f; r.iz = dz != 0.f ? frcp(dz) : 0.f;
+    return r;
+}
+
 __device__ __forceinline__ void slab_interval(float cx, float cy, float cz, float hx, float hy, float hz, float ox, float oy,
-                                              float oz, float dx, float dy, float dz, float& tmin, float& tmax, int& fmin,
-                                              int& fmax) {
+                                              float oz, float dx, float dy, float dz, const RayInv& inv, float& tmin, float& tmax,
+                                              int& fmin, int& fmax) {
     tmin = -LSCPM_INF; tmax = LSCPM_INF; fmin = 0; fmax = 0;
-    const float c[3] = {cx, cy, cz}, h[3] = {hx, hy, hz}, o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz};
+    const float c[3] = {cx, cy, cz}, h[3] = {hx, hy, hz}, o[3] = {ox, oy, oz}, d[3] = {dx, dy, dz}, iv[3] = {inv.ix, inv.iy, inv.iz};
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
         const float rel = o[ax] - c[ax];
@@ -650,9 +659,10 @@ __device__ __forceinline__ void slab_interval(float cx, float cy, float cz, floa
             if (fabsf(rel) > h[ax]) { tmin = LSCPM_INF; tmax = -LSCPM_INF; }
             continue;
         }
-        float tlo = (-h[ax] - rel) / d[ax], thi = (h[ax] - rel) / d[ax];
-        int flo = 2 * ax, fhi = 2 * ax + 1;
-        if (tlo > thi) { const float tt = tlo; tlo = thi; thi = tt; flo = 2 * ax + 1; fhi = 2 * ax; }
+        const float ta = (-h[ax] - rel) * iv[ax], tb = (h[ax] - rel) * iv[ax];
+        const bool fwd = d[ax] > 0.f;                    // entering through the low face, leaving through the high one
+        const float tlo = fwd ? ta : tb, thi = fwd ? tb : ta;
+        const int flo = 2 * ax + (fwd ? 0 : 1), fhi = 2 * ax + (fwd ? 1 : 0);
         if (tlo > tmin) { tmin = tlo; fmin = flo; }
         if (thi < tmax) { tmax = thi; fmax = fhi; }
     }
@@ -664,13 +674,20 @@ __device__ __forceinline__ float normal_gap(float t, int f, float dx, float dy, 
 }
 
 // first outside box met by the straight line from (ox,oy,oz) along d, a box starting at distance ~0 included
-// (pvtrace's `adjacent = intersections[1]` for a photon leaving the plate: ties sort the plate first)
-__device__ __noinline__ int ext_ahead(const DevScene& S, float ox, float oy, float oz, float dx, float dy, float dz) {
+// (pvtrace's `adjacent = intersections[1]` for a photon leaving the plate: ties sort the plate first).  `face` is the
+// plate face the photon is on: only boxes reaching beyond that face's plane can lie ahead (S.ext_beyond[face]; for the
+// photovoltaic variants none beyond the top face, one beyond each of the others).
+__device__ __noinline__ int ext_ahead(const DevScene& S, int face, float ox, float oy, float oz, float dx, float dy, float dz) {
     int best = -1; float tbest = LSCPM_INF;
-    for (int i = 0; i < S.n_ext; ++i) {
+    unsigned todo = S.ext_beyond[face];
+    if (!todo) return best;
+    const RayInv inv = ray_inverse(dx, dy, dz);
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1u;
         const DevExtBox& b = S.ext[i];
         float tmin, tmax; int f, fx;
-        slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, ox, oy, oz, dx, dy, dz, tmin, tmax, f, fx);
+        slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, ox, oy, oz, dx, dy, dz, inv, tmin, tmax, f, fx);
         if (tmin <= tmax && tmax > 0.f && normal_gap(tmin, f, dx, dy, dz) > -EXT_TOL && tmin < tbest) {
             tbest = tmin; best = i;
         }
@@ -686,11 +703,12 @@ __device__ __noinline__ int ext_ahead(const DevScene& S, float ox, float oy, flo
 __device__ __forceinline__ bool outside_hit(const DevScene& S, float x, float y, float z, float dx, float dy, float dz, int skip,
                                             float& t_best, int& node, int& face) {
     t_best = LSCPM_INF; node = -1; face = 0;
+    const RayInv inv = ray_inverse(dx, dy, dz);
     for (int i = 0; i < S.n_ext; ++i) {
         if (i + 1 == skip) continue;
         const DevExtBox& b = S.ext[i];
         float tmin, tmax; int f, fx;
-        slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, x, y, z, dx, dy, dz, tmin, tmax, f, fx);
+        slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, x, y, z, dx, dy, dz, inv, tmin, tmax, f, fx);
         if (!(tmin <= tmax) || !(tmax > 0.f)) continue;
         // on its face (gap along the face normal within EXT_TOL: coincident faces differ by float rounding), heading in
         if (normal_gap(tmin, f, dx, dy, dz) <= EXT_TOL) { t_best = 0.f; node = i + 1; face = f; return true; }
@@ -698,7 +716,7 @@ __device__ __forceinline__ bool outside_hit(const DevScene& S, float x, float y,
     }
     if (skip != 0) {
         float tmin, tmax; int f, fx;
-        slab_interval(0.f, 0.f, 0.f, S.hx, S.hy, S.hz, x, y, z, dx, dy, dz, tmin, tmax, f, fx);
+        slab_interval(0.f, 0.f, 0.f, S.hx, S.hy, S.hz, x, y, z, dx, dy, dz, inv, tmin, tmax, f, fx);
         if (tmin <= tmax && tmax > 0.f && normal_gap(tmin, f, dx, dy, dz) > EXT_TOL && tmin < t_best) { t_best = tmin; node = 0; face = f; }
     }
     return false;
@@ -865,7 +883,7 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
     const bool leaving = flat && p.medium != MED_AIR;
     if (EXT && leaving) {
         // adjacent = second intersection along the ray: an outside box straight ahead (even across an air gap) lends its index
-        const int e = ext_ahead(S, abs_x(S, p), p.y, p.z + S.zc, p.dx, p.dy, p.dz);
+        const int e = ext_ahead(S, h.face, abs_x(S, p), p.y, p.z + S.zc, p.dx, p.dy, p.dz);
         if (e >= 0) n2 = S.ext[e].n;
     }
     const float n1 = S.med[h.container].n;
@@ -892,6 +910,131 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
         return (p.steps + 1 > MAXSTEPS) ? BIN_KILL : S.exit_base_plate + h.face;
     }
     if (h.kind == SURF_OUTER) p.medium = (p.medium == MED_PLATE) ? MED_OUTER : MED_PLATE;
+    else p.medium = (p.medium == MED_OUTER) ? MED_INNER : MED_OUTER;
+    return -1;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// The same follow() iteration cut where photons stop doing the same thing, for the block-sorted kernel:
+// `advance` (nearest interface, free path, move: identical work for every photon in flight) ends by naming the
+// interaction the photon is waiting for, the `interact_*` functions carry it out.  advance + interact_* performs
+// exactly the arithmetic of photon_step, with the same Philox draw.
+// ------------------------------------------------------------------------------------------------
+// class order = deal order: FLAT and CYL share the Fresnel code, CELL has no work of its own, ABSORB and FRESH share the source code
+constexpr int CLS_FLAT = 0, CLS_CYL = 1, CLS_CELL = 2, CLS_ABSORB = 3, CLS_FRESH = 4, CLS_OUT = 5, CLS_IDLE = 6, N_CLS = 7;
+
+// pending-interaction word: class | surface kind | face + 1 | container | adjacent | sibling flag
+__device__ __forceinline__ unsigned pack_pending(int cls, int kind, int face, int container, int adj, bool sibling) {
+    return (unsigned)cls | ((unsigned)kind << 4) | ((unsigned)(face + 1) << 7) | ((unsigned)container << 11) |
+           ((unsigned)adj << 14) | ((sibling ? 1u : 0u) << 17);
+}
+__device__ __forceinline__ int pending_kind(unsigned w) { return (w >> 4) & 7; }
+__device__ __forceinline__ int pending_face(unsigned w) { return (int)((w >> 7) & 15) - 1; }
+__device__ __forceinline__ int pending_container(unsigned w) { return (w >> 11) & 7; }
+__device__ __forceinline__ int pending_adj(unsigned w) { return (w >> 14) & 7; }
+__device__ __forceinline__ bool pending_sibling(unsigned w) { return (w >> 17) & 1; }
+
+// first half of the iteration; returns -1 or BIN_KILL (step limit)
+template <bool EXT>
+__device__ __forceinline__ int advance(const DevScene& S, Photon& p, const uint32_t w_x, unsigned& pend) {
+    if (EXT && p.medium == MED_OUT) { pend = CLS_OUT; return -1; }
+    Hit h;
+    if (p.medium == MED_AIR) {   // waiting on the plate face for its entry Fresnel test
+        h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false;
+    } else {
+        h = compute_hit(S, p);
+    }
+    p.steps += h.kind != SURF_CELL ? 1 : 0;
+    if (p.steps > MAXSTEPS) return BIN_KILL;
+    float alpha = 0.f;
+    alpha = h.container == MED_PLATE ? p.a_plate : alpha;
+    alpha = h.container == MED_OUTER ? p.a_outer : alpha;
+    alpha = h.container == MED_INNER ? p.a_inner : alpha;
+    const float depth = alpha <= ALPHA_ZERO ? LSCPM_INF : fdiv(-flog(one_minus_u01(w_x)), alpha);
+    const bool absorbed = depth < h.t;
+    const float travel = absorbed ? depth : h.t;
+    p.xr = fmaf(p.dx, travel, p.xr); p.y = fmaf(p.dy, travel, p.y); p.z = fmaf(p.dz, travel, p.z);
+    int cls = (h.kind == SURF_BOX || h.kind == SURF_CAP) ? CLS_FLAT : CLS_CYL;
+    if (h.kind == SURF_CELL) cls = CLS_CELL;
+    if (absorbed) cls = CLS_ABSORB;
+    if (cls == CLS_CELL) {   // step into the neighbouring cell; nothing physical happens here
+        p.kc += h.face;
+        LSCPM_CHECK(p.kc >= 0 && p.kc < S.n_ch);
+        p.xr = h.face > 0 ? -0.5f * S.pitch : 0.5f * S.pitch;
+    }
+    pend = pack_pending(cls, h.kind, h.face, h.container, h.adj, h.maybe_sibling);
+    return -1;
+}
+
+// absorbed inside the container: choose the component ~ alpha_i, radiative test.  Returns the tally bin, or -1 with
+// p.aux carrying the emission table when the luminophore re-emits.
+__device__ __forceinline__ int interact_absorb(const DevScene& S, Photon& p, unsigned pend, float u_pick, uint32_t w_z) {
+    const int container = pending_container(pend);
+    float alpha = 0.f;
+    alpha = container == MED_PLATE ? p.a_plate : alpha;
+    alpha = container == MED_OUTER ? p.a_outer : alpha;
+    alpha = container == MED_INNER ? p.a_inner : alpha;
+    const DevMedium& m = S.med[container];
+    const int index = pick_component(S, container, p.wl, alpha, u_pick * alpha);
+    const DevComponent& comp = m.comp[index];
+    if (comp.kind == COMP_LUMINOPHORE && u01(w_z) < comp.qy) {
+        p.aux = (p.aux & 0xffff) | (comp.ems_table << 16);
+        return -1;
+    }
+    LSCPM_CHECK(p.kc >= 0 && p.kc < S.n_ch && index >= 0 && index < m.n_comp);
+    const int base = container == MED_PLATE ? S.abs_base_plate
+                   : (container == MED_OUTER ? __ldg(S.abs_base_outer + p.kc) : __ldg(S.abs_base_inner + p.kc));
+    return base + index;
+}
+
+// Fresnel test at the interface the photon has been moved to; returns the tally bin or -1
+template <bool EXT>
+__device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, unsigned pend, float u_surf) {
+    const int kind = pending_kind(pend), face = pending_face(pend), container = pending_container(pend);
+    int adj = pending_adj(pend);
+    const bool flat = kind == SURF_BOX || kind == SURF_CAP;
+    float nx, ny, nz;
+    box_normal(face, nx, ny, nz);
+    if (flat) {
+        if (p.medium != MED_AIR) {   // snap the coordinate of the face that was hit
+            if (face < 2) { if (kind == SURF_BOX) p.xr = (face & 1) ? S.cell_hi_last : S.cell_lo_first; }
+            else if (face < 4) p.y = (face & 1) ? S.hy : -S.hy;
+            else p.z = ((face & 1) ? S.hz : -S.hz) - S.zc;
+        }
+    } else {
+        const float inv = frsqrt(fmaf(p.xr, p.xr, p.z * p.z));
+        nx = p.xr * inv; ny = 0.f; nz = p.z * inv;
+        if (pending_sibling(pend) && sibling_ahead(S, p.kc, p.xr, p.y, p.z, p.dx, p.dy, p.dz) >= 0) adj = MED_OUTER;
+    }
+    float n2 = S.med[adj].n;
+    const bool leaving = flat && p.medium != MED_AIR;
+    if (EXT && leaving) {
+        const int e = ext_ahead(S, face, abs_x(S, p), p.y, p.z + S.zc, p.dx, p.dy, p.dz);
+        if (e >= 0) n2 = S.ext[e].n;
+    }
+    const float n1 = S.med[container].n;
+    const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, n1, n2);
+    const bool reflected = u_surf < I.R;
+    if (reflected) reflect_dir(p, I); else refract_dir(p, I);
+    if (p.medium == MED_AIR) {
+        if (reflected) return BIN_ENTRY_REFLECT;
+        p.medium = (p.aux >> 4) & 3;
+        return -1;
+    }
+    if (EXT) p.aux = note_surface(p.aux, false, 0, face, leaving && !reflected);
+    if (reflected) return -1;
+    if (flat) {
+        if (EXT) {
+            const float xa = abs_x(S, p);
+            p.kc = 0; p.xr = xa - axis_x(S, 0);
+            p.medium = MED_OUT;
+            return -1;
+        }
+        p.medium = MED_AIR;
+        return (p.steps + 1 > MAXSTEPS) ? BIN_KILL : S.exit_base_plate + face;
+    }
+    if (kind == SURF_OUTER) p.medium = (p.medium == MED_PLATE) ? MED_OUTER : MED_PLATE;
     else p.medium = (p.medium == MED_OUTER) ? MED_INNER : MED_OUTER;
     return -1;
 }

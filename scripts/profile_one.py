@@ -1,0 +1,20 @@
+"""One warm-up and one measured launch of the trace kernel on the config-2 workload (for ncu captures)."""
+import sys, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+import lscpm_b200
+lscpm_b200.install()
+from lscpm_b200 import backend, flatten
+from helpers import standard_scene, am15_like_photon_spectrum
+
+nb = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+ppb = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
+arrays = flatten.flatten_scene(standard_scene(tilt=0, elevation=90, spectrum=am15_like_photon_spectrum()))
+scene = backend.SceneHandle(arrays, 0)
+plan = backend.Plan(scene, [arrays.light] * nb, list(range(nb)))
+tallies = plan.new_tallies()
+for seed in (1, 2):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); plan.trace_into(tallies, ppb, seed); e1.record(); torch.cuda.synchronize()
+    print(f"seed {seed}: {e0.elapsed_time(e1):.2f} ms  {nb * ppb / e0.elapsed_time(e1) / 1e3:.0f} Mphotons/s", flush=True)
