@@ -38,7 +38,6 @@ struct TraceArgs {
     uint2 key;
     unsigned long long* work_counter;
     unsigned long long* tallies;         // [n_batches][n_bins + LSCPM_N_COUNTERS]
-    unsigned int* error;                 // watchdog flag of the queue kernel
 };
 
 __device__ __forceinline__ bool counts_as_event(int ev) {
@@ -442,355 +441,6 @@ trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ 
 #endif
 }
 
-// K2q (experimental, LSCPM_TRACE_KERNEL=queue): barrier-free regrouping.  One 1024-thread block per SM; photon records
-// that wait for their next interaction sit in shared-memory PAGES of 32 records, one page stream per class.  A warp pops a
-// whole page of ONE class (so its 32 lanes do the same thing), runs the interaction and the common advance, and pushes
-// every record to the page stream of its new class: positions are reserved with one shared-memory atomic per class and
-// warp, the first record of a page allocates it from a 64-bit free mask, a per-page commit counter tells the consumer when
-// all reserved records have landed.  No block barrier: warps only ever wait for a producer that is between its
-// reservation and its commit.  Photon indices come from a block-level work cursor behind a spin lock; tallies go to
-// per-warp shared rows tagged with the block's current batch.  Every wait loop carries a watchdog that makes the kernel
-// give up (error flag) instead of hanging.
-constexpr int Q_THREADS = 1024, Q_WARPS = Q_THREADS / 32, Q_PAGES = 64, Q_RING = 256;   // Q_RING logical page slots per class
-constexpr unsigned Q_MAX_ACTIVE = 1408;     // records alive per block: 1024 in registers + 12 pages queued
-constexpr int Q_NONE = 15;                  // class of a lane without a record
-constexpr unsigned Q_WATCHDOG = 4000000u;
-
-struct QueueControl {
-    unsigned tail[8];                 // per class: records reserved so far (logical position)
-    unsigned head[8];                 // per class: logical pages claimed by consumers
-    unsigned commit[8][Q_RING];       // per class and logical page slot: records committed
-    unsigned ring[8][Q_RING];         // physical page of the slot, 0xFF = not allocated yet
-    unsigned free_mask[2];
-    unsigned active;                  // records alive in the block
-    unsigned lock;                    // work cursor lock
-    unsigned long long cur_base;
-    unsigned cur_left;
-    int cur_batch;
-    int more;
-    int error;
-};
-
-__device__ __forceinline__ unsigned ld_volatile(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
-
-__device__ __forceinline__ int queue_alloc_page(QueueControl& ctl) {
-    for (unsigned spins = 0; spins < Q_WATCHDOG; ++spins) {
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-            unsigned m = ld_volatile(&ctl.free_mask[w]);
-            while (m) {
-                const int b = __ffs(m) - 1;
-                const unsigned old = atomicAnd(&ctl.free_mask[w], ~(1u << b));
-                if (old & (1u << b)) return w * 32 + b;
-                m = old & ~(1u << b);
-            }
-        }
-        __nanosleep(64);
-    }
-    ctl.error = 1;
-    return 0;
-}
-
-template <bool EXT>
-__global__ void __launch_bounds__(Q_THREADS, 1)
-trace_queue_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceArgs A) {
-    extern __shared__ uint4 qsm[];
-    QueueControl& ctl = *reinterpret_cast<QueueControl*>(qsm);
-    uint4* pool = qsm + (sizeof(QueueControl) + 15) / 16;                       // [Q_PAGES][5][32]
-    unsigned int* hist_all = reinterpret_cast<unsigned int*>(pool + Q_PAGES * 5 * 32);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned lane_lt = (1u << lane) - 1u;
-    const int stride = S.n_bins + LSCPM_N_COUNTERS;
-    unsigned int* hist = hist_all + warp * stride;
-    {
-        unsigned* w = reinterpret_cast<unsigned*>(&ctl);
-        for (int i = tid; i < (int)(sizeof(QueueControl) / 4); i += Q_THREADS) w[i] = 0u;
-        for (int i = tid; i < Q_WARPS * stride; i += Q_THREADS) hist_all[i] = 0u;
-    }
-    __syncthreads();
-    for (int i = tid; i < 8 * Q_RING; i += Q_THREADS) (&ctl.ring[0][0])[i] = 0xFFu;
-    if (tid == 0) { ctl.free_mask[0] = ctl.free_mask[1] = 0xFFFFFFFFu; ctl.more = 1; }
-    __syncthreads();
-    int hb = -1;                            // warp-uniform: batch of this warp's shared tally row
-
-    Photon p;
-    p.xr = p.y = p.z = p.dx = p.dy = p.dz = p.wl = p.a_plate = p.a_outer = p.a_inner = 0.f;
-    p.kc = p.medium = p.steps = p.aux = 0;
-    Rng rng;
-    rng.key = A.key; rng.p_lo = rng.p_hi = rng.batch = rng.calls = 0;
-    int batch = 0;
-    unsigned n_events = 0, pend = 0;
-    float u_surf = 0.f;
-    uint32_t w_z = 0;
-    int pbin = -1;
-    unsigned idle_spins = 0, turn = 0;
-
-    for (;;) {
-        // ---- pick a page: the class with the most full pages, else new photons, else the fullest open page ----------
-        const unsigned t_c = lane < N_CLS ? ld_volatile(&ctl.tail[lane]) : 0u;
-        const unsigned h_c = lane < N_CLS ? ld_volatile(&ctl.head[lane]) : 0u;
-        const int full = max((int)(t_c >> 5) - (int)h_c, 0);
-        const int part = (t_c >> 5) == h_c ? (int)(t_c & 31u) : 0;
-        int cls = -1; unsigned L = 0; int n_valid = 0; bool virgin = false;
-        // among the classes with a full page prefer longer streams, rotate the rest of the preference over warps and turns
-        const unsigned score = full > 0 ? (unsigned)(min(full, 3) * 8 + ((lane + warp + (int)turn) & 7) + 1) : 0u;
-        ++turn;
-        const unsigned best = __reduce_max_sync(FULL_MASK, (score << 8) | (unsigned)lane);
-        if (best >> 8) {
-            const int c = (int)(best & 255u);
-            const unsigned h = __shfl_sync(FULL_MASK, h_c, c);
-            int ok = 0;
-            if (lane == 0) ok = atomicCAS(&ctl.head[c], h, h + 1u) == h;
-            ok = __shfl_sync(FULL_MASK, ok, 0);
-            if (!ok) continue;
-            cls = c; L = h; n_valid = 32;
-        } else {
-            // block state, read by lane 0 and broadcast so that every decision below is warp-uniform
-            unsigned st_error = 0, st_active = 0, st_work = 0;
-            if (lane == 0) {
-                st_error = ld_volatile(reinterpret_cast<const unsigned*>(&ctl.error));
-                st_active = ld_volatile(&ctl.active);
-                st_work = (ld_volatile(reinterpret_cast<const unsigned*>(&ctl.more)) || ld_volatile(&ctl.cur_left) > 0u) ? 1u : 0u;
-            }
-            st_error = __shfl_sync(FULL_MASK, st_error, 0); st_active = __shfl_sync(FULL_MASK, st_active, 0);
-            st_work = __shfl_sync(FULL_MASK, st_work, 0);
-            if (st_error) break;
-            int admitted = 0;
-            if (st_work && st_active + 32u <= Q_MAX_ACTIVE) {
-                // reserve room for 32 new records before starting them (undone below for the indices that are not granted)
-                if (lane == 0) {
-                    const unsigned old = atomicAdd(&ctl.active, 32u);
-                    if (old + 32u <= Q_MAX_ACTIVE) admitted = 1; else atomicSub(&ctl.active, 32u);
-                }
-                admitted = __shfl_sync(FULL_MASK, admitted, 0);
-            }
-            if (admitted) {
-                virgin = true; cls = CLS_FRESH; n_valid = 32;
-            } else {
-                const unsigned best2 = __reduce_max_sync(FULL_MASK, ((unsigned)part << 8) | (unsigned)lane);
-                if (best2 >> 8) {
-                    const int c = (int)(best2 & 255u);
-                    const unsigned h = __shfl_sync(FULL_MASK, h_c, c);
-                    int nv = 0;
-                    if (lane == 0 && atomicCAS(&ctl.head[c], h, h + 1u) == h) {
-                        // the page is ours; close it so that producers move on to the next one
-                        for (;;) {
-                            const unsigned t = ld_volatile(&ctl.tail[c]);
-                            if ((t >> 5) > h) { nv = 32; break; }
-                            if (atomicCAS(&ctl.tail[c], t, (h + 1u) << 5) == t) { nv = (int)(t & 31u); break; }
-                        }
-                    }
-                    nv = __shfl_sync(FULL_MASK, nv, 0);
-                    if (nv == 0) continue;
-                    cls = c; L = h; n_valid = nv;
-                } else {
-                    if (!st_work && st_active == 0u) break;
-                    if (++idle_spins > Q_WATCHDOG) { if (lane == 0) ctl.error = 2; break; }
-                    __nanosleep(200);
-                    continue;
-                }
-            }
-        }
-        idle_spins = 0;
-        const bool valid = lane < n_valid;
-        // ---- read the page ---------------------------------------------------------------------------------
-        if (!virgin) {
-            const int slot = (int)(L & (Q_RING - 1));
-            unsigned phys = 0xFFu;
-            if (lane == 0) {
-                for (unsigned spins = 0;; ++spins) {
-                    phys = ld_volatile(&ctl.ring[cls][slot]);
-                    if (phys != 0xFFu && ld_volatile(&ctl.commit[cls][slot]) == (unsigned)n_valid) break;
-                    if (spins > Q_WATCHDOG) { ctl.error = 3; phys = 0xFFu; break; }
-                    __nanosleep(32);
-                }
-            }
-            phys = __shfl_sync(FULL_MASK, phys, 0);
-            if (phys == 0xFFu) break;
-            __threadfence_block();
-            if (valid) {
-                const uint4* pg = pool + (size_t)phys * 5 * 32 + lane;
-                const uint4 q0 = pg[0], q1 = pg[32], q2 = pg[64], q3 = pg[96], q4 = pg[128];
-                p.xr = __uint_as_float(q0.x); p.y = __uint_as_float(q0.y); p.z = __uint_as_float(q0.z); p.dx = __uint_as_float(q0.w);
-                p.dy = __uint_as_float(q1.x); p.dz = __uint_as_float(q1.y); p.wl = __uint_as_float(q1.z); p.a_plate = __uint_as_float(q1.w);
-                p.a_outer = __uint_as_float(q2.x); p.a_inner = __uint_as_float(q2.y);
-                p.kc = q2.z & 0xfff; p.medium = (q2.z >> 12) & 15; p.steps = q2.z >> 16; p.aux = (int)q2.w;
-                rng.p_lo = q3.x; rng.p_hi = q3.y; batch = (int)q3.z; rng.calls = q3.w;
-                n_events = q4.x; pend = q4.y; u_surf = __uint_as_float(q4.z); w_z = q4.w;
-                pbin = (int)q4.z;
-            }
-            __syncwarp();
-            __threadfence_block();
-            if (lane == 0) {
-                ctl.commit[cls][slot] = 0u;
-                *reinterpret_cast<volatile unsigned*>(&ctl.ring[cls][slot]) = 0xFFu;
-                __threadfence_block();
-                atomicOr(&ctl.free_mask[phys >> 5], 1u << (phys & 31u));
-            }
-        } else {
-            pbin = -1;
-        }
-        // ---- the interaction this page was waiting for ------------------------------------------------------
-        int bin = -1;
-        bool fly = false, source = false, fresh = false, retired = false;
-        if (cls == CLS_FRESH) {
-            // tallies of the photons that ended
-            const bool have = valid && pbin >= 0;
-            if (__any_sync(FULL_MASK, have)) {
-                int cb = 0;
-                if (lane == 0) cb = (int)ld_volatile(reinterpret_cast<const unsigned*>(&ctl.cur_batch));
-                cb = __shfl_sync(FULL_MASK, cb, 0);
-                if (cb != hb && __any_sync(FULL_MASK, have && batch == cb)) {
-                    if (hb >= 0) flush_row(hist, A.tallies + (size_t)hb * stride, stride, lane);
-                    hb = cb;
-                }
-                const bool local = have && batch == hb;
-                const unsigned grp = __match_any_sync(FULL_MASK, local ? pbin : -1);
-                if (local && (grp & lane_lt) == 0u) atomicAdd(hist + pbin, (unsigned)__popc(grp));
-                const unsigned ev = __reduce_add_sync(FULL_MASK, local ? (n_events & 0xffffu) : 0u);
-                const unsigned em = __reduce_add_sync(FULL_MASK, local ? (n_events >> 16) : 0u);
-                if (lane == 0) {
-                    if (ev) atomicAdd(hist + S.n_bins, ev);
-                    if (em) atomicAdd(hist + S.n_bins + 1, em);
-                }
-                if (have && !local) {
-                    unsigned long long* row = A.tallies + (size_t)batch * stride;
-                    atomicAdd(row + pbin, 1ULL);
-                    atomicAdd(row + S.n_bins, (unsigned long long)(n_events & 0xffffu));
-                    if (n_events >> 16) atomicAdd(row + S.n_bins + 1, (unsigned long long)(n_events >> 16));
-                }
-                __syncwarp();
-            }
-            pbin = -1;
-            // new photon indices from the block's work cursor (lane 0 holds the lock)
-            unsigned long long base1 = 0, base2 = 0; unsigned k1 = 0, k2 = 0; int b1 = 0, b2 = 0;
-            if (lane == 0) {
-                unsigned spins = 0;
-                while (atomicCAS(&ctl.lock, 0u, 1u) != 0u) { if (++spins > Q_WATCHDOG) { ctl.error = 4; break; } __nanosleep(32); }
-                __threadfence_block();
-                unsigned need = (unsigned)n_valid;
-                unsigned long long cb = *reinterpret_cast<volatile unsigned long long*>(&ctl.cur_base);
-                unsigned cl = ld_volatile(&ctl.cur_left);
-                int cba = (int)ld_volatile(reinterpret_cast<const unsigned*>(&ctl.cur_batch));
-                int more = (int)ld_volatile(reinterpret_cast<const unsigned*>(&ctl.more));
-                k1 = min(need, cl); base1 = cb; b1 = cba; cb += k1; cl -= k1; need -= k1;
-                if (need > 0u && more) {
-                    claim_item(A, cb, cl, cba, more);
-                    k2 = min(need, cl); base2 = cb; b2 = cba; cb += k2; cl -= k2;
-                }
-                *reinterpret_cast<volatile unsigned long long*>(&ctl.cur_base) = cb;
-                *reinterpret_cast<volatile unsigned*>(&ctl.cur_left) = cl;
-                *reinterpret_cast<volatile int*>(&ctl.cur_batch) = cba;
-                *reinterpret_cast<volatile int*>(&ctl.more) = more;
-                const unsigned got = k1 + k2;
-                if (got < (unsigned)n_valid) atomicSub(&ctl.active, (unsigned)n_valid - got);   // retired (or never started)
-                __threadfence_block();
-                atomicExch(&ctl.lock, 0u);
-            }
-            base1 = __shfl_sync(FULL_MASK, base1, 0); base2 = __shfl_sync(FULL_MASK, base2, 0);
-            k1 = __shfl_sync(FULL_MASK, k1, 0); k2 = __shfl_sync(FULL_MASK, k2, 0);
-            b1 = __shfl_sync(FULL_MASK, b1, 0); b2 = __shfl_sync(FULL_MASK, b2, 0);
-            if (valid) {
-                const unsigned r = (unsigned)lane;
-                unsigned long long g = 0; int nb = -1;
-                if (r < k1) { g = base1 + r; nb = b1; }
-                else if (r - k1 < k2) { g = base2 + (r - k1); nb = b2; }
-                if (nb >= 0) {
-                    batch = nb;
-                    rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32); rng.calls = 0;
-                    n_events = 0;
-                    source = fresh = true;
-                } else {
-                    retired = true;
-                }
-            }
-        } else if (valid) {
-            if (cls == CLS_ABSORB) {
-                n_events += 1u;
-                bin = interact_absorb(S, p, pend, u_surf, w_z);
-                if (bin < 0) { n_events += 0x10000u; source = true; }
-            } else if (cls <= CLS_CYL) {
-                n_events += 1u;
-                bin = interact_surface<EXT>(S, p, pend, u_surf);
-                fly = bin < 0;
-            } else if (cls == CLS_CELL) {
-                fly = true;
-            } else if (EXT && cls == CLS_OUT) {
-                OutState q;
-                q.x = abs_x(S, p); q.y = p.y; q.z = p.z + S.zc; q.dx = p.dx; q.dy = p.dy; q.dz = p.dz; q.aux = p.aux; q.steps = p.steps;
-                const OutResult r = outside_step(S, q, u_surf);
-                p.dx = r.dx; p.dy = r.dy; p.dz = r.dz; p.aux = r.aux; p.steps = r.steps;
-                if (counts_as_event(r.event)) n_events += 1u + (unsigned)r.extra;
-                if (r.entered) { p.y = r.y; locate_in_plate(S, p, r.x, r.z); }
-                else { p.kc = 0; p.xr = r.x - axis_x(S, 0); p.y = r.y; p.z = r.z - S.zc; }
-                bin = r.bin;
-                fly = bin < 0;
-            }
-        }
-        if (source) {
-            rng.batch = A.batches[batch].batch_id;
-            const uint4 v = rng.next();
-            WavelengthDraw wd;
-            if (fresh) bin = source_fresh<EXT>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr);
-            else source_emit(S, v, p, wd);
-            source_finish(S, p, wd);
-            fly = bin < 0;
-        }
-        if (fly) {
-            rng.batch = A.batches[batch].batch_id;
-            const uint4 w = rng.next();
-            u_surf = u01(w.y); w_z = w.z;
-            bin = advance<EXT>(S, p, w.x, pend);
-        }
-        if (bin >= 0) { pend = CLS_FRESH; pbin = bin; }
-        // ---- push every record to the page stream of its new class ----------------------------------------------
-        __syncwarp();
-        const int ncls = (valid && !retired) ? (int)(pend & 15u) : Q_NONE;
-        {
-            // one pass for all classes: the lowest lane of every class group reserves the group's positions
-            const unsigned grp = __match_any_sync(FULL_MASK, ncls);
-            const bool mine = ncls != Q_NONE;
-            const int leader = __ffs(grp) - 1;
-            const unsigned n = (unsigned)__popc(grp);
-            unsigned pos0 = 0;
-            if (mine && lane == leader) pos0 = atomicAdd(&ctl.tail[ncls], n);
-            pos0 = __shfl_sync(FULL_MASK, pos0, leader);
-            const unsigned pos = pos0 + (unsigned)__popc(grp & lane_lt);
-            const int slot = (int)((pos >> 5) & (Q_RING - 1));
-            if (mine && (pos & 31u) == 0u) {     // first record of a page: allocate and publish it
-                const int phys = queue_alloc_page(ctl);
-                *reinterpret_cast<volatile unsigned*>(&ctl.ring[ncls][slot]) = (unsigned)phys;
-            }
-            __syncwarp();
-            if (mine) {
-                unsigned phys = 0xFFu, spins = 0;
-                for (;;) {
-                    phys = ld_volatile(&ctl.ring[ncls][slot]);
-                    if (phys != 0xFFu) break;
-                    if (++spins > Q_WATCHDOG) { ctl.error = 5; phys = 0u; break; }
-                    __nanosleep(32);
-                }
-                uint4* pg = pool + (size_t)phys * 5 * 32 + (pos & 31u);
-                pg[0] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z), __float_as_uint(p.dx));
-                pg[32] = make_uint4(__float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl), __float_as_uint(p.a_plate));
-                pg[64] = make_uint4(__float_as_uint(p.a_outer), __float_as_uint(p.a_inner),
-                                    (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16), (unsigned)p.aux);
-                pg[96] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.calls);
-                pg[128] = make_uint4(n_events, pend, ncls == CLS_FRESH ? (unsigned)pbin : __float_as_uint(u_surf), w_z);
-                __threadfence_block();
-            }
-            __syncwarp();
-            if (mine && lane == leader) {
-                const unsigned first = min(n, 32u - (pos0 & 31u));
-                atomicAdd(&ctl.commit[ncls][(pos0 >> 5) & (Q_RING - 1)], first);
-                if (n > first) atomicAdd(&ctl.commit[ncls][((pos0 >> 5) + 1u) & (Q_RING - 1)], n - first);
-            }
-        }
-    }
-    if (hb >= 0) flush_row(hist, A.tallies + (size_t)hb * stride, stride, lane);
-    if (ctl.error && tid == 0) atomicExch(A.error, (unsigned int)ctl.error);
-}
-
 // K1 (debug/emit): the rays a batch generates, in plate-local coordinates
 __global__ void emit_kernel(const __grid_constant__ DevScene S, const DevBatch* batch, const float* spec_x,
                             const float* spec_cdf, const unsigned short* spec_guide, unsigned long long photon_begin,
@@ -1083,8 +733,6 @@ struct LscpmScene {
     size_t trace_smem = 0;
     bool sorted = false;                 // block-sorted kernel or the lane-per-photon kernel
     bool sorted_forced = false;
-    bool queue = false;                  // experimental barrier-free regrouping kernel (LSCPM_TRACE_KERNEL=queue)
-    size_t queue_smem = 0;
     int sort_blocks_per_sm = 0;
     size_t sort_smem = 0;
 };
@@ -1551,8 +1199,7 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
         (rc = upload(fwd, &s->d_tab_fwd)) || (rc = upload(inv, &s->d_tab_inv)) ||
         (rc = upload(abs_outer, &s->d_abs_outer)) || (rc = upload(abs_inner, &s->d_abs_inner)))
         return bail(rc);
-    if ((e = cudaMalloc((void**)&s->d_counters, sizeof(unsigned long long) * (COUNTER_RING + 1))) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc counters"));
-    if ((e = cudaMemset(s->d_counters, 0, sizeof(unsigned long long) * (COUNTER_RING + 1))) != cudaSuccess) return bail(cuda_fail(e, "cudaMemset counters"));
+    if ((e = cudaMalloc((void**)&s->d_counters, sizeof(unsigned long long) * COUNTER_RING)) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc counters"));
     s->dev.tab_x = s->d_tab_x; s->dev.tab_y = s->d_tab_y; s->dev.tab_cdf = s->d_tab_cdf;
     s->dev.tab_fwd = s->d_tab_fwd; s->dev.tab_inv = s->d_tab_inv;
     s->dev.abs_base_outer = s->d_abs_outer; s->dev.abs_base_inner = s->d_abs_inner;
@@ -1577,15 +1224,6 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
     if (which && strcmp(which, "lanes") == 0) s->sorted = false;
     if (which && strcmp(which, "sorted") == 0) s->sorted = true;
     s->sorted_forced = which && strcmp(which, "sorted") == 0;
-    if (which && strcmp(which, "queue") == 0) {
-        s->queue_smem = ((sizeof(QueueControl) + 15) / 16) * 16 + (size_t)Q_PAGES * 5 * 32 * sizeof(uint4) +
-                        (size_t)Q_WARPS * (s->dev.n_bins + LSCPM_N_COUNTERS) * sizeof(unsigned int);
-        if (s->queue_smem > 227 * 1024) return bail(fail(LSCPM_EUNSUPPORTED, "too many tally bins for the queue kernel"));
-        if ((e = cudaFuncSetAttribute(s->dev.n_ext > 0 ? trace_queue_kernel<true> : trace_queue_kernel<false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->queue_smem)) != cudaSuccess)
-            return bail(cuda_fail(e, "cudaFuncSetAttribute (queue kernel)"));
-        s->queue = true; s->sorted = false;
-    }
     s->sort_smem = (size_t)(s->dev.n_bins + LSCPM_N_COUNTERS) * sizeof(unsigned int);
     if (s->sort_smem > 24 * 1024) s->sorted = false;    // static exchange buffer + row must stay under 48 KB
     if (s->sorted) {
@@ -1705,26 +1343,6 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
     a.n_chunks = a.chunks_per_batch * (unsigned long long)p->n_batches;
     int rc = pick_counter(s, stream, &a.work_counter);
     if (rc) return rc;
-    a.error = reinterpret_cast<unsigned int*>(s->d_counters + COUNTER_RING);
-    if (s->queue) {
-        const unsigned long long want = (total + Q_THREADS - 1) / Q_THREADS;
-        const int blocks = (int)std::max<unsigned long long>(1ULL, std::min<unsigned long long>((unsigned long long)s->n_sm, want));
-        unsigned long long item = std::min<unsigned long long>(std::max<unsigned long long>(total / ((unsigned long long)s->n_sm * 8ULL), 1024ULL), 16384ULL);
-        item = std::min<unsigned long long>(item, std::max<unsigned long long>(photon_count, 1ULL));
-        a.chunk = (unsigned)item;
-        a.chunks_per_batch = (photon_count + item - 1) / item;
-        a.n_chunks = a.chunks_per_batch * (unsigned long long)p->n_batches;
-        if (s->dev.n_ext > 0) trace_queue_kernel<true><<<blocks, Q_THREADS, s->queue_smem, stream>>>(s->dev, a);
-        else trace_queue_kernel<false><<<blocks, Q_THREADS, s->queue_smem, stream>>>(s->dev, a);
-        CUDA_TRY(cudaGetLastError());
-        // experimental: wait and report the watchdog
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        unsigned int err = 0;
-        CUDA_TRY(cudaMemcpy(&err, a.error, sizeof(err), cudaMemcpyDeviceToHost));
-        if (err) { cudaMemset(a.error, 0, sizeof(err)); return fail(LSCPM_ECUDA, "queue kernel watchdog fired (code " + std::to_string(err) + ")"); }
-        g_launches.fetch_add(1);
-        return LSCPM_OK;
-    }
     if (sorted) {
         // a block drinks from two work items at a time; tiny launches need fewer blocks than the grid
         const unsigned long long want = (total + SORT_THREADS - 1) / SORT_THREADS;

@@ -37,8 +37,7 @@ def timed(plan, tallies, ppb, seed):
 for label, kw in CASES.items():
     arrays = flatten.flatten_scene(standard_scene(**kw))
     out = {}
-    KERNELS = ("lanes", "sorted") + (("queue",) if os.environ.get("COMPARE_QUEUE") else ())
-    for which in KERNELS:
+    for which in ("lanes", "sorted"):
         scene = handle(arrays, which)
         for nb, ppb in ((3, 70_001), (64, 1_000_000)):
             plan = backend.Plan(scene, [arrays.light] * nb, list(range(nb)))
@@ -49,10 +48,6 @@ for label, kw in CASES.items():
             out[(which, nb)] = (tallies.cpu().numpy().copy(), ms)
     for nb, ppb in ((3, 70_001), (64, 1_000_000)):
         a, ms_a = out[("lanes", nb)]; b, ms_b = out[("sorted", nb)]
-        if "queue" in KERNELS:
-            q, ms_q = out[("queue", nb)]
-            print(f"   queue kernel: {ms_q:.2f} ms ({nb * ppb / ms_q / 1e3:.0f} Mph/s) speed-up vs lanes {ms_a / ms_q:.2f}  photons {int(q[:, :scene.n_bins].sum())}/{nb * ppb}"
-                  f"  bins differing {int((np.abs(a - q)[:, :scene.n_bins] > 0).sum())}  events {int(q[:, scene.n_bins].sum())}", flush=True)
         n = nb * ppb
         assert a[:, :scene.n_bins].sum() == n, "lanes kernel lost photons"
         assert b[:, :scene.n_bins].sum() == n, f"sorted kernel lost photons: {b[:, :scene.n_bins].sum()} vs {n}"
