@@ -382,11 +382,14 @@ trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ 
             }
         } else if (cls == CLS_ABSORB) {
             n_events += 1u;
-            bin = interact_absorb(S, p, pend, u_surf, w_z);
+            int ev;
+            bin = interact_absorb(S, p, pending_container(pend), u_surf, w_z, ev);
             if (bin < 0) { n_events += 0x10000u; source = true; }   // re-emitted by the luminophore
         } else if (cls == CLS_FLAT || cls == CLS_CYL) {
             n_events += 1u;
-            bin = interact_surface<EXT>(S, p, pend, u_surf);
+            int ev;
+            bin = interact_surface<EXT>(S, p, pending_kind(pend), pending_face(pend), pending_container(pend), pending_adj(pend),
+                                        pending_sibling(pend), u_surf, ev);
             fly = bin < 0;
         } else if (cls == CLS_CELL) {
             fly = true;

@@ -807,119 +807,11 @@ struct StepOut {
     int extra;       // additional interaction events folded into this iteration (photon absorbed by an outside box)
 };
 
-template <bool EXT>
-__device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const uint4 w, StepOut& out) {
-    out.extra = 0;
-    if (EXT && p.medium == MED_OUT) {
-        OutState q;
-        q.x = abs_x(S, p); q.y = p.y; q.z = p.z + S.zc; q.dx = p.dx; q.dy = p.dy; q.dz = p.dz; q.aux = p.aux; q.steps = p.steps;
-        const OutResult r = outside_step(S, q, u01(w.y));
-        p.dx = r.dx; p.dy = r.dy; p.dz = r.dz; p.aux = r.aux; p.steps = r.steps;
-        out.event = r.event; out.medium = MED_AIR; out.ch = r.node; out.kind = SURF_BOX; out.face = r.face; out.extra = r.extra;
-        if (r.entered) { p.y = r.y; locate_in_plate(S, p, r.x, r.z); }
-        else { p.kc = 0; p.xr = r.x - axis_x(S, 0); p.y = r.y; p.z = r.z - S.zc; }
-        return r.bin;
-    }
-    Hit h = compute_hit(S, p);
-    if (p.medium == MED_AIR) {
-        h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false;
-    }
-    // a virtual crossing is not a follow() iteration
-    p.steps += h.kind != SURF_CELL ? 1 : 0;
-    if (p.steps > MAXSTEPS) { out.event = EV_KILL; return BIN_KILL; }
-    // branch-free select of the container's attenuation (the compiler turned the ternary chain into a jump table)
-    float alpha = 0.f;
-    alpha = h.container == MED_PLATE ? p.a_plate : alpha;
-    alpha = h.container == MED_OUTER ? p.a_outer : alpha;
-    alpha = h.container == MED_INNER ? p.a_inner : alpha;
-    const float depth = alpha <= ALPHA_ZERO ? LSCPM_INF : fdiv(-flog(one_minus_u01(w.x)), alpha);
-    const float u_surf = u01(w.y);
-    out.medium = h.container; out.ch = p.kc; out.kind = h.kind; out.face = h.face;
-    const bool absorbed = depth < h.t;
-    const float travel = absorbed ? depth : h.t;
-    p.xr = fmaf(p.dx, travel, p.xr); p.y = fmaf(p.dy, travel, p.y); p.z = fmaf(p.dz, travel, p.z);
-
-    if (absorbed) {
-        // absorbed inside the container: choose the component ~ alpha_i, radiative test
-        const DevMedium& m = S.med[h.container];
-        const int index = pick_component(S, h.container, p.wl, alpha, u_surf * alpha);
-        const DevComponent& comp = m.comp[index];
-        if (comp.kind == COMP_LUMINOPHORE && u01(w.z) < comp.qy) {
-            p.aux = (p.aux & 0xffff) | (comp.ems_table << 16);
-            out.event = EV_EMIT;
-            return STEP_EMIT;
-        }
-        out.event = comp.kind == COMP_REACTOR ? EV_REACT : EV_ABSORB;
-        LSCPM_CHECK(p.kc >= 0 && p.kc < S.n_ch && index >= 0 && index < m.n_comp);
-        const int base = h.container == MED_PLATE ? S.abs_base_plate
-                       : (h.container == MED_OUTER ? __ldg(S.abs_base_outer + p.kc) : __ldg(S.abs_base_inner + p.kc));
-        return base + index;
-    }
-
-    if (h.kind == SURF_CELL) {
-        // step into the neighbouring cell; nothing physical happens here
-        p.kc += h.face;
-        LSCPM_CHECK(p.kc >= 0 && p.kc < S.n_ch);
-        p.xr = h.face > 0 ? -0.5f * S.pitch : 0.5f * S.pitch;
-        out.event = EV_NONE;
-        return -1;
-    }
-    const bool flat = h.kind == SURF_BOX || h.kind == SURF_CAP;
-    float nx, ny, nz;
-    box_normal(h.face, nx, ny, nz);
-    if (flat) {
-        if (p.medium != MED_AIR) {   // snap the coordinate of the face that was hit
-            if (h.face < 2) { if (h.kind == SURF_BOX) p.xr = (h.face & 1) ? S.cell_hi_last : S.cell_lo_first; }
-            else if (h.face < 4) p.y = (h.face & 1) ? S.hy : -S.hy;
-            else p.z = ((h.face & 1) ? S.hz : -S.hz) - S.zc;
-        }
-    } else {
-        const float inv = frsqrt(fmaf(p.xr, p.xr, p.z * p.z));
-        nx = p.xr * inv; ny = 0.f; nz = p.z * inv;
-        // leaving the tube wall: pvtrace's adjacent is whatever the straight continuation meets next
-        if (h.maybe_sibling && sibling_ahead(S, p.kc, p.xr, p.y, p.z, p.dx, p.dy, p.dz) >= 0) h.adj = MED_OUTER;
-    }
-    float n2 = S.med[h.adj].n;
-    const bool leaving = flat && p.medium != MED_AIR;
-    if (EXT && leaving) {
-        // adjacent = second intersection along the ray: an outside box straight ahead (even across an air gap) lends its index
-        const int e = ext_ahead(S, h.face, abs_x(S, p), p.y, p.z + S.zc, p.dx, p.dy, p.dz);
-        if (e >= 0) n2 = S.ext[e].n;
-    }
-    const float n1 = S.med[h.container].n;
-    const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, n1, n2);
-    const bool reflected = u_surf < I.R;
-    if (reflected) reflect_dir(p, I); else refract_dir(p, I);
-    out.event = reflected ? EV_REFLECT : EV_TRANSMIT;
-    if (p.medium == MED_AIR) {
-        if (reflected) return BIN_ENTRY_REFLECT;   // bounced off at first contact, leaves the scene
-        p.medium = (p.aux >> 4) & 3;
-        return -1;
-    }
-    if (EXT) p.aux = note_surface(p.aux, false, 0, h.face, leaving && !reflected);
-    if (reflected) return -1;
-    if (flat) {
-        if (EXT) {   // the air around the plate has geometry: keep following
-            const float xa = abs_x(S, p);
-            p.kc = 0; p.xr = xa - axis_x(S, 0);
-            p.medium = MED_OUT;
-            return -1;
-        }
-        // left the plate assembly: the next follow() iteration meets only the world sphere -> EXIT
-        p.medium = MED_AIR;
-        return (p.steps + 1 > MAXSTEPS) ? BIN_KILL : S.exit_base_plate + h.face;
-    }
-    if (h.kind == SURF_OUTER) p.medium = (p.medium == MED_PLATE) ? MED_OUTER : MED_PLATE;
-    else p.medium = (p.medium == MED_OUTER) ? MED_INNER : MED_OUTER;
-    return -1;
-}
-
-
 // ------------------------------------------------------------------------------------------------
-// The same follow() iteration cut where photons stop doing the same thing, for the block-sorted kernel:
-// `advance` (nearest interface, free path, move: identical work for every photon in flight) ends by naming the
-// interaction the photon is waiting for, the `interact_*` functions carry it out.  advance + interact_* performs
-// exactly the arithmetic of photon_step, with the same Philox draw.
+// The iteration is written in two halves, cut where photons stop doing the same thing: `advance` (nearest interface,
+// free path, move: identical work for every photon in flight) ends by naming the interaction the photon is waiting for,
+// the `interact_*` functions carry it out.  photon_step (below) runs them back to back for the lane-per-photon kernel
+// and the recorders; the block-sorted kernel re-deals the block's photons between the two halves.
 // ------------------------------------------------------------------------------------------------
 // class order = deal order: FLAT and CYL share the Fresnel code, CELL has no work of its own, ABSORB and FRESH share the source code
 constexpr int CLS_FLAT = 0, CLS_CYL = 1, CLS_CELL = 2, CLS_ABSORB = 3, CLS_FRESH = 4, CLS_OUT = 5, CLS_IDLE = 6, N_CLS = 7;
@@ -935,18 +827,24 @@ __device__ __forceinline__ int pending_container(unsigned w) { return (w >> 11) 
 __device__ __forceinline__ int pending_adj(unsigned w) { return (w >> 14) & 7; }
 __device__ __forceinline__ bool pending_sibling(unsigned w) { return (w >> 17) & 1; }
 
-// first half of the iteration; returns -1 or BIN_KILL (step limit)
-template <bool EXT>
-__device__ __forceinline__ int advance(const DevScene& S, Photon& p, const uint32_t w_x, unsigned& pend) {
-    if (EXT && p.medium == MED_OUT) { pend = CLS_OUT; return -1; }
-    Hit h;
-    if (p.medium == MED_AIR) {   // waiting on the plate face for its entry Fresnel test
-        h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false;
+// first half of the iteration for a photon in the plate assembly (or waiting on its face): nearest interface, free
+// path, move.  Returns -1 or BIN_KILL (step limit); `cls` names the interaction that follows, `h` describes it.
+// BRANCH_ENTRY: skip the geometry for a photon still waiting for its entry Fresnel test (pays when whole warps are in
+// that state - the sorted kernel; the lane kernel computes and overrides, which costs no branch).
+template <bool BRANCH_ENTRY>
+__device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const uint32_t w_x, Hit& h, int& cls) {
+    if (BRANCH_ENTRY) {
+        if (p.medium == MED_AIR) { h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false; }
+        else h = compute_hit(S, p);
     } else {
         h = compute_hit(S, p);
+        if (p.medium == MED_AIR) { h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false; }
     }
+    cls = CLS_CELL;
+    // a virtual crossing is not a follow() iteration
     p.steps += h.kind != SURF_CELL ? 1 : 0;
     if (p.steps > MAXSTEPS) return BIN_KILL;
+    // branch-free select of the container's attenuation (the compiler turned the ternary chain into a jump table)
     float alpha = 0.f;
     alpha = h.container == MED_PLATE ? p.a_plate : alpha;
     alpha = h.container == MED_OUTER ? p.a_outer : alpha;
@@ -955,7 +853,7 @@ __device__ __forceinline__ int advance(const DevScene& S, Photon& p, const uint3
     const bool absorbed = depth < h.t;
     const float travel = absorbed ? depth : h.t;
     p.xr = fmaf(p.dx, travel, p.xr); p.y = fmaf(p.dy, travel, p.y); p.z = fmaf(p.dz, travel, p.z);
-    int cls = (h.kind == SURF_BOX || h.kind == SURF_CAP) ? CLS_FLAT : CLS_CYL;
+    cls = (h.kind == SURF_BOX || h.kind == SURF_CAP) ? CLS_FLAT : CLS_CYL;
     if (h.kind == SURF_CELL) cls = CLS_CELL;
     if (absorbed) cls = CLS_ABSORB;
     if (cls == CLS_CELL) {   // step into the neighbouring cell; nothing physical happens here
@@ -963,14 +861,22 @@ __device__ __forceinline__ int advance(const DevScene& S, Photon& p, const uint3
         LSCPM_CHECK(p.kc >= 0 && p.kc < S.n_ch);
         p.xr = h.face > 0 ? -0.5f * S.pitch : 0.5f * S.pitch;
     }
-    pend = pack_pending(cls, h.kind, h.face, h.container, h.adj, h.maybe_sibling);
     return -1;
+}
+
+// the sorted kernel's form: the result packed into the pending word that travels with the photon record
+template <bool EXT>
+__device__ __forceinline__ int advance(const DevScene& S, Photon& p, const uint32_t w_x, unsigned& pend) {
+    if (EXT && p.medium == MED_OUT) { pend = CLS_OUT; return -1; }
+    Hit h; int cls;
+    const int killed = advance_hit<true>(S, p, w_x, h, cls);
+    pend = pack_pending(cls, h.kind, h.face, h.container, h.adj, h.maybe_sibling);
+    return killed;
 }
 
 // absorbed inside the container: choose the component ~ alpha_i, radiative test.  Returns the tally bin, or -1 with
 // p.aux carrying the emission table when the luminophore re-emits.
-__device__ __forceinline__ int interact_absorb(const DevScene& S, Photon& p, unsigned pend, float u_pick, uint32_t w_z) {
-    const int container = pending_container(pend);
+__device__ __forceinline__ int interact_absorb(const DevScene& S, Photon& p, int container, float u_pick, uint32_t w_z, int& event) {
     float alpha = 0.f;
     alpha = container == MED_PLATE ? p.a_plate : alpha;
     alpha = container == MED_OUTER ? p.a_outer : alpha;
@@ -980,8 +886,10 @@ __device__ __forceinline__ int interact_absorb(const DevScene& S, Photon& p, uns
     const DevComponent& comp = m.comp[index];
     if (comp.kind == COMP_LUMINOPHORE && u01(w_z) < comp.qy) {
         p.aux = (p.aux & 0xffff) | (comp.ems_table << 16);
+        event = EV_EMIT;
         return -1;
     }
+    event = comp.kind == COMP_REACTOR ? EV_REACT : EV_ABSORB;
     LSCPM_CHECK(p.kc >= 0 && p.kc < S.n_ch && index >= 0 && index < m.n_comp);
     const int base = container == MED_PLATE ? S.abs_base_plate
                    : (container == MED_OUTER ? __ldg(S.abs_base_outer + p.kc) : __ldg(S.abs_base_inner + p.kc));
@@ -990,9 +898,8 @@ __device__ __forceinline__ int interact_absorb(const DevScene& S, Photon& p, uns
 
 // Fresnel test at the interface the photon has been moved to; returns the tally bin or -1
 template <bool EXT>
-__device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, unsigned pend, float u_surf) {
-    const int kind = pending_kind(pend), face = pending_face(pend), container = pending_container(pend);
-    int adj = pending_adj(pend);
+__device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, int kind, int face, int container, int adj, bool maybe_sibling,
+                                                float u_surf, int& event) {
     const bool flat = kind == SURF_BOX || kind == SURF_CAP;
     float nx, ny, nz;
     box_normal(face, nx, ny, nz);
@@ -1005,7 +912,8 @@ __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, un
     } else {
         const float inv = frsqrt(fmaf(p.xr, p.xr, p.z * p.z));
         nx = p.xr * inv; ny = 0.f; nz = p.z * inv;
-        if (pending_sibling(pend) && sibling_ahead(S, p.kc, p.xr, p.y, p.z, p.dx, p.dy, p.dz) >= 0) adj = MED_OUTER;
+        // leaving the tube wall: pvtrace's adjacent is whatever the straight continuation meets next
+        if (maybe_sibling && sibling_ahead(S, p.kc, p.xr, p.y, p.z, p.dx, p.dy, p.dz) >= 0) adj = MED_OUTER;
     }
     float n2 = S.med[adj].n;
     const bool leaving = flat && p.medium != MED_AIR;
@@ -1017,8 +925,9 @@ __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, un
     const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, n1, n2);
     const bool reflected = u_surf < I.R;
     if (reflected) reflect_dir(p, I); else refract_dir(p, I);
+    event = reflected ? EV_REFLECT : EV_TRANSMIT;
     if (p.medium == MED_AIR) {
-        if (reflected) return BIN_ENTRY_REFLECT;
+        if (reflected) return BIN_ENTRY_REFLECT;   // bounced off at first contact, leaves the scene
         p.medium = (p.aux >> 4) & 3;
         return -1;
     }
@@ -1037,6 +946,33 @@ __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, un
     if (kind == SURF_OUTER) p.medium = (p.medium == MED_PLATE) ? MED_OUTER : MED_PLATE;
     else p.medium = (p.medium == MED_OUTER) ? MED_INNER : MED_OUTER;
     return -1;
+}
+
+// one whole iteration: advance, then the interaction it names
+template <bool EXT>
+__device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const uint4 w, StepOut& out) {
+    out.extra = 0;
+    if (EXT && p.medium == MED_OUT) {
+        OutState q;
+        q.x = abs_x(S, p); q.y = p.y; q.z = p.z + S.zc; q.dx = p.dx; q.dy = p.dy; q.dz = p.dz; q.aux = p.aux; q.steps = p.steps;
+        const OutResult r = outside_step(S, q, u01(w.y));
+        p.dx = r.dx; p.dy = r.dy; p.dz = r.dz; p.aux = r.aux; p.steps = r.steps;
+        out.event = r.event; out.medium = MED_AIR; out.ch = r.node; out.kind = SURF_BOX; out.face = r.face; out.extra = r.extra;
+        if (r.entered) { p.y = r.y; locate_in_plate(S, p, r.x, r.z); }
+        else { p.kc = 0; p.xr = r.x - axis_x(S, 0); p.y = r.y; p.z = r.z - S.zc; }
+        return r.bin;
+    }
+    out.ch = p.kc;
+    Hit h; int cls;
+    const int killed = advance_hit<false>(S, p, w.x, h, cls);
+    out.medium = h.container; out.kind = h.kind; out.face = h.face;
+    if (killed >= 0) { out.event = EV_KILL; return killed; }
+    if (cls == CLS_ABSORB) {
+        const int bin = interact_absorb(S, p, h.container, u01(w.y), w.z, out.event);
+        return bin < 0 ? STEP_EMIT : bin;
+    }
+    if (cls == CLS_CELL) { out.event = EV_NONE; return -1; }
+    return interact_surface<EXT>(S, p, h.kind, h.face, h.container, h.adj, h.maybe_sibling, u01(w.y), out.event);
 }
 
 }  // namespace lscpm

@@ -1,8 +1,16 @@
 """The reference's own runner tests (reference tests/test_simulation_runner.py:12-33), unchanged in
-substance, now exercising the CUDA path through the mirrored entry points."""
+substance, now exercising the CUDA path through the mirrored entry points.
+
+The reference runs them unseeded with 100-200 photons against bands that are about +-2.2 sigma wide at that count (a
+~3 % failure rate per run, for the reference as for this repo).  Here the same calls carry ``seed=`` (an extra of the
+mirrored runner) so the test is deterministic; ``test_runner_bands_at_statistics`` then checks the same bands with
+enough photons that they mean something."""
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+
+SEED = 20260101
 
 
 def green_photons():
@@ -17,18 +25,30 @@ def test_run_direct_simulation(built_library):
     from miniplant.simulation_runner import run_direct_simulation
 
     good = run_direct_simulation(tilt_angle=40, solar_elevation=50, solar_azimuth=180,
-                                 solar_spectrum_function=green_photons, num_photons=200)
+                                 solar_spectrum_function=green_photons, num_photons=200, seed=SEED)
     assert 0.20 <= good <= 0.40
     bad = run_direct_simulation(tilt_angle=0, solar_elevation=10, solar_azimuth=180,
-                                solar_spectrum_function=red_photons, num_photons=200)
+                                solar_spectrum_function=red_photons, num_photons=200, seed=SEED)
     assert bad <= 0.2
 
 
 def test_run_diffuse_simulation(built_library):
     from miniplant.simulation_runner import run_diffuse_simulation
 
-    standard = run_diffuse_simulation(solar_spectrum_function=green_photons)
+    standard = run_diffuse_simulation(solar_spectrum_function=green_photons, seed=SEED)
     assert 0.20 <= standard <= 0.40
+
+
+def test_runner_bands_at_statistics(built_library):
+    """The same three bands at 2e5 photons (sigma ~ 0.001): the fractions sit well inside them, whatever the seed."""
+    from miniplant.simulation_runner import run_diffuse_simulation, run_direct_simulation
+
+    good = run_direct_simulation(tilt_angle=40, solar_elevation=50, solar_azimuth=180,
+                                 solar_spectrum_function=green_photons, num_photons=200_000)
+    bad = run_direct_simulation(tilt_angle=0, solar_elevation=10, solar_azimuth=180,
+                                solar_spectrum_function=red_photons, num_photons=200_000)
+    standard = run_diffuse_simulation(solar_spectrum_function=green_photons, num_photons=200_000)
+    assert 0.22 <= good <= 0.38 and bad <= 0.15 and 0.22 <= standard <= 0.38, (good, bad, standard)
 
 
 def test_render_with_workers_raises(built_library):
