@@ -96,7 +96,7 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
             const uint4 w = rng.next();
             StepOut so;
             status = photon_step<EXT>(S, p, w, so);
-            if (counts_as_event(so.event)) n_events += 1u + (unsigned)so.extra;
+            n_events += (unsigned)so.extra + (counts_as_event(so.event) ? 1u : 0u);
             if (so.event == EV_EMIT) n_events += 0x10000u;
         }
         // ---- tally the photons that ended -----------------------------------------------------------
@@ -423,7 +423,7 @@ trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ 
             rng.batch = A.batches[batch].batch_id;
             const uint4 w = rng.next();
             u_surf = u01(w.y); w_z = w.z;
-            bin = advance<EXT>(S, p, w.x, pend);
+            bin = advance<EXT>(S, p, w.x, pend, n_events);
         }
         if (bin >= 0) { pend = CLS_FRESH; pbin = bin; }
     }
@@ -568,7 +568,7 @@ __global__ void follow_kernel(const __grid_constant__ DevScene S, const FollowIn
     while (bin < 0) {
         const uint4 w = rng.next();
         StepOut so;
-        bin = ext ? photon_step<true>(S, p, w, so) : photon_step<false>(S, p, w, so);
+        bin = ext ? photon_step<true, false>(S, p, w, so) : photon_step<false, false>(S, p, w, so);   // recorders keep every reflection as a step
         if (bin == STEP_EMIT) {
             const uint4 v = rng.next();
             WavelengthDraw wd;

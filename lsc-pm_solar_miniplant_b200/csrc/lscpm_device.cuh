@@ -827,12 +827,168 @@ __device__ __forceinline__ int pending_container(unsigned w) { return (w >> 11) 
 __device__ __forceinline__ int pending_adj(unsigned w) { return (w >> 14) & 7; }
 __device__ __forceinline__ bool pending_sibling(unsigned w) { return (w >> 17) & 1; }
 
+// ------------------------------------------------------------------------------------------------
+// Plate flight (standard scene, photon in the PMMA): straight to the next REAL event.
+// pvtrace follows a photon that is trapped by total internal reflection bounce by bounce, and this kernel used to add a
+// virtual step at every cell boundary; both are pure geometry.  Unfold the plate instead: mirror it at its z faces and
+// the trapped photon travels a straight line through a lattice of capillary images - columns at x = cx0 + k*pitch,
+// images of the axis at z' = m*T for even m and m*T - 2*zc for odd m (T = plate thickness).  One free path L is drawn for
+// the whole flight (free paths are memoryless, so this is the same distribution as one draw per segment), the flight ends
+// at the first of: absorption at L, a y or x face of the plate, a z face if the photon is NOT trapped (Fresnel test with
+// R < 1: a real random event), the first capillary image hit.  Then the end point is folded back: slab index m gives
+// the number of reflections (each one a follow() iteration and an interaction event of the reference, so both counters
+// advance by |m|), z and dz are mirrored for odd m.  Trapped is decided by interface_eval's own expression.
+// FOLD = false (path recorders, probe): the z faces always end the flight, so every reflection stays a step of its own.
+// ------------------------------------------------------------------------------------------------
+// Every product and sum below is an explicit intrinsic: the two trace kernels inline this code separately and must
+// round identically (a fused multiply-add contracted in one copy only moves a grazing hit in 2e-4 of the photons and
+// breaks the bit-identity the kernels are tested for).
+//
+// first intersection with the image circle centred (0, c) in the frame of its column; `cross0` is the cross product for
+// c = 0, ra2 = a * r_o^2.  Returns INF when the line misses, the circle is behind, or c lies outside [c_lo, c_hi].
+__device__ __forceinline__ float image_hit(float ox, float z, float dx, float dz, float cross0, float ra2, float r_o2, float c,
+                                           float c_lo, float c_hi) {
+    const float oz = __fsub_rn(z, c);
+    const float b = fmaf(ox, dx, __fmul_rn(oz, dz));
+    const float cr = fmaf(c, dx, cross0);
+    const float disc = fmaf(-cr, cr, ra2);
+    const float cc = __fsub_rn(fmaf(ox, ox, __fmul_rn(oz, oz)), r_o2);
+    const float t = __fmul_rn(cc, frcp(__fsub_rn(fsqrt(fmaxf(disc, 0.f)), b)));
+    const bool ok = c >= c_lo && c <= c_hi && disc > 0.f && b < 0.f && t > 0.f;
+    return ok ? t : LSCPM_INF;
+}
+
+template <bool FOLD>
+__device__ __forceinline__ void plate_flight(const DevScene& S, Photon& p, const float L, Hit& h, int& cls, int& bounces) {
+    const float T = 2.f * S.hz;
+    const float z_bot = __fsub_rn(-S.hz, S.zc);         // plate faces relative to the capillary axes
+    const float delta = -2.f * S.zc;                    // offset of the mirrored (odd) images of the axes
+    // the real flat faces ahead
+    const float ty = p.dy != 0.f ? __fmul_rn(__fsub_rn(copysignf(S.hy, p.dy), p.y), frcp(p.dy)) : LSCPM_INF;
+    const float tzf = p.dz != 0.f ? __fmul_rn(__fsub_rn(__fsub_rn(copysignf(S.hz, p.dz), S.zc), p.z), frcp(p.dz)) : LSCPM_INF;
+    const float x_face = p.dx >= 0.f ? fmaf((float)(S.n_ch - 1 - p.kc), S.pitch, S.cell_hi_last)
+                                     : fmaf(-(float)p.kc, S.pitch, S.cell_lo_first);
+    const float tx = p.dx != 0.f ? __fmul_rn(__fsub_rn(x_face, p.xr), frcp(p.dx)) : LSCPM_INF;
+    bool trapped = false;
+    if (FOLD) {   // interface_eval's own test for the z faces
+        const float n1 = S.med[MED_PLATE].n, n2 = S.med[MED_AIR].n;
+        const float eta = __fmul_rn(n1, frcp(n2));
+        const float c = fminf(fabsf(p.dz), 1.f);
+        const float s2 = fmaxf(fmaf(-c, c, 1.f), 0.f);
+        trapped = n2 < n1 && fmaf(-__fmul_rn(eta, eta), s2, 1.f) < 0.f;
+    }
+    float t_end = ty; int face = p.dy > 0.f ? 3 : 2;
+    if (tx < t_end) { t_end = tx; face = p.dx > 0.f ? 1 : 0; }
+    if (!trapped && tzf < t_end) { t_end = tzf; face = p.dz > 0.f ? 5 : 4; }
+    const bool absorbed = L < t_end;
+    t_end = fminf(t_end, L);
+    // capillary images: the photon's own column and the next one in the direction of travel.  A flight that reaches
+    // beyond them stops at the far cell boundary (a virtual crossing, as between cells before: the next iteration draws
+    // a new free path, which changes nothing because free paths are memoryless).  Two columns settle most flights and
+    // keep the lanes of a warp in step; an open-ended column loop ran at 4 of 32 lanes.
+    int hit_col = -1, hit_par = 0; float hit_c = 0.f; float t_hit = t_end;
+    bool crossing = false;
+    const float a = fmaf(p.dx, p.dx, __fmul_rn(p.dz, p.dz));
+    const int step = p.dx >= 0.f ? 1 : -1;
+    if (S.has_caps && a > 1e-30f) {
+        const float ra = __fmul_rn(S.r_o, fsqrt(a)), ra2 = __fmul_rn(a, S.r_o2);
+        const float inv_dx = p.dx != 0.f ? frcp(p.dx) : 0.f;
+        const float two_T = 2.f * T, inv_2T = frcp(two_T);
+        int j = p.kc;
+#pragma unroll
+        for (int trip = 0; trip < 2; ++trip) {
+            const float ox = fmaf(-(float)(j - p.kc), S.pitch, p.xr);
+            if (__fsub_rn(fabsf(ox), S.r_o) > __fmul_rn(fabsf(p.dx), t_hit)) break;   // the column starts beyond the end of the flight
+            const float cross0 = fmaf(ox, p.dz, -__fmul_rn(p.z, p.dx));
+            // centres c whose circle the line crosses: |cross0 + c*dx| < ra; and not wholly behind the ray in z'
+            float c_lo = -LSCPM_INF, c_hi = LSCPM_INF;
+            bool line_meets = true;
+            if (p.dx != 0.f) {
+                const float u = __fmul_rn(__fsub_rn(-cross0, ra), inv_dx), v = __fmul_rn(__fadd_rn(-cross0, ra), inv_dx);
+                c_lo = fminf(u, v); c_hi = fmaxf(u, v);
+            } else {
+                line_meets = fabsf(cross0) < ra;
+            }
+            if (p.dz >= 0.f) c_lo = fmaxf(c_lo, __fsub_rn(p.z, S.r_o));
+            if (p.dz <= 0.f) c_hi = fminf(c_hi, __fadd_rn(p.z, S.r_o));
+            float t_col = LSCPM_INF, c_col = 0.f; int par_col = 0;
+#pragma unroll
+            for (int parity = 0; parity < 2; ++parity) {
+                const float c0 = parity ? __fadd_rn(T, delta) : 0.f;
+                // the first lattice point c0 + n*2T inside the interval, in the direction of travel; in the photon's own
+                // column that image can lie behind it, so the second one is tried as well
+                float c1, c2;
+                if (p.dz >= 0.f) { c1 = fmaf(ceilf(__fmul_rn(__fsub_rn(c_lo, c0), inv_2T)), two_T, c0); c2 = __fadd_rn(c1, two_T); }
+                else { c1 = fmaf(floorf(__fmul_rn(__fsub_rn(c_hi, c0), inv_2T)), two_T, c0); c2 = __fsub_rn(c1, two_T); }
+                if (line_meets && c1 >= c_lo && c1 <= c_hi) {
+                    const float t1 = image_hit(ox, p.z, p.dx, p.dz, cross0, ra2, S.r_o2, c1, c_lo, c_hi);
+                    if (t1 < t_col) { t_col = t1; c_col = c1; par_col = parity; }
+                    if (trip == 0) {
+                        const float t2 = image_hit(ox, p.z, p.dx, p.dz, cross0, ra2, S.r_o2, c2, c_lo, c_hi);
+                        if (t2 < t_col) { t_col = t2; c_col = c2; par_col = parity; }
+                    }
+                }
+            }
+            if (t_col < t_hit) { t_hit = t_col; hit_col = j; hit_c = c_col; hit_par = par_col; break; }
+            // no hit in column j: is there another column ahead, and does the flight reach its cell?
+            const int jn = j + step;
+            if (p.dx == 0.f || jn < 0 || jn >= S.n_ch) break;
+            if (trip == 1) {
+                const float t_stop = __fmul_rn(__fsub_rn(__fmul_rn((float)(j - p.kc) + 0.5f * (float)step, S.pitch), p.xr), inv_dx);
+                if (t_stop < t_hit) { t_hit = t_stop; crossing = true; hit_col = jn; }
+                break;
+            }
+            j = jn;
+        }
+    }
+    // move, then fold back into the real plate
+    const float t = t_hit;
+    const float x_rel = fmaf(p.dx, t, p.xr), zu = fmaf(p.dz, t, p.z);
+    p.y = fmaf(p.dy, t, p.y);
+    const float inv_T = frcp(T);
+    int m;
+    if (hit_col >= 0 && !crossing) {
+        m = (int)rintf(__fmul_rn(__fsub_rn(hit_c, hit_par ? delta : 0.f), inv_T));
+        p.xr = fmaf(-(float)(hit_col - p.kc), S.pitch, x_rel);
+        p.kc = hit_col;
+        p.z = __fsub_rn(zu, hit_c);
+    } else {
+        int k = p.kc + (int)rintf(__fmul_rn(x_rel, S.inv_pitch));
+        k = min(max(k, 0), S.n_ch - 1);
+        p.xr = fmaf(-(float)(k - p.kc), S.pitch, x_rel);
+        if (crossing) { k = hit_col; p.xr = step > 0 ? -0.5f * S.pitch : 0.5f * S.pitch; }   // on the boundary, in the cell ahead
+        p.kc = k;
+        m = trapped ? (int)floorf(__fmul_rn(__fsub_rn(zu, z_bot), inv_T)) : 0;
+        p.z = fmaf(-(float)m, T, zu);
+    }
+    const bool image = hit_col >= 0 && !crossing;
+    if (m & 1) { p.z = __fsub_rn(image ? 0.f : delta, p.z); p.dz = -p.dz; }
+    bounces = abs(m);
+    h.t = t; h.ch = p.kc; h.container = MED_PLATE; h.maybe_sibling = false;
+    if (image) { h.kind = SURF_OUTER; h.face = 0; h.adj = MED_OUTER; cls = CLS_CYL; }
+    else if (crossing) { h.kind = SURF_CELL; h.face = step; h.adj = MED_PLATE; cls = CLS_CELL; }
+    else { h.kind = SURF_BOX; h.face = face; h.adj = MED_AIR; cls = absorbed ? CLS_ABSORB : CLS_FLAT; }
+}
+
 // first half of the iteration for a photon in the plate assembly (or waiting on its face): nearest interface, free
-// path, move.  Returns -1 or BIN_KILL (step limit); `cls` names the interaction that follows, `h` describes it.
+// path, move.  Returns -1 or BIN_KILL (step limit); `cls` names the interaction that follows, `h` describes it,
+// `extra` counts the reflections folded into a plate flight.
 // BRANCH_ENTRY: skip the geometry for a photon still waiting for its entry Fresnel test (pays when whole warps are in
 // that state - the sorted kernel; the lane kernel computes and overrides, which costs no branch).
-template <bool BRANCH_ENTRY>
-__device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const uint32_t w_x, Hit& h, int& cls) {
+// FLIGHT: plate flights (scenes without outside boxes); FOLD: fold total internal reflections into them.
+template <bool BRANCH_ENTRY, bool FLIGHT, bool FOLD>
+__device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const uint32_t w_x, Hit& h, int& cls, int& extra) {
+    extra = 0;
+    cls = CLS_CELL;
+    if (FLIGHT && p.medium == MED_PLATE) {
+        const float alpha = p.a_plate;
+        const float depth = alpha <= ALPHA_ZERO ? LSCPM_INF : __fmul_rn(-flog(one_minus_u01(w_x)), frcp(alpha));
+        int bounces;
+        plate_flight<FOLD>(S, p, depth, h, cls, bounces);
+        extra = bounces;
+        p.steps += (cls != CLS_CELL ? 1 : 0) + bounces;
+        return p.steps > MAXSTEPS ? BIN_KILL : -1;
+    }
     if (BRANCH_ENTRY) {
         if (p.medium == MED_AIR) { h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false; }
         else h = compute_hit(S, p);
@@ -840,7 +996,6 @@ __device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const u
         h = compute_hit(S, p);
         if (p.medium == MED_AIR) { h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false; }
     }
-    cls = CLS_CELL;
     // a virtual crossing is not a follow() iteration
     p.steps += h.kind != SURF_CELL ? 1 : 0;
     if (p.steps > MAXSTEPS) return BIN_KILL;
@@ -866,10 +1021,11 @@ __device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const u
 
 // the sorted kernel's form: the result packed into the pending word that travels with the photon record
 template <bool EXT>
-__device__ __forceinline__ int advance(const DevScene& S, Photon& p, const uint32_t w_x, unsigned& pend) {
+__device__ __forceinline__ int advance(const DevScene& S, Photon& p, const uint32_t w_x, unsigned& pend, unsigned& n_events) {
     if (EXT && p.medium == MED_OUT) { pend = CLS_OUT; return -1; }
-    Hit h; int cls;
-    const int killed = advance_hit<true>(S, p, w_x, h, cls);
+    Hit h; int cls, extra;
+    const int killed = advance_hit<true, !EXT, true>(S, p, w_x, h, cls, extra);
+    n_events += (unsigned)extra;
     pend = pack_pending(cls, h.kind, h.face, h.container, h.adj, h.maybe_sibling);
     return killed;
 }
@@ -949,7 +1105,7 @@ __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, in
 }
 
 // one whole iteration: advance, then the interaction it names
-template <bool EXT>
+template <bool EXT, bool FOLD = true>
 __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const uint4 w, StepOut& out) {
     out.extra = 0;
     if (EXT && p.medium == MED_OUT) {
@@ -964,7 +1120,7 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
     }
     out.ch = p.kc;
     Hit h; int cls;
-    const int killed = advance_hit<false>(S, p, w.x, h, cls);
+    const int killed = advance_hit<false, !EXT, FOLD>(S, p, w.x, h, cls, out.extra);
     out.medium = h.container; out.kind = h.kind; out.face = h.face;
     if (killed >= 0) { out.event = EV_KILL; return killed; }
     if (cls == CLS_ABSORB) {
