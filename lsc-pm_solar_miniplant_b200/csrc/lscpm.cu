@@ -507,14 +507,29 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
         o.found = 1; o.t = e.t; o.kind = SURF_BOX; o.face = e.face; o.container = MED_AIR; o.adj = MED_PLATE; o.ch = 0;
         box_normal(e.face, nx, ny, nz);
     } else {
-        // march over virtual cell crossings until a real interface
+        // to the next real interface: the trace kernels' own geometry.  In the plastic of a scene without outside boxes
+        // that is a plate flight without folding (every face ends it); otherwise compute_hit, marching over virtual cell
+        // crossings.
         float travelled = 0.f;
-        Hit h = compute_hit(S, p);
-        while (h.kind == SURF_CELL) {
-            travelled += h.t;
-            p.y = fmaf(p.dy, h.t, p.y); p.z = fmaf(p.dz, h.t, p.z);
-            p.kc += h.face; p.xr = h.face > 0 ? -0.5f * S.pitch : 0.5f * S.pitch;
+        Hit h;
+        if (S.n_ext == 0 && p.medium == MED_PLATE) {
+            const float dx0 = p.dx, dy0 = p.dy, dz0 = p.dz;
+            for (;;) {
+                int cls, bounces;
+                plate_flight<false>(S, p, LSCPM_INF, h, cls, bounces);
+                if (cls != CLS_CELL) break;
+                travelled += h.t;
+            }
+            // the flight moved the photon onto the interface: step back so that the common code below finds it at h.t
+            p.xr = fmaf(-dx0, h.t, p.xr); p.y = fmaf(-dy0, h.t, p.y); p.z = fmaf(-dz0, h.t, p.z);
+        } else {
             h = compute_hit(S, p);
+            while (h.kind == SURF_CELL) {
+                travelled += h.t;
+                p.y = fmaf(p.dy, h.t, p.y); p.z = fmaf(p.dz, h.t, p.z);
+                p.kc += h.face; p.xr = h.face > 0 ? -0.5f * S.pitch : 0.5f * S.pitch;
+                h = compute_hit(S, p);
+            }
         }
         const float xr = fmaf(p.dx, h.t, p.xr), yy = fmaf(p.dy, h.t, p.y), zz = fmaf(p.dz, h.t, p.z);
         o.found = 1; o.t = travelled + h.t; o.kind = h.kind; o.face = h.face; o.ch = p.kc; o.container = h.container; o.adj = h.adj;

@@ -911,24 +911,29 @@ __device__ __forceinline__ void plate_flight(const DevScene& S, Photon& p, const
             }
             if (p.dz >= 0.f) c_lo = fmaxf(c_lo, __fsub_rn(p.z, S.r_o));
             if (p.dz <= 0.f) c_hi = fminf(c_hi, __fadd_rn(p.z, S.r_o));
-            float t_col = LSCPM_INF, c_col = 0.f; int par_col = 0;
-#pragma unroll
-            for (int parity = 0; parity < 2; ++parity) {
-                const float c0 = parity ? __fadd_rn(T, delta) : 0.f;
-                // the first lattice point c0 + n*2T inside the interval, in the direction of travel; in the photon's own
-                // column that image can lie behind it, so the second one is tried as well
-                float c1, c2;
-                if (p.dz >= 0.f) { c1 = fmaf(ceilf(__fmul_rn(__fsub_rn(c_lo, c0), inv_2T)), two_T, c0); c2 = __fadd_rn(c1, two_T); }
-                else { c1 = fmaf(floorf(__fmul_rn(__fsub_rn(c_hi, c0), inv_2T)), two_T, c0); c2 = __fsub_rn(c1, two_T); }
-                if (line_meets && c1 >= c_lo && c1 <= c_hi) {
-                    const float t1 = image_hit(ox, p.z, p.dx, p.dz, cross0, ra2, S.r_o2, c1, c_lo, c_hi);
-                    if (t1 < t_col) { t_col = t1; c_col = c1; par_col = parity; }
-                    if (trip == 0) {
-                        const float t2 = image_hit(ox, p.z, p.dx, p.dz, cross0, ra2, S.r_o2, c2, c_lo, c_hi);
-                        if (t2 < t_col) { t_col = t2; c_col = c2; par_col = parity; }
-                    }
-                }
+            if (!line_meets) { c_lo = LSCPM_INF; c_hi = -LSCPM_INF; }
+            // image centres form two lattices of period 2T: even images at n*2T, odd (mirrored) ones at T + delta + n*2T.
+            // Candidates: the first point of either lattice inside the interval, in the direction of travel; in the photon's
+            // own column that image can lie behind it, so the next one in order is tried as well.  Branch-free.
+            const float c_odd = __fadd_rn(T, delta);
+            float e1, e2, o1, o2;
+            if (p.dz >= 0.f) {
+                e1 = __fmul_rn(ceilf(__fmul_rn(c_lo, inv_2T)), two_T); e2 = __fadd_rn(e1, two_T);
+                o1 = fmaf(ceilf(__fmul_rn(__fsub_rn(c_lo, c_odd), inv_2T)), two_T, c_odd); o2 = __fadd_rn(o1, two_T);
+            } else {
+                e1 = __fmul_rn(floorf(__fmul_rn(c_hi, inv_2T)), two_T); e2 = __fsub_rn(e1, two_T);
+                o1 = fmaf(floorf(__fmul_rn(__fsub_rn(c_hi, c_odd), inv_2T)), two_T, c_odd); o2 = __fsub_rn(o1, two_T);
             }
+            const bool up = p.dz >= 0.f;
+            const float first = up ? fminf(e1, o1) : fmaxf(e1, o1);
+            const float second = up ? fminf(fmaxf(e1, o1), fminf(e2, o2)) : fmaxf(fminf(e1, o1), fmaxf(e2, o2));
+            float t_col = image_hit(ox, p.z, p.dx, p.dz, cross0, ra2, S.r_o2, first, c_lo, c_hi);
+            float c_col = first;
+            if (trip == 0) {
+                const float t2 = image_hit(ox, p.z, p.dx, p.dz, cross0, ra2, S.r_o2, second, c_lo, c_hi);
+                if (t2 < t_col) { t_col = t2; c_col = second; }
+            }
+            const int par_col = (c_col == o1 || c_col == o2) ? 1 : 0;
             if (t_col < t_hit) { t_hit = t_col; hit_col = j; hit_c = c_col; hit_par = par_col; break; }
             // no hit in column j: is there another column ahead, and does the flight reach its cell?
             const int jn = j + step;
