@@ -50,6 +50,10 @@ constexpr int EV_GENERATE = 0, EV_REFLECT = 1, EV_TRANSMIT = 2, EV_ABSORB = 3, E
               EV_REACT = 7, EV_NONE = -1;
 constexpr int BIN_KILL = 0, BIN_MISS = 1, BIN_ENTRY_REFLECT = 2;
 constexpr int SURF_NONE = 0, SURF_BOX = 1, SURF_OUTER = 2, SURF_INNER = 3, SURF_CAP = 4, SURF_CELL = 5;
+#ifndef LSCPM_FLIGHT_COLUMNS
+#define LSCPM_FLIGHT_COLUMNS 2
+#endif
+constexpr int FLIGHT_COLUMNS = LSCPM_FLIGHT_COLUMNS;   // capillary columns a plate flight looks at before it stops at a cell boundary
 constexpr int MAXSTEPS = 1000;            // pvtrace follow(maxsteps=1000)
 constexpr float ALPHA_ZERO = 1e-8f;       // numpy.isclose(alpha, 0) in Material.penetration_depth
 constexpr float KB_EV = 8.617333262145e-5f;
@@ -336,6 +340,9 @@ __device__ __forceinline__ void cylinder_roots(float a, float inv_a, float b, fl
 
 // Next interface for a photon in PLATE / OUTER / INNER (pvtrace next_hit, literal outcomes); also returns the
 // virtual cell crossing (SURF_CELL) for plate flights.  One code path for all media.
+// PLATE_TOO = false: the caller never asks for a photon in the plastic (plate flights handle those), so the plate's own
+// candidates are left out.
+template <bool PLATE_TOO = true>
 __device__ __forceinline__ Hit compute_hit(const DevScene& S, const Photon& p) {
     Hit h;
     h.ch = p.kc;
@@ -367,14 +374,16 @@ __device__ __forceinline__ Hit compute_hit(const DevScene& S, const Photon& p) {
     const int yface = p.dy > 0.f ? 3 : 2;
     // PLATE: box faces / cell boundary / the cell's capillary
     float t_pl = tz; int k_pl = SURF_BOX, f_pl = p.dz > 0.f ? 5 : 4, adj_pl = MED_AIR;
-    if (ty < t_pl) { t_pl = ty; f_pl = yface; }
-    if (tx < t_pl) {
-        t_pl = tx;
-        const bool plate_face = p.dx > 0.f ? last : first;
-        k_pl = plate_face ? SURF_BOX : SURF_CELL;
-        f_pl = plate_face ? (p.dx > 0.f ? 1 : 0) : (p.dx > 0.f ? 1 : -1);
+    if (PLATE_TOO) {
+        if (ty < t_pl) { t_pl = ty; f_pl = yface; }
+        if (tx < t_pl) {
+            t_pl = tx;
+            const bool plate_face = p.dx > 0.f ? last : first;
+            k_pl = plate_face ? SURF_BOX : SURF_CELL;
+            f_pl = plate_face ? (p.dx > 0.f ? 1 : 0) : (p.dx > 0.f ? 1 : -1);
+        }
+        if (o_near < t_pl) { t_pl = o_near; k_pl = SURF_OUTER; f_pl = 0; adj_pl = MED_OUTER; }
     }
-    if (o_near < t_pl) { t_pl = o_near; k_pl = SURF_OUTER; f_pl = 0; adj_pl = MED_OUTER; }
     // OUTER: inner cylinder, else cap (coincides with the plate face: plate sorts first and becomes container and
     // hit node), else the tube's own outer surface (adjacent provisional: sibling search may upgrade it)
     // Container: whenever the straight line leaves the tube through its CAP (ty <= o_far) the tube's only remaining
@@ -394,7 +403,7 @@ __device__ __forceinline__ Hit compute_hit(const DevScene& S, const Photon& p) {
     const int c_in = in_cap ? MED_PLATE : MED_INNER;
     const int adj_in = in_cap ? MED_OUTER : ((ty <= o_far) ? MED_PLATE : MED_OUTER);
 
-    const bool is_pl = p.medium == MED_PLATE, is_ou = p.medium == MED_OUTER;
+    const bool is_pl = PLATE_TOO && p.medium == MED_PLATE, is_ou = p.medium == MED_OUTER;
     h.t = fmaxf(is_pl ? t_pl : (is_ou ? t_ou : t_in), 0.f);
     h.kind = is_pl ? k_pl : (is_ou ? k_ou : k_in);
     h.face = is_pl ? f_pl : ((h.kind == SURF_CAP) ? yface : 0);
@@ -858,14 +867,52 @@ __device__ __forceinline__ float image_hit(float ox, float z, float dx, float dz
     return ok ? t : LSCPM_INF;
 }
 
+// images of column `ox` (x of the photon relative to the column's axis) met by an upward ray (dz >= 0): the image
+// centres form two lattices of period 2T - even images at n*2T, odd (mirrored) ones at T + delta + n*2T.  Candidates: the
+// first point of either lattice inside the interval of centres whose circle the line crosses, going up; in the photon's
+// own column (`two`) that image can lie behind it, so the next one in order is tried as well.  Branch-free.
+struct ColumnHit { float t, c; int odd; };
+__device__ __forceinline__ ColumnHit column_images(float ox, float z, float dx, float dz, float ra, float ra2, float r_o, float r_o2,
+                                                   float inv_dx, float T, float delta, bool two) {
+    const float two_T = 2.f * T, inv_2T = frcp(two_T);
+    const float cross0 = fmaf(ox, dz, -__fmul_rn(z, dx));
+    // centres c whose circle the line crosses: |cross0 + c*dx| < ra; and not wholly below the ray's start
+    float c_lo = -LSCPM_INF, c_hi = LSCPM_INF;
+    if (dx != 0.f) {
+        const float u = __fmul_rn(__fsub_rn(-cross0, ra), inv_dx), v = __fmul_rn(__fadd_rn(-cross0, ra), inv_dx);
+        c_lo = fminf(u, v); c_hi = fmaxf(u, v);
+    } else if (!(fabsf(cross0) < ra)) {
+        c_lo = LSCPM_INF; c_hi = -LSCPM_INF;
+    }
+    c_lo = fmaxf(c_lo, __fsub_rn(z, r_o));
+    if (dz == 0.f) c_hi = fminf(c_hi, __fadd_rn(z, r_o));
+    const float c_odd = __fadd_rn(T, delta);
+    const float e1 = __fmul_rn(ceilf(__fmul_rn(c_lo, inv_2T)), two_T), e2 = __fadd_rn(e1, two_T);
+    const float o1 = fmaf(ceilf(__fmul_rn(__fsub_rn(c_lo, c_odd), inv_2T)), two_T, c_odd), o2 = __fadd_rn(o1, two_T);
+    const float first = fminf(e1, o1);
+    const float second = fminf(fmaxf(e1, o1), fminf(e2, o2));
+    ColumnHit r;
+    r.t = image_hit(ox, z, dx, dz, cross0, ra2, r_o2, first, c_lo, c_hi);
+    r.c = first;
+    if (two) {
+        const float t2 = image_hit(ox, z, dx, dz, cross0, ra2, r_o2, second, c_lo, c_hi);
+        if (t2 < r.t) { r.t = t2; r.c = second; }
+    }
+    r.odd = (r.c == o1 || r.c == o2) ? 1 : 0;
+    return r;
+}
+
 template <bool FOLD>
 __device__ __forceinline__ void plate_flight(const DevScene& S, Photon& p, const float L, Hit& h, int& cls, int& bounces) {
+    // mirror the problem so that the photon travels upwards: z -> s*z with s = sign(dz); the capillary axes then sit at s*zc
+    const float sgn = p.dz >= 0.f ? 1.f : -1.f;
+    const float z0 = __fmul_rn(sgn, p.z), dz = fabsf(p.dz), zc = __fmul_rn(sgn, S.zc);
     const float T = 2.f * S.hz;
-    const float z_bot = __fsub_rn(-S.hz, S.zc);         // plate faces relative to the capillary axes
-    const float delta = -2.f * S.zc;                    // offset of the mirrored (odd) images of the axes
+    const float z_bot = __fsub_rn(-S.hz, zc);           // lower plate face relative to the capillary axes
+    const float delta = -2.f * zc;                      // offset of the mirrored (odd) images of the axes
     // the real flat faces ahead
     const float ty = p.dy != 0.f ? __fmul_rn(__fsub_rn(copysignf(S.hy, p.dy), p.y), frcp(p.dy)) : LSCPM_INF;
-    const float tzf = p.dz != 0.f ? __fmul_rn(__fsub_rn(__fsub_rn(copysignf(S.hz, p.dz), S.zc), p.z), frcp(p.dz)) : LSCPM_INF;
+    const float tzf = dz != 0.f ? __fmul_rn(__fsub_rn(__fsub_rn(S.hz, zc), z0), frcp(dz)) : LSCPM_INF;
     const float x_face = p.dx >= 0.f ? fmaf((float)(S.n_ch - 1 - p.kc), S.pitch, S.cell_hi_last)
                                      : fmaf(-(float)p.kc, S.pitch, S.cell_lo_first);
     const float tx = p.dx != 0.f ? __fmul_rn(__fsub_rn(x_face, p.xr), frcp(p.dx)) : LSCPM_INF;
@@ -873,7 +920,7 @@ __device__ __forceinline__ void plate_flight(const DevScene& S, Photon& p, const
     if (FOLD) {   // interface_eval's own test for the z faces
         const float n1 = S.med[MED_PLATE].n, n2 = S.med[MED_AIR].n;
         const float eta = __fmul_rn(n1, frcp(n2));
-        const float c = fminf(fabsf(p.dz), 1.f);
+        const float c = fminf(dz, 1.f);
         const float s2 = fmaxf(fmaf(-c, c, 1.f), 0.f);
         trapped = n2 < n1 && fmaf(-__fmul_rn(eta, eta), s2, 1.f) < 0.f;
     }
@@ -886,59 +933,24 @@ __device__ __forceinline__ void plate_flight(const DevScene& S, Photon& p, const
     // beyond them stops at the far cell boundary (a virtual crossing, as between cells before: the next iteration draws
     // a new free path, which changes nothing because free paths are memoryless).  Two columns settle most flights and
     // keep the lanes of a warp in step; an open-ended column loop ran at 4 of 32 lanes.
-    int hit_col = -1, hit_par = 0; float hit_c = 0.f; float t_hit = t_end;
+    int hit_col = -1, hit_odd = 0; float hit_c = 0.f; float t_hit = t_end;
     bool crossing = false;
-    const float a = fmaf(p.dx, p.dx, __fmul_rn(p.dz, p.dz));
+    const float a = fmaf(p.dx, p.dx, __fmul_rn(dz, dz));
     const int step = p.dx >= 0.f ? 1 : -1;
     if (S.has_caps && a > 1e-30f) {
         const float ra = __fmul_rn(S.r_o, fsqrt(a)), ra2 = __fmul_rn(a, S.r_o2);
         const float inv_dx = p.dx != 0.f ? frcp(p.dx) : 0.f;
-        const float two_T = 2.f * T, inv_2T = frcp(two_T);
         int j = p.kc;
 #pragma unroll
-        for (int trip = 0; trip < 2; ++trip) {
+        for (int trip = 0; trip < FLIGHT_COLUMNS; ++trip) {
             const float ox = fmaf(-(float)(j - p.kc), S.pitch, p.xr);
             if (__fsub_rn(fabsf(ox), S.r_o) > __fmul_rn(fabsf(p.dx), t_hit)) break;   // the column starts beyond the end of the flight
-            const float cross0 = fmaf(ox, p.dz, -__fmul_rn(p.z, p.dx));
-            // centres c whose circle the line crosses: |cross0 + c*dx| < ra; and not wholly behind the ray in z'
-            float c_lo = -LSCPM_INF, c_hi = LSCPM_INF;
-            bool line_meets = true;
-            if (p.dx != 0.f) {
-                const float u = __fmul_rn(__fsub_rn(-cross0, ra), inv_dx), v = __fmul_rn(__fadd_rn(-cross0, ra), inv_dx);
-                c_lo = fminf(u, v); c_hi = fmaxf(u, v);
-            } else {
-                line_meets = fabsf(cross0) < ra;
-            }
-            if (p.dz >= 0.f) c_lo = fmaxf(c_lo, __fsub_rn(p.z, S.r_o));
-            if (p.dz <= 0.f) c_hi = fminf(c_hi, __fadd_rn(p.z, S.r_o));
-            if (!line_meets) { c_lo = LSCPM_INF; c_hi = -LSCPM_INF; }
-            // image centres form two lattices of period 2T: even images at n*2T, odd (mirrored) ones at T + delta + n*2T.
-            // Candidates: the first point of either lattice inside the interval, in the direction of travel; in the photon's
-            // own column that image can lie behind it, so the next one in order is tried as well.  Branch-free.
-            const float c_odd = __fadd_rn(T, delta);
-            float e1, e2, o1, o2;
-            if (p.dz >= 0.f) {
-                e1 = __fmul_rn(ceilf(__fmul_rn(c_lo, inv_2T)), two_T); e2 = __fadd_rn(e1, two_T);
-                o1 = fmaf(ceilf(__fmul_rn(__fsub_rn(c_lo, c_odd), inv_2T)), two_T, c_odd); o2 = __fadd_rn(o1, two_T);
-            } else {
-                e1 = __fmul_rn(floorf(__fmul_rn(c_hi, inv_2T)), two_T); e2 = __fsub_rn(e1, two_T);
-                o1 = fmaf(floorf(__fmul_rn(__fsub_rn(c_hi, c_odd), inv_2T)), two_T, c_odd); o2 = __fsub_rn(o1, two_T);
-            }
-            const bool up = p.dz >= 0.f;
-            const float first = up ? fminf(e1, o1) : fmaxf(e1, o1);
-            const float second = up ? fminf(fmaxf(e1, o1), fminf(e2, o2)) : fmaxf(fminf(e1, o1), fmaxf(e2, o2));
-            float t_col = image_hit(ox, p.z, p.dx, p.dz, cross0, ra2, S.r_o2, first, c_lo, c_hi);
-            float c_col = first;
-            if (trip == 0) {
-                const float t2 = image_hit(ox, p.z, p.dx, p.dz, cross0, ra2, S.r_o2, second, c_lo, c_hi);
-                if (t2 < t_col) { t_col = t2; c_col = second; }
-            }
-            const int par_col = (c_col == o1 || c_col == o2) ? 1 : 0;
-            if (t_col < t_hit) { t_hit = t_col; hit_col = j; hit_c = c_col; hit_par = par_col; break; }
+            const ColumnHit ch = column_images(ox, z0, p.dx, dz, ra, ra2, S.r_o, S.r_o2, inv_dx, T, delta, trip == 0);
+            if (ch.t < t_hit) { t_hit = ch.t; hit_col = j; hit_c = ch.c; hit_odd = ch.odd; break; }
             // no hit in column j: is there another column ahead, and does the flight reach its cell?
             const int jn = j + step;
             if (p.dx == 0.f || jn < 0 || jn >= S.n_ch) break;
-            if (trip == 1) {
+            if (trip == FLIGHT_COLUMNS - 1) {
                 const float t_stop = __fmul_rn(__fsub_rn(__fmul_rn((float)(j - p.kc) + 0.5f * (float)step, S.pitch), p.xr), inv_dx);
                 if (t_stop < t_hit) { t_hit = t_stop; crossing = true; hit_col = jn; }
                 break;
@@ -946,33 +958,31 @@ __device__ __forceinline__ void plate_flight(const DevScene& S, Photon& p, const
             j = jn;
         }
     }
-    // move, then fold back into the real plate
+    // move, then fold back into the real plate (selects, no branches)
     const float t = t_hit;
-    const float x_rel = fmaf(p.dx, t, p.xr), zu = fmaf(p.dz, t, p.z);
+    const float x_rel = fmaf(p.dx, t, p.xr), zu = fmaf(dz, t, z0);
     p.y = fmaf(p.dy, t, p.y);
     const float inv_T = frcp(T);
-    int m;
-    if (hit_col >= 0 && !crossing) {
-        m = (int)rintf(__fmul_rn(__fsub_rn(hit_c, hit_par ? delta : 0.f), inv_T));
-        p.xr = fmaf(-(float)(hit_col - p.kc), S.pitch, x_rel);
-        p.kc = hit_col;
-        p.z = __fsub_rn(zu, hit_c);
-    } else {
-        int k = p.kc + (int)rintf(__fmul_rn(x_rel, S.inv_pitch));
-        k = min(max(k, 0), S.n_ch - 1);
-        p.xr = fmaf(-(float)(k - p.kc), S.pitch, x_rel);
-        if (crossing) { k = hit_col; p.xr = step > 0 ? -0.5f * S.pitch : 0.5f * S.pitch; }   // on the boundary, in the cell ahead
-        p.kc = k;
-        m = trapped ? (int)floorf(__fmul_rn(__fsub_rn(zu, z_bot), inv_T)) : 0;
-        p.z = fmaf(-(float)m, T, zu);
-    }
     const bool image = hit_col >= 0 && !crossing;
-    if (m & 1) { p.z = __fsub_rn(image ? 0.f : delta, p.z); p.dz = -p.dz; }
-    bounces = abs(m);
+    int k = p.kc + (int)rintf(__fmul_rn(x_rel, S.inv_pitch));
+    k = min(max(k, 0), S.n_ch - 1);
+    k = hit_col >= 0 ? hit_col : k;
+    const float xr_new = fmaf(-(float)(k - p.kc), S.pitch, x_rel);
+    p.xr = crossing ? (step > 0 ? -0.5f * S.pitch : 0.5f * S.pitch) : xr_new;   // a crossing lands on the boundary, in the cell ahead
+    p.kc = k;
+    const int m_img = (int)rintf(__fmul_rn(__fsub_rn(hit_c, hit_odd ? delta : 0.f), inv_T));
+    const int m_flat = trapped ? (int)floorf(__fmul_rn(__fsub_rn(zu, z_bot), inv_T)) : 0;
+    const int m = image ? m_img : m_flat;
+    float z = image ? __fsub_rn(zu, hit_c) : fmaf(-(float)m, T, zu);
+    float dz_out = dz;
+    if (m & 1) { z = __fsub_rn(image ? 0.f : delta, z); dz_out = -dz; }
+    p.z = __fmul_rn(sgn, z); p.dz = __fmul_rn(sgn, dz_out);
+    bounces = m;                                        // the mirrored photon only ever moves up: m >= 0
     h.t = t; h.ch = p.kc; h.container = MED_PLATE; h.maybe_sibling = false;
-    if (image) { h.kind = SURF_OUTER; h.face = 0; h.adj = MED_OUTER; cls = CLS_CYL; }
-    else if (crossing) { h.kind = SURF_CELL; h.face = step; h.adj = MED_PLATE; cls = CLS_CELL; }
-    else { h.kind = SURF_BOX; h.face = face; h.adj = MED_AIR; cls = absorbed ? CLS_ABSORB : CLS_FLAT; }
+    h.kind = image ? SURF_OUTER : (crossing ? SURF_CELL : SURF_BOX);
+    h.face = image ? 0 : (crossing ? step : face);
+    h.adj = image ? MED_OUTER : (crossing ? MED_PLATE : MED_AIR);
+    cls = image ? CLS_CYL : (crossing ? CLS_CELL : (absorbed ? CLS_ABSORB : CLS_FLAT));
 }
 
 // first half of the iteration for a photon in the plate assembly (or waiting on its face): nearest interface, free
@@ -996,9 +1006,9 @@ __device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const u
     }
     if (BRANCH_ENTRY) {
         if (p.medium == MED_AIR) { h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false; }
-        else h = compute_hit(S, p);
+        else h = compute_hit<!FLIGHT>(S, p);
     } else {
-        h = compute_hit(S, p);
+        h = compute_hit<!FLIGHT>(S, p);
         if (p.medium == MED_AIR) { h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false; }
     }
     // a virtual crossing is not a follow() iteration
