@@ -63,9 +63,10 @@ __device__ __forceinline__ void flush_row(unsigned int* hist, unsigned long long
     __syncwarp();
 }
 
-// EXT: the scene has boxes outside the plate (photovoltaic variants); the standard scene runs the EXT = false
-// instantiation, which contains none of that code.
-template <bool EXT>
+// EXT: the scene has boxes outside the plate (photovoltaic variants); the standard scene runs an EXT = false
+// instantiation, which contains none of that code.  FLIGHT: photons in the plastic go straight to their next real event
+// (plate_flight); chosen when the plate holds a luminophore, i.e. when there is trapped light to fold.
+template <bool EXT, bool FLIGHT>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceArgs A) {
     extern __shared__ unsigned int smem_rows[];
@@ -95,7 +96,7 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
         if (alive) {
             const uint4 w = rng.next();
             StepOut so;
-            status = photon_step<EXT>(S, p, w, so);
+            status = photon_step<EXT, FLIGHT>(S, p, w, so);
             n_events += (unsigned)so.extra + (counts_as_event(so.event) ? 1u : 0u);
             if (so.event == EV_EMIT) n_events += 0x10000u;
         }
@@ -217,7 +218,7 @@ __device__ __forceinline__ void claim_item(const TraceArgs& A, unsigned long lon
     left = (unsigned)min((unsigned long long)A.chunk, A.photon_count - first);
 }
 
-template <bool EXT, int BLOCK>
+template <bool EXT, bool FLIGHT, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, SORT_MIN_BLOCKS)
 trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceArgs A) {
     constexpr int NW = BLOCK / 32;
@@ -423,7 +424,7 @@ trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ 
             rng.batch = A.batches[batch].batch_id;
             const uint4 w = rng.next();
             u_surf = u01(w.y); w_z = w.z;
-            bin = advance<EXT>(S, p, w.x, pend, n_events);
+            bin = advance<EXT, FLIGHT>(S, p, w.x, pend, n_events);
         }
         if (bin >= 0) { pend = CLS_FRESH; pbin = bin; }
     }
@@ -583,7 +584,8 @@ __global__ void follow_kernel(const __grid_constant__ DevScene S, const FollowIn
     while (bin < 0) {
         const uint4 w = rng.next();
         StepOut so;
-        bin = ext ? photon_step<true, false>(S, p, w, so) : photon_step<false, false>(S, p, w, so);   // recorders keep every reflection as a step
+        // recorders keep every reflection as a step of its own (FOLD = false)
+        bin = ext ? photon_step<true, false, false>(S, p, w, so) : photon_step<false, true, false>(S, p, w, so);
         if (bin == STEP_EMIT) {
             const uint4 v = rng.next();
             WavelengthDraw wd;
@@ -751,6 +753,7 @@ struct LscpmScene {
     size_t trace_smem = 0;
     bool sorted = false;                 // block-sorted kernel or the lane-per-photon kernel
     bool sorted_forced = false;
+    bool flight = false;                 // plate flights (scenes without outside boxes whose plate holds a luminophore)
     int sort_blocks_per_sm = 0;
     size_t sort_smem = 0;
 };
@@ -1043,6 +1046,16 @@ int lower_batch(const LscpmScene* s, const LscpmBatchDesc* b, const std::vector<
     return LSCPM_OK;
 }
 
+typedef void (*TraceKernel)(const DevScene, const TraceArgs);
+TraceKernel lane_kernel(const LscpmScene* s) {
+    if (s->dev.n_ext > 0) return trace_kernel<true, false>;
+    return s->flight ? trace_kernel<false, true> : trace_kernel<false, false>;
+}
+TraceKernel sorted_kernel(const LscpmScene* s) {
+    if (s->dev.n_ext > 0) return trace_sorted_kernel<true, false, SORT_THREADS>;
+    return s->flight ? trace_sorted_kernel<false, true, SORT_THREADS> : trace_sorted_kernel<false, false, SORT_THREADS>;
+}
+
 int pick_counter(LscpmScene* s, cudaStream_t stream, unsigned long long** out) {
     const unsigned slot = s->next_counter.fetch_add(1) % COUNTER_RING;
     *out = s->d_counters + slot;
@@ -1224,13 +1237,21 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(cuda_fail(e, "cudaGetDeviceProperties"));
     s->n_sm = prop.multiProcessorCount;
+    // plate flights pay where light is trapped in the plastic, i.e. when the plate's material re-emits; a plate without a
+    // luminophore (the reference's include_dye=False) is crossed once and is faster with the plain cell march.
+    // LSCPM_PLATE_FLIGHTS=0|1 overrides (diagnostics; tallies agree statistically, not bit for bit).
+    s->flight = false;
+    if (s->dev.n_ext == 0)
+        for (int c = 0; c < s->dev.med[MED_PLATE].n_comp; ++c)
+            if (s->dev.med[MED_PLATE].comp[c].kind == COMP_LUMINOPHORE) s->flight = true;
+    if (const char* f = getenv("LSCPM_PLATE_FLIGHTS")) s->flight = s->dev.n_ext == 0 && f[0] == '1';
     s->trace_smem = (size_t)(TRACE_THREADS / 32) * (size_t)(s->dev.n_bins + LSCPM_N_COUNTERS) * sizeof(unsigned int);
     if (s->trace_smem > 200 * 1024) return bail(fail(LSCPM_EUNSUPPORTED, "too many tally bins for the per-warp shared rows"));
     if (s->trace_smem > 48 * 1024 &&
-        (e = cudaFuncSetAttribute(s->dev.n_ext > 0 ? trace_kernel<true> : trace_kernel<false>,
+        (e = cudaFuncSetAttribute(lane_kernel(s),
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->trace_smem)) != cudaSuccess)
         return bail(cuda_fail(e, "cudaFuncSetAttribute"));
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, s->dev.n_ext > 0 ? trace_kernel<true> : trace_kernel<false>,
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, lane_kernel(s),
                                                            TRACE_THREADS, s->trace_smem)) != cudaSuccess)
         return bail(cuda_fail(e, "occupancy query (is the library built for this GPU's architecture?)"));
     if (s->blocks_per_sm < 1) return bail(fail(LSCPM_ECUDA, "trace kernel does not fit on an SM"));
@@ -1246,7 +1267,7 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
     if (s->sort_smem > 24 * 1024) s->sorted = false;    // static exchange buffer + row must stay under 48 KB
     if (s->sorted) {
         if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                 &s->sort_blocks_per_sm, s->dev.n_ext > 0 ? trace_sorted_kernel<true, SORT_THREADS> : trace_sorted_kernel<false, SORT_THREADS>,
+                 &s->sort_blocks_per_sm, sorted_kernel(s),
                  SORT_THREADS, s->sort_smem)) != cudaSuccess)
             return bail(cuda_fail(e, "occupancy query (sorted kernel)"));
         if (s->sort_blocks_per_sm < 1) return bail(fail(LSCPM_ECUDA, "sorted trace kernel does not fit on an SM"));
@@ -1365,12 +1386,10 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
         // a block drinks from two work items at a time; tiny launches need fewer blocks than the grid
         const unsigned long long want = (total + SORT_THREADS - 1) / SORT_THREADS;
         const int blocks = (int)std::max<unsigned long long>(1ULL, std::min<unsigned long long>((unsigned long long)grid, want));
-        if (s->dev.n_ext > 0) trace_sorted_kernel<true, SORT_THREADS><<<blocks, SORT_THREADS, s->sort_smem, stream>>>(s->dev, a);
-        else trace_sorted_kernel<false, SORT_THREADS><<<blocks, SORT_THREADS, s->sort_smem, stream>>>(s->dev, a);
+        sorted_kernel(s)<<<blocks, SORT_THREADS, s->sort_smem, stream>>>(s->dev, a);
     } else {
         const int blocks = (int)std::min<unsigned long long>((unsigned long long)grid, (a.n_chunks + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32));
-        if (s->dev.n_ext > 0) trace_kernel<true><<<std::max(blocks, 1), TRACE_THREADS, s->trace_smem, stream>>>(s->dev, a);
-        else trace_kernel<false><<<std::max(blocks, 1), TRACE_THREADS, s->trace_smem, stream>>>(s->dev, a);
+        lane_kernel(s)<<<std::max(blocks, 1), TRACE_THREADS, s->trace_smem, stream>>>(s->dev, a);
     }
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());

@@ -1035,11 +1035,12 @@ __device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const u
 }
 
 // the sorted kernel's form: the result packed into the pending word that travels with the photon record
-template <bool EXT>
+template <bool EXT, bool FLIGHT>
 __device__ __forceinline__ int advance(const DevScene& S, Photon& p, const uint32_t w_x, unsigned& pend, unsigned& n_events) {
+    static_assert(!(EXT && FLIGHT), "plate flights assume air beyond the z faces");
     if (EXT && p.medium == MED_OUT) { pend = CLS_OUT; return -1; }
     Hit h; int cls, extra;
-    const int killed = advance_hit<true, !EXT, true>(S, p, w_x, h, cls, extra);
+    const int killed = advance_hit<true, FLIGHT, true>(S, p, w_x, h, cls, extra);
     n_events += (unsigned)extra;
     pend = pack_pending(cls, h.kind, h.face, h.container, h.adj, h.maybe_sibling);
     return killed;
@@ -1120,8 +1121,9 @@ __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, in
 }
 
 // one whole iteration: advance, then the interaction it names
-template <bool EXT, bool FOLD = true>
+template <bool EXT, bool FLIGHT, bool FOLD = true>
 __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const uint4 w, StepOut& out) {
+    static_assert(!(EXT && FLIGHT), "plate flights assume air beyond the z faces");
     out.extra = 0;
     if (EXT && p.medium == MED_OUT) {
         OutState q;
@@ -1135,7 +1137,7 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
     }
     out.ch = p.kc;
     Hit h; int cls;
-    const int killed = advance_hit<false, !EXT, FOLD>(S, p, w.x, h, cls, out.extra);
+    const int killed = advance_hit<false, FLIGHT, FOLD>(S, p, w.x, h, cls, out.extra);
     out.medium = h.container; out.kind = h.kind; out.face = h.face;
     if (killed >= 0) { out.event = EV_KILL; return killed; }
     if (cls == CLS_ABSORB) {
