@@ -155,15 +155,21 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
             WavelengthDraw wd;
             int bin = -1;
             if (fresh) {
-                bin = source_fresh<EXT>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr);
-                n_events = 0;
+                bin = source_fresh<EXT, true>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr, n_events);
                 alive = true;
             } else {
                 source_emit(S, v, p, wd);
             }
             source_finish(S, p, wd);
-            if (bin >= 0) {   // the ray never touches the plate (rare): tally straight to global memory
-                atomicAdd(A.tallies + (size_t)batch * stride + bin, 1ULL);
+            if (bin >= 0) {   // reflected off the plate at first contact, or never touched it
+                if (batch == hbatch) {
+                    atomicAdd(hist + bin, 1u);
+                    if (n_events) atomicAdd(hist + S.n_bins, n_events);
+                } else {   // the warp moved on to another work item within this refill (work items shorter than a warp)
+                    unsigned long long* row = A.tallies + (size_t)batch * stride;
+                    atomicAdd(row + bin, 1ULL);
+                    if (n_events) atomicAdd(row + S.n_bins, (unsigned long long)n_events);
+                }
                 alive = false;
             }
         }
@@ -410,7 +416,7 @@ trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ 
             rng.batch = A.batches[batch].batch_id;
             const uint4 v = rng.next();
             WavelengthDraw wd;
-            if (fresh) bin = source_fresh<EXT>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr);
+            if (fresh) bin = source_fresh<EXT, true>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr, n_events);
             else source_emit(S, v, p, wd);
             source_finish(S, p, wd);
 #ifdef SORT_SPLIT_SOURCE   // the advance of a (re-)emitted photon waits for the next deal: +1..4 % on the standard scene, -25 % with outside boxes
@@ -457,8 +463,9 @@ __global__ void emit_kernel(const __grid_constant__ DevScene S, const DevBatch* 
     Photon p;
     WavelengthDraw wd;
     float origin[3];
-    if (S.n_ext > 0) source_fresh<true>(S, *batch, spec_x, spec_cdf, spec_guide, rng, v, p, wd, origin);
-    else source_fresh<false>(S, *batch, spec_x, spec_cdf, spec_guide, rng, v, p, wd, origin);
+    unsigned events;
+    if (S.n_ext > 0) source_fresh<true, false>(S, *batch, spec_x, spec_cdf, spec_guide, rng, v, p, wd, origin, events);
+    else source_fresh<false, false>(S, *batch, spec_x, spec_cdf, spec_guide, rng, v, p, wd, origin, events);
     source_finish(S, p, wd);
     float* o = out + 7 * i;
     o[0] = origin[0]; o[1] = origin[1]; o[2] = origin[2]; o[3] = p.dx; o[4] = p.dy; o[5] = p.dz; o[6] = p.wl;

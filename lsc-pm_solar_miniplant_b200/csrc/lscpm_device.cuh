@@ -597,11 +597,16 @@ __device__ __forceinline__ int place_photon(const DevScene& S, Photon& p, float 
     return -1;
 }
 
-// generation-specific half: anchor point, direction, placement; fills the wavelength draw.  Returns -1 or BIN_MISS.
-template <bool EXT>
+// generation-specific half: anchor point, direction, placement; fills the wavelength draw.  Returns -1, BIN_MISS or
+// (ENTER) BIN_ENTRY_REFLECT.
+// ENTER (trace kernels, scenes without outside boxes): the photon's first follow() iteration - the Fresnel test on the
+// plate face it arrives at - is carried out here with the fourth word of the generation draw, instead of costing the warp
+// a whole iteration of its own; `events` is the number of interaction events that made (0 or 1).
+template <bool EXT, bool ENTER>
 __device__ __forceinline__ int source_fresh(const DevScene& S, const DevBatch& B, const float* __restrict__ spec_x,
                                             const float* __restrict__ spec_cdf, const unsigned short* __restrict__ spec_guide,
-                                            Rng& rng, const uint4 v, Photon& p, WavelengthDraw& wd, float* origin) {
+                                            Rng& rng, const uint4 v, Photon& p, WavelengthDraw& wd, float* origin, unsigned& events) {
+    events = 0u;
     const float mx = (2.f * u01(v.x) - 1.f) * B.mask_half[0];
     const float my = (2.f * u01(v.y) - 1.f) * B.mask_half[1];
     const float ax = fmaf(B.A[0], mx, fmaf(B.A[1], my, B.A[3]));
@@ -620,7 +625,19 @@ __device__ __forceinline__ int source_fresh(const DevScene& S, const DevBatch& B
     }
     const float ox = fmaf(-B.back_off, p.dx, ax), oy = fmaf(-B.back_off, p.dy, ay), oz = fmaf(-B.back_off, p.dz, az);
     if (origin) { origin[0] = ox; origin[1] = oy; origin[2] = oz; }
-    return place_photon<EXT>(S, p, ox, oy, oz, B.anchor_on_top && p.dz < 0.f, ax, ay);
+    const int bin = place_photon<EXT>(S, p, ox, oy, oz, B.anchor_on_top && p.dz < 0.f, ax, ay);
+    if (ENTER && !EXT && bin < 0 && p.medium == MED_AIR) {
+        float nx, ny, nz;
+        box_normal(p.aux & 7, nx, ny, nz);
+        const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, S.med[MED_AIR].n, S.med[MED_PLATE].n);
+        const bool reflected = u01(v.w) < I.R;
+        if (reflected) reflect_dir(p, I); else refract_dir(p, I);
+        p.steps = 1;
+        events = 1u;
+        if (reflected) return BIN_ENTRY_REFLECT;   // bounced off at first contact, leaves the scene
+        p.medium = (p.aux >> 4) & 3;
+    }
+    return bin;
 }
 
 // emission-specific half: isotropic direction, kT-restricted CDF window of the luminophore stored in p.aux
