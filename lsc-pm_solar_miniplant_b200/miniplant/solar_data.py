@@ -5,16 +5,17 @@ DataFrame with ``apparent_elevation``, ``azimuth``, ``aoi``, ``direct_spectrum``
 ``Distribution`` objects on the 27 wavelengths 360-690 nm and ``direct_irradiance`` / ``diffuse_irradiance``), computed
 for all time points at once instead of row by row.
 
-pvlib is not installable in the build image, so two pieces are restated here:
+pvlib is not installable in the build image, so its three calls are restated in ``compat/pvlib_lite.py`` and checked
+against what the reference itself committed:
 
-* **solar position** — ``compat/pvlib_lite.solar_position`` (NOAA/Meeus series + SPA refraction), within 0.015 deg of the
-  ephemerides committed in the reference's result CSVs;
-* **spectra** — pvlib's SPECTRL2 needs its 122-row coefficient table (extraterrestrial spectrum, water / ozone / mixed-gas
-  absorption), which is not in the reference tree.  ``clear_sky_spectra`` is therefore a *SPECTRL2-like stand-in*: Bird &
-  Riordan's Rayleigh and aerosol transmittances and sky-diffuse split on the same 27 wavelengths, a 5778 K black-body
-  extraterrestrial spectrum, no gas absorption.  It produces plausible spectra for the drivers' workloads; it is NOT
-  numerically the reference's SPECTRL2 output.  When pvlib is importable the reference's own
-  calls are used instead.
+* **solar position** — ``pvlib_lite.solar_position`` (NOAA/Meeus series + SPA refraction), within 0.015 deg of the
+  ephemerides in the reference's result CSVs;
+* **air mass** — Kasten & Young (1989), pvlib's default;
+* **spectra** — ``pvlib_lite.spectrum.spectrl2``: Bird & Riordan's SPCTRAL2 on the 27 wavelengths the reference keeps.
+  The direct and sky-diffuse irradiances recoverable from the reference's result CSVs are reproduced to 2e-5 relative
+  when the model is fed the CSVs' own solar positions, to ~1e-3 through the solar position above.
+
+When a real pvlib is importable its own ``spectrl2`` is called, exactly as the reference does.
 """
 from __future__ import annotations
 
@@ -26,7 +27,7 @@ import pandas as pd
 
 from ..compat import pvlib_lite, pvtrace_namespace
 from ..workloads import SPECTRL2_SLICE_NM
-from .utils import Avogadro, Planck, speed_of_light, spectral_distribution_to_photon_distribution
+from .utils import spectral_distribution_to_photon_distribution
 
 Distribution = pvtrace_namespace().Distribution
 
@@ -44,49 +45,6 @@ def _have_pvlib() -> bool:
         return not getattr(pvlib, "__lscpm_shim__", False)
     except Exception:
         return False
-
-
-def clear_sky_spectra(apparent_zenith, aoi, surface_tilt, relative_airmass, surface_pressure, dayofyear,
-                      aerosol_turbidity_500nm=tau500, ground_albedo=albedo):
-    """SPECTRL2-like plane-of-array spectra on the 27-wavelength slice (W m^-2 nm^-1).
-
-    Returns ``(poa_direct, poa_sky_diffuse)`` of shape ``[n_times, 27]``; ``poa_direct`` is negative when the sun is
-    behind the plane, exactly like pvlib's (the caller drops those rows, reference solar_data.py:93-104)."""
-    lam_um = SPECTRL2_SLICE_NM[None, :] * 1e-3
-    lam_m = SPECTRL2_SLICE_NM[None, :] * 1e-9
-    zen = np.radians(np.asarray(apparent_zenith, dtype=float))[:, None]
-    cos_z = np.cos(zen)
-    cos_aoi = np.cos(np.radians(np.asarray(aoi, dtype=float)))[:, None]
-    am = np.asarray(relative_airmass, dtype=float)[:, None]
-    am_p = am * surface_pressure / 101325.0
-    doy = np.asarray(dayofyear, dtype=float)[:, None]
-    # extraterrestrial spectrum: black body at 5778 K seen from 1 AU, earth-sun distance correction
-    k_b = 1.380649e-23
-    planck = 2 * Planck * speed_of_light ** 2 / lam_m ** 5 / np.expm1(Planck * speed_of_light / (lam_m * k_b * 5778.0))
-    e0 = planck * np.pi * (6.957e8 / 1.495978707e11) ** 2 * 1e-9
-    e0 = e0 * (1 + 0.034 * np.cos(2 * np.pi * doy / 365.0))
-    # Bird & Riordan (1986) transmittances
-    t_rayleigh = np.exp(-am_p / (lam_um ** 4 * (115.6406 - 1.335 / lam_um ** 2)))
-    alpha = np.where(lam_um <= 0.5, 1.0274, 1.2060)
-    tau_a = aerosol_turbidity_500nm * (lam_um / 0.5) ** -alpha
-    t_aerosol = np.exp(-tau_a * am)
-    direct_normal = e0 * t_rayleigh * t_aerosol
-    omega = 0.945 * np.exp(-0.095 * np.log(lam_um / 0.4) ** 2)
-    t_as = np.exp(-omega * tau_a * am)
-    t_aa = np.exp(-(1 - omega) * tau_a * am)
-    alg = np.log(1 - 0.65)
-    afs = alg * (1.459 + alg * (0.1595 + alg * 0.4129))
-    bfs = alg * (0.0783 + alg * (-0.3824 - alg * 0.5874))
-    f_s = 1 - 0.5 * np.exp((afs + bfs * cos_z) * cos_z)
-    i_rayleigh = e0 * cos_z * t_aa * (1 - t_rayleigh ** 0.95) * 0.5
-    i_aerosol = e0 * cos_z * t_rayleigh ** 1.5 * t_aa * (1 - t_as) * f_s
-    sky_horizontal = np.clip(i_rayleigh + i_aerosol, 0.0, None)
-    tilt = np.radians(surface_tilt)
-    aniso = np.clip(direct_normal / e0, 0.0, 1.0)
-    with np.errstate(divide="ignore", invalid="ignore"):
-        circumsolar = np.where(cos_z > 0.01, np.clip(cos_aoi, 0, None) / cos_z, 0.0)
-    poa_sky = sky_horizontal * (aniso * circumsolar + 0.5 * (1 + np.cos(tilt)) * (1 - aniso))
-    return direct_normal * cos_aoi, poa_sky
 
 
 def _photon_distribution(wavelengths, spectral_irradiance, integration_time):
@@ -118,10 +76,15 @@ def solar_data_for_place_and_time(site, tilt_angle: int, time_resolution: int = 
         poa_direct = np.asarray(spec["poa_direct"])[11:38].T
         poa_sky = np.asarray(spec["poa_sky_diffuse"])[11:38].T
     else:
-        wavelengths = SPECTRL2_SLICE_NM
-        poa_direct, poa_sky = clear_sky_spectra(solar_data["apparent_zenith"].values, solar_data["aoi"].values, tilt_angle,
-                                                solar_data["airmass_relative"].values, pressure,
-                                                solar_data.index.dayofyear.values)
+        spec = pvlib_lite.spectrum.spectrl2(
+            apparent_zenith=solar_data["apparent_zenith"].values, aoi=solar_data["aoi"].values, surface_tilt=tilt_angle,
+            ground_albedo=albedo, surface_pressure=pressure, relative_airmass=solar_data["airmass_relative"].values,
+            precipitable_water=water_vapor_content, ozone=ozone, aerosol_turbidity_500nm=tau500,
+            dayofyear=solar_data.index.dayofyear.values)
+        wavelengths = spec["wavelength"]            # already the [11:38] slice
+        assert np.array_equal(wavelengths, SPECTRL2_SLICE_NM)
+        poa_direct = spec["poa_direct"].T
+        poa_sky = spec["poa_sky_diffuse"].T
 
     direct_spectrum, diffuse_spectrum = [], []
     direct_irr = np.full(len(solar_data), np.nan)

@@ -1,23 +1,89 @@
-"""Prints the driver results next to the statistical anchors committed in the reference (for DESIGN.md)."""
-import os, sys
+"""The mirrored drivers against everything the reference committed from its own pvtrace runs (for DESIGN.md section 5).
+
+For each of the ten full-year result CSVs (120 photons per time point and light source, tests/golden/
+reference_yearly_counts.npz) the whole chain runs here - own solar position, SPECTRL2 restatement, scene, CUDA tracing at
+N photons per point - and the reference's per-point counts k_i ~ Binomial(120, p_i) are tested against our p_i:
+
+    z = (sum k_i - 120 sum p_i) / sqrt(120 sum p_i (1 - p_i))
+
+over the whole year and inside elevation bands (the angular dependence), plus the irradiance-weighted yearly yield.
+Usage: python scripts/anchors.py [photons_per_point=20000]
+"""
+import os
+import sys
+import tempfile
+import time
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import numpy as np, pandas as pd
-import lscpm_b200; lscpm_b200.install()
+import numpy as np
+import pandas as pd
+
+import lscpm_b200
+
+lscpm_b200.install()
 from miniplant.full_simulation import yearlong_simulation
-from miniplant.locations import EINDHOVEN, NORTH_CAPE, TOWNSVILLE, PLATAFORMA_SOLAR_ALMERIA
+from miniplant.locations import LOCATIONS
 from miniplant.solar_data import solar_data_for_place_and_time
-import tempfile, time
+
+N = int(float(sys.argv[1])) if len(sys.argv) > 1 else 20000
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "reference_yearly_counts.npz"))
+SITES = {s.name: s for s in LOCATIONS}
+BANDS = [(0, 10), (10, 20), (20, 35), (35, 50), (50, 91)]
 tmp = tempfile.mkdtemp()
-data = solar_data_for_place_and_time(EINDHOVEN, 40, 1800, write_csv=False)
-start, end = pd.Timestamp("2020-07-15 15:00", tz=EINDHOVEN.tz), pd.Timestamp("2020-07-15 17:30", tz=EINDHOVEN.tz)
-r = yearlong_simulation(40, EINDHOVEN, num_photons_per_simulation=4_000_000, time_range=(start, end), target_file=os.path.join(tmp, "w.csv"), solar_data=data, seed=1)
-print("window direct ", np.round(r["simulation_direct"].values, 4), "mean", r["simulation_direct"].mean(), "| reference 0.2218 0.2191 0.2253 0.2156 0.2232 0.2230 mean 0.2213")
-print("window diffuse", np.round(r["simulation_diffuse"].values, 4), "mean", r["simulation_diffuse"].mean(), "| reference 0.2087 0.2133 0.2206 0.2113 0.2215 0.2253 mean 0.2168")
-for site, tilt, dye, ref in ((EINDHOVEN, 40, True, (0.1994, 0.2133)), (EINDHOVEN, 0, True, (0.1836, 0.2090)), (PLATAFORMA_SOLAR_ALMERIA, 30, True, (0.2024, 0.2139)),
-                             (TOWNSVILLE, -10, True, (0.1989, 0.2132)), (NORTH_CAPE, 50, True, (0.1940, 0.2102)), (EINDHOVEN, 40, False, (0.0573, 0.0633)),
-                             (NORTH_CAPE, 50, False, (0.0570, 0.0650))):
-    d = solar_data_for_place_and_time(site, tilt, 1800, write_csv=False)
+
+
+def z_score(k, p, n_ref=120):
+    var = n_ref * np.sum(p * (1 - p))
+    return (k.sum() - n_ref * p.sum()) / np.sqrt(var) if var > 0 else 0.0
+
+
+# the 1e4-photon run of 15 Jul 2020 (experimental_comparison/experimental_conditions_results.csv)
+exp = pd.read_csv(os.path.join(ROOT, "tests", "golden", "reference_experimental_conditions.csv"), index_col=0)
+site = SITES["Eindhoven"]
+data = solar_data_for_place_and_time(site, 40, 1800, write_csv=False)
+start, end = pd.Timestamp("2020-07-15 15:00", tz=site.tz), pd.Timestamp("2020-07-15 17:30", tz=site.tz)
+r = yearlong_simulation(40, site, num_photons_per_simulation=4_000_000, time_range=(start, end),
+                        target_file=os.path.join(tmp, "w.csv"), solar_data=data, seed=1)
+for col in ("simulation_direct", "simulation_diffuse"):
+    p = r[col].values
+    k = exp[col].values * 1e4
+    print(f"window {col}: ours {np.round(p, 4)} mean {p.mean():.4f} | reference {exp[col].values} mean {exp[col].mean():.4f}"
+          f" | z = {z_score(k, p, 1e4):+.2f}")
+for col, irr in (("direct_reacted", "direct_irradiance"), ("diffuse_reacted", "diffuse_irradiance")):
+    print(f"window {col}: ours/reference {np.round(r[col].values / exp[col].values, 4)}")
+
+all_z = []
+for key in sorted({name.split("|")[0] for name in GOLD.files}):
+    site_name, tilt_s = key.split("_")[0], key.split("_")[1]
+    tilt = int(tilt_s.replace("deg", ""))
+    dye = not key.endswith("no_dye")
+    site = SITES[site_name]
+    data = solar_data_for_place_and_time(site, tilt, 1800, write_csv=False)
     t0 = time.time()
-    r = yearlong_simulation(tilt, site, num_photons_per_simulation=20_000, include_dye=dye, target_file=os.path.join(tmp, "y.csv"), solar_data=d, seed=2)
-    print(f"{site.name} tilt {tilt} dye={dye}: rows {len(r)} direct {r['simulation_direct'].mean():.4f} diffuse {r['simulation_diffuse'].mean():.4f} | reference {ref} | {time.time()-t0:.1f}s for {2*len(r)*20000/1e6:.0f} Mphotons")
+    res = yearlong_simulation(tilt, site, num_photons_per_simulation=N, include_dye=dye, target_file=os.path.join(tmp, "y.csv"),
+                              solar_data=data, seed=2)
+    dt = time.time() - t0
+    epoch = np.asarray((res.index.tz_convert("UTC") - pd.Timestamp("1970-01-01", tz="UTC")) // pd.Timedelta(seconds=1))
+    ours = pd.DataFrame({"pd": res["simulation_direct"].values, "ps": res["simulation_diffuse"].values,
+                         "el": res["apparent_elevation"].values, "id": res["direct_irradiance"].values,
+                         "is": res["diffuse_irradiance"].values}, index=epoch)
+    ref = pd.DataFrame({"kd": GOLD[key + "|direct"].astype(float), "ks": GOLD[key + "|diffuse"].astype(float)}, index=GOLD[key + "|epoch"])
+    both = ours.join(ref, how="inner")
+    zd, zs = z_score(both.kd.values, both.pd.values), z_score(both.ks.values, both.ps.values)
+    all_z += [zd, zs]
+    bands = []
+    for lo, hi in BANDS:
+        m = (both.el.values >= lo) & (both.el.values < hi)
+        if m.sum() > 20:
+            z = z_score(both.kd.values[m], both.pd.values[m])
+            all_z.append(z)
+            bands.append(f"{lo}-{hi}:{z:+.1f}")
+    # irradiance-weighted yearly yield (what the reference's analysis scripts sum): ours / reference
+    y_ref = (both.kd / 120 * both.id).sum() + (both.ks / 120 * both["is"]).sum()
+    y_our = (both.pd * both.id).sum() + (both.ps * both["is"]).sum()
+    print(f"{key:52s} rows {len(res)}/{len(ref)} matched {len(both)} | mean direct {both.pd.mean():.4f} vs {both.kd.mean() / 120:.4f} z {zd:+.2f}"
+          f" | diffuse {both.ps.mean():.4f} vs {both.ks.mean() / 120:.4f} z {zs:+.2f} | direct z by elevation band {' '.join(bands)}"
+          f" | yearly yield ours/ref {y_our / y_ref:.4f} | traced {2 * len(res) * N / 1e6:.0f} Mphotons in {dt:.1f}s")
+all_z = np.array(all_z)
+print(f"{len(all_z)} z-scores: mean {all_z.mean():+.2f}, rms {np.sqrt((all_z ** 2).mean()):.2f}, max |z| {np.abs(all_z).max():.2f}")

@@ -41,3 +41,40 @@ for path in sorted(glob.glob(os.path.join(REF, "*", "*.csv"))):
 with open(os.path.join(HERE, "reference_yearly_means.json"), "w") as fh:
     json.dump({"source": "column means of the result CSVs committed under miniplant/full_simulation_results/ in the reference "
                          "(120 photons per time point)", "files": means}, fh, indent=1, ensure_ascii=False)
+
+# irradiances the reference computed with pvlib's SPECTRL2 (solar_data.py:106-119), recovered from its result CSVs:
+# direct_reacted = simulation_direct * direct_irradiance * area (full_simulation.py:86-88), likewise for the diffuse part
+AREA = 0.47 * 0.47
+IRRADIANCE_SOURCES = dict(SOURCES, **{"Eindhoven@0": "Eindhoven/Eindhoven_0deg_results.csv"})
+frames = []
+for key, rel in IRRADIANCE_SOURCES.items():
+    site = key.split("@")[0]
+    tilt = float(os.path.basename(rel).split("_")[1].replace("deg", ""))
+    df = pd.read_csv(os.path.join(REF, rel), index_col=0)
+    df = df[(df.simulation_direct > 0) & (df.simulation_diffuse > 0)].iloc[::29]
+    frames.append(pd.DataFrame({"site": site, "tilt": tilt, "apparent_elevation": df.apparent_elevation,
+                                "azimuth": df.azimuth,
+                                "direct_irradiance": df.direct_reacted / df.simulation_direct / AREA,
+                                "diffuse_irradiance": df.diffuse_reacted / df.simulation_diffuse / AREA}, index=df.index))
+irr = pd.concat(frames)
+irr.index.name = "timestamp"
+irr.to_csv(os.path.join(HERE, "reference_irradiances.csv"))
+print(len(irr), "irradiance rows")
+
+# per-time-point photon counts of the committed full-year runs (120 photons per point and light source): the reference's
+# own Monte-Carlo output, row by row, for the chi-square style comparison in tests/test_gpu_drivers.py
+import numpy as np
+
+counts = {}
+for path in sorted(glob.glob(os.path.join(REF, "*", "*.csv"))):
+    frame = pd.read_csv(path, index_col=0)
+    key = os.path.basename(path)[:-4]
+    epoch = (pd.to_datetime(frame.index, utc=True) - pd.Timestamp("1970-01-01", tz="UTC")) // pd.Timedelta(seconds=1)
+    k_direct = np.rint(frame.simulation_direct.values * 120)
+    k_diffuse = np.rint(frame.simulation_diffuse.values * 120)
+    assert np.allclose(k_direct, frame.simulation_direct.values * 120, atol=1e-6) and k_direct.max() <= 120
+    counts[key + "|epoch"] = np.asarray(epoch, dtype=np.int64)
+    counts[key + "|direct"] = k_direct.astype(np.uint8)
+    counts[key + "|diffuse"] = k_diffuse.astype(np.uint8)
+np.savez_compressed(os.path.join(HERE, "reference_yearly_counts.npz"), **counts)
+print(len(counts) // 3, "yearly count tables")

@@ -24,11 +24,12 @@ def test_experimental_window_against_reference_csv(tmp_path, built_library):
     ours = pd.read_csv(target, index_col=0)
     ref = pd.read_csv(os.path.join(GOLDEN, "reference_experimental_conditions.csv"), index_col=0)
     assert list(ours.columns) == list(ref.columns) and len(ours) == len(ref) == 6
-    # the reference's numbers carry +-0.004 of Monte-Carlo noise (1e4 photons) and come from real SPECTRL2 spectra;
-    # ours use the SPECTRL2-like stand-in, so this is an anchor, not a parity claim
-    assert abs(ours["simulation_direct"].mean() - ref["simulation_direct"].mean()) < 0.012
-    assert abs(ours["simulation_diffuse"].mean() - ref["simulation_diffuse"].mean()) < 0.015
-    assert np.allclose(ours["direct_reacted"], ref["direct_reacted"], rtol=0.08)
+    # the reference's fractions carry +-0.004 of Monte-Carlo noise per point (1e4 photons), +-0.0017 on the mean of six;
+    # the irradiances behind *_reacted are reproduced to 1e-3 (tests/test_solar_stage.py)
+    assert abs(ours["simulation_direct"].mean() - ref["simulation_direct"].mean()) < 0.006
+    assert abs(ours["simulation_diffuse"].mean() - ref["simulation_diffuse"].mean()) < 0.006
+    assert np.allclose(ours["direct_reacted"], ref["direct_reacted"], rtol=0.06)
+    assert np.allclose(ours["diffuse_reacted"], ref["diffuse_reacted"], rtol=0.08)
 
 
 def test_full_year_in_one_launch(tmp_path, built_library):
@@ -45,8 +46,9 @@ def test_full_year_in_one_launch(tmp_path, built_library):
     assert lib.lscpm_launch_count() - before == 1              # 16 096 batches, one kernel launch
     assert len(res) == 8048
     # the reference's committed year (120 photons x 8048 points): mean 0.1994 direct, 0.2133 diffuse
-    assert abs(res["simulation_direct"].mean() - 0.1994) < 0.012
-    assert abs(res["simulation_diffuse"].mean() - 0.2133) < 0.015
+    # two independent 120-photon years: the means differ by sqrt(2) x 0.0004 of noise
+    assert abs(res["simulation_direct"].mean() - 0.1994) < 0.003
+    assert abs(res["simulation_diffuse"].mean() - 0.2133) < 0.003
     assert set(np.round(res["simulation_direct"] * 120).astype(int) - res["simulation_direct"] * 120 < 1e-9) == {True}
 
 
@@ -67,30 +69,50 @@ def test_tilt_sweep_driver(tmp_path, built_library):
     assert totals[0] != totals[40] != totals[80]
 
 
-@pytest.mark.parametrize("site_name,tilt,dye,csv", [
-    ("Eindhoven", 0, True, "Eindhoven_0deg_results.csv"),
-    ("Townsville", -10, True, "Townsville_-10deg_results.csv"),
-    ("North Cape", 50, True, "North Cape_50deg_results.csv"),
-    ("Eindhoven", 40, False, "Eindhoven_40deg_results_no_dye.csv"),
-    ("North Cape", 50, False, "North Cape_50deg_results_no_dye.csv"),
-])
-def test_yearly_means_against_the_reference_results(site_name, tilt, dye, csv, tmp_path, built_library):
-    """The whole chain (solar position, spectra stand-in, scene, tracing) against the full-year results the reference
-    committed: same number of time points, yearly mean reacted fractions within 1.5 % (dye) / 1 % (no dye) relative.
-    The reference's means carry +-0.0004 of Monte-Carlo noise (120 photons x ~8000 points)."""
-    import json
+def _binomial_z(k, p, n_ref=120):
+    """z-score of the reference's counts k_i ~ Binomial(n_ref, p_i) against our high-statistics p_i"""
+    return (k.sum() - n_ref * p.sum()) / np.sqrt(n_ref * np.sum(p * (1 - p)))
 
+
+@pytest.mark.parametrize("site_name,tilt,dye,csv", [
+    ("Eindhoven", 0, True, "Eindhoven_0deg_results"),
+    ("Eindhoven", 40, True, "Eindhoven_40deg_results"),
+    ("Townsville", -10, True, "Townsville_-10deg_results"),
+    ("North Cape", 50, True, "North Cape_50deg_results"),
+    ("Plataforma Solar de Almería", 30, True, "Plataforma Solar de Almería_30deg_results"),
+    ("Eindhoven", 40, False, "Eindhoven_40deg_results_no_dye"),
+    ("North Cape", 50, False, "North Cape_50deg_results_no_dye"),
+    ("Townsville", -10, False, "Townsville_-10deg_results_no_dye"),
+])
+def test_yearly_counts_against_the_reference_results(site_name, tilt, dye, csv, tmp_path, built_library):
+    """The whole chain (solar position, SPECTRL2 restatement, scene, CUDA tracing) against the reference's own pvtrace
+    output: the per-time-point counts of its committed full-year runs (120 photons per point, ~1e6 photons per file and
+    light source; tests/golden/reference_yearly_counts.npz).  Our p_i come from 2e4 photons per point; the reference's
+    counts must be Binomial(120, p_i): z of the yearly totals and of three elevation bands within +-4.5, yearly means
+    within 0.8 % (measured over the ten files, scripts/anchors.py: no-dye z = -0.9...+1.3, dye z = -1.1...-1.9, i.e. ours
+    +0.3 % above pvtrace with dye, inside the north star's 99.9 % band at 1e6 photons)."""
     from miniplant.full_simulation import yearlong_simulation
     from miniplant.locations import LOCATIONS
     from miniplant.solar_data import solar_data_for_place_and_time
 
-    with open(os.path.join(GOLDEN, "reference_yearly_means.json")) as fh:
-        ref = json.load(fh)["files"][csv]
+    gold = np.load(os.path.join(GOLDEN, "reference_yearly_counts.npz"))
     site = next(s for s in LOCATIONS if s.name == site_name)
     data = solar_data_for_place_and_time(site, tilt, 1800, write_csv=False)
-    assert abs(len(data) - ref["rows"]) <= 1
-    res = yearlong_simulation(tilt, site, num_photons_per_simulation=5000, include_dye=dye, target_file=tmp_path / "y.csv",
+    res = yearlong_simulation(tilt, site, num_photons_per_simulation=20000, include_dye=dye, target_file=tmp_path / "y.csv",
                               solar_data=data, seed=9)
-    tol = 0.015 if dye else 0.01
-    assert abs(res["simulation_direct"].mean() / ref["simulation_direct_mean"] - 1) < tol
-    assert abs(res["simulation_diffuse"].mean() / ref["simulation_diffuse_mean"] - 1) < tol + 0.005
+    epoch = np.asarray((res.index.tz_convert("UTC") - pd.Timestamp("1970-01-01", tz="UTC")) // pd.Timedelta(seconds=1))
+    ours = pd.DataFrame({"pd": res["simulation_direct"].values, "ps": res["simulation_diffuse"].values,
+                         "el": res["apparent_elevation"].values}, index=epoch)
+    ref = pd.DataFrame({"kd": gold[csv + "|direct"].astype(float), "ks": gold[csv + "|diffuse"].astype(float)},
+                       index=gold[csv + "|epoch"])
+    both = ours.join(ref, how="inner")
+    assert len(both) >= len(ref) - 1 and abs(len(res) - len(ref)) <= 1
+    tol = 0.008 if dye else 0.012      # the reference's yearly means carry 0.2 % (dye) / 0.4 % (no dye) of Monte-Carlo noise
+    assert abs(both.pd.mean() / (both.kd.mean() / 120) - 1) < tol
+    assert abs(both.ps.mean() / (both.ks.mean() / 120) - 1) < tol
+    assert abs(_binomial_z(both.kd.values, both.pd.values)) < 4.5
+    assert abs(_binomial_z(both.ks.values, both.ps.values)) < 4.5
+    for lo, hi in ((0, 15), (15, 35), (35, 91)):
+        m = (both.el.values >= lo) & (both.el.values < hi)
+        if m.sum() > 200:
+            assert abs(_binomial_z(both.kd.values[m], both.pd.values[m])) < 4.5, (lo, hi)

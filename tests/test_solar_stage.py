@@ -41,9 +41,41 @@ def test_solar_data_for_place_and_time():
         assert frame["azimuth"].count() == points[name]
 
 
-def test_year_has_the_reference_row_count_and_plausible_irradiance():
-    """Anchors (not parity: the spectra come from the SPECTRL2-like stand-in): same 8048 half-hour points as the
-    reference's Eindhoven 40 deg run; integrated direct photon flux of the experimental window within 3 %."""
+def test_spectrl2_reproduces_the_reference_irradiances():
+    """Pins the SPECTRL2 restatement on reference output: the direct / sky-diffuse irradiances pvlib produced for the
+    reference's committed full-year runs (recovered from the result CSVs, tests/golden/make_ephemerides.py), 1394 time
+    points over four sites and five tilts, fed with the CSVs' own solar positions.  Relative error <= 1e-4 everywhere
+    (measured: median 2e-5, maximum 7e-5)."""
+    from lscpm_b200.compat import pvlib_lite
+    from miniplant import solar_data
+    from miniplant.utils import spectral_distribution_to_photon_distribution
+    from lscpm_b200.compat.pvtrace_api import Distribution
+
+    gold = pd.read_csv(os.path.join(GOLDEN, "reference_irradiances.csv"), index_col=0)
+    sites = _sites()
+    for (name, tilt), group in gold.groupby(["site", "tilt"]):
+        site = sites[name]
+        doy = pd.to_datetime(group.index, utc=True).tz_convert(site.tz).dayofyear.values
+        zenith = 90.0 - group["apparent_elevation"].values
+        spec = pvlib_lite.spectrum.spectrl2(
+            apparent_zenith=zenith, aoi=pvlib_lite.irradiance.aoi(tilt, 180, zenith, group["azimuth"].values),
+            surface_tilt=tilt, ground_albedo=solar_data.albedo, surface_pressure=pvlib_lite.alt2pres(site.altitude),
+            relative_airmass=pvlib_lite.relative_airmass(zenith), precipitable_water=solar_data.water_vapor_content,
+            ozone=solar_data.ozone, aerosol_turbidity_500nm=solar_data.tau500, dayofyear=doy)
+        assert spec["wavelength"].shape == (27,) and spec["poa_direct"].shape == (27, len(group))
+        for key, column in (("poa_direct", "direct_irradiance"), ("poa_sky_diffuse", "diffuse_irradiance")):
+            got = np.empty(len(group))
+            for i in range(len(group)):   # the reference's own conversion and integration (utils.py:26-36, solar_data.py:114-119)
+                d = spectral_distribution_to_photon_distribution(Distribution(spec["wavelength"], spec[key][:, i]), 1800)
+                got[i] = np.trapezoid(d._y, d._x)
+            err = np.abs(got / group[column].values - 1)
+            assert err.max() < 1e-4, (name, tilt, key, err.max())
+
+
+def test_year_has_the_reference_row_count_and_irradiance():
+    """The whole solar stage (own solar position -> air mass -> SPECTRL2 restatement): same 8048 half-hour points as
+    the reference's Eindhoven 40 deg run, irradiances of the experimental window within 1e-3, yearly irradiance-weighted
+    mean within 2e-4 of the reference's (a 0.015 deg position error only matters at sunrise and sunset)."""
     from miniplant.locations import EINDHOVEN
     from miniplant.solar_data import solar_data_for_place_and_time
 
@@ -54,11 +86,20 @@ def test_year_has_the_reference_row_count_and_plausible_irradiance():
     assert len(window) == len(exp) == 6
     ref_direct = (exp["direct_reacted"] / exp["simulation_direct"] / 0.47 ** 2).values
     ref_diffuse = (exp["diffuse_reacted"] / exp["simulation_diffuse"] / 0.47 ** 2).values
-    assert np.allclose(window["direct_irradiance"].values, ref_direct, rtol=0.03)
-    assert np.allclose(window["diffuse_irradiance"].values, ref_diffuse, rtol=0.25)
+    assert np.allclose(window["direct_irradiance"].values, ref_direct, rtol=1e-3)
+    assert np.allclose(window["diffuse_irradiance"].values, ref_diffuse, rtol=1e-3)
     assert np.allclose(window["apparent_elevation"].values, exp["apparent_elevation"].values, atol=0.01)
     spectrum = window["direct_spectrum"].iloc[0]
     assert len(spectrum._x) == 27 and spectrum._x[0] == 360 and spectrum._x[-1] == 690
+    gold = pd.read_csv(os.path.join(GOLDEN, "reference_irradiances.csv"), index_col=0)
+    gold = gold[(gold.site == "Eindhoven") & (gold.tilt == 40)]
+    ours = frame.copy()
+    ours.index = ours.index.map(str)
+    ours = ours.loc[gold.index]
+    for column in ("direct_irradiance", "diffuse_irradiance"):
+        ratio = ours[column].values / gold[column].values
+        assert abs(np.median(ratio) - 1) < 2e-4, (column, np.median(ratio))
+        assert abs(np.average(ratio, weights=gold[column].values) - 1) < 2e-4, column
 
 
 @pytest.mark.parametrize("tilt,elev,az", [(0, 90, 180), (40, 50, 180), (-10, 35.5, 213.5), (25, 5, 95)])
