@@ -172,6 +172,23 @@ class spectrum:  # namespace mirroring ``pvlib.spectrum``
                 "poa_global": poa_direct + poa_sky + poa_ground}
 
 
+class _Zone:
+    """The one ``pytz`` timezone method the reference calls on ``Location.pytz`` (``localize``,
+    experimental_comparison/simulate_experimental_conditions.py:15-16), on top of ``zoneinfo``."""
+
+    def __init__(self, name):
+        from zoneinfo import ZoneInfo
+
+        self.zone = name
+        self._info = ZoneInfo(name)
+
+    def localize(self, naive):
+        return naive.replace(tzinfo=self._info)
+
+    def __repr__(self):
+        return f"<tz {self.zone}>"
+
+
 class Location:
     """Site record with the two ``pvlib.location.Location`` methods the solar stage calls."""
 
@@ -181,6 +198,12 @@ class Location:
         self.tz = tz
         self.altitude = altitude
         self.name = name
+        try:
+            import pytz  # type: ignore
+
+            self.pytz = pytz.timezone(tz)
+        except ImportError:
+            self.pytz = _Zone(tz)
 
     def get_solarposition(self, times, pressure=None, temperature=12.0):
         return solar_position(times, self.latitude, self.longitude, self.altitude, pressure, temperature)

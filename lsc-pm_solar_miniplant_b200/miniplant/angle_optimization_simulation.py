@@ -54,3 +54,13 @@ def evaluate_tilt_angle(tilt_angle: int, location, workers: int = None, time_res
     target_file.parent.mkdir(parents=True, exist_ok=True)
     results.to_csv(target_file, columns=("apparent_elevation", "azimuth", "simulation_direct", "direct_reacted"))
     return results
+
+
+if __name__ == "__main__":   # reference :111-120
+    from miniplant.locations import TOWNSVILLE
+
+    site = TOWNSVILLE
+
+    tilt_range = list(range(0, -40, -5))
+    for tilt in tilt_range:
+        evaluate_tilt_angle(tilt_angle=tilt, location=site, workers=12, time_resolution=1800)

@@ -92,3 +92,21 @@ def yearlong_simulation(
     results.to_csv(target_file, columns=("apparent_elevation", "azimuth", "simulation_direct", "direct_reacted",
                                          "simulation_diffuse", "diffuse_reacted"))
     return results
+
+
+if __name__ == "__main__":   # reference :128-148
+    logging.getLogger("pvtrace").setLevel(logging.WARNING)  # use logging.DEBUG for more printouts
+
+    from miniplant.locations import EINDHOVEN
+
+    sim_to_run = [(EINDHOVEN, 40)]
+
+    for sim_params in sim_to_run:
+        print(f"Now simulating {sim_params[0].name} at {sim_params[1]} deg tilt angle")
+        yearlong_simulation(
+            tilt_angle=sim_params[1],
+            location=sim_params[0],
+            workers=12,
+            time_resolution=60 * 30,
+            include_dye=True,
+        )

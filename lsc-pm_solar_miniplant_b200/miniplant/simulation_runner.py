@@ -114,3 +114,18 @@ def run_diffuse_simulation(
         include_dye=include_dye,
     )
     return _common_simulation_runner(scene, num_photons, render, workers, **runner_kwargs)
+
+
+if __name__ == "__main__":   # reference :127-143, without the Meshcat window (render=True needs the renderer)
+    res = run_direct_simulation(
+        tilt_angle=40,
+        solar_elevation=50,
+        solar_azimuth=180,
+        add_bottom_PV=True,
+        add_side_PV=True,
+        num_photons=100,
+    )
+
+    bottom = res[-2]
+    side = res[-1]
+    print(f"SIMU ENDED - bottom={bottom} side={side}")

@@ -199,3 +199,17 @@ def test_oracle_against_the_reference_yearly_results():
         n = len(rows)
         assert abs(frac[:n].mean() / ref[key]["simulation_direct_mean"] - 1) < 0.025, (dye, frac[:n].mean())
         assert abs(frac[n:].mean() / ref[key]["simulation_diffuse_mean"] - 1) < 0.025, (dye, frac[n:].mean())
+
+
+def test_experimental_conditions_script_window():
+    """reference experimental_comparison/simulate_experimental_conditions.py: the script's window, built with
+    ``Location.pytz.localize``, selects the six half-hour points of the committed result CSV."""
+    from miniplant.experimental_comparison import simulate_experimental_conditions as script
+    from miniplant.locations import EINDHOVEN
+    from miniplant.solar_data import solar_data_for_place_and_time
+
+    assert script.XP_START.utcoffset().total_seconds() == 7200 and script.target_file.name == "experimental_conditions_results.csv"
+    frame = solar_data_for_place_and_time(EINDHOVEN, 40, 1800, write_csv=False)
+    window = frame.loc[script.time_interval[0]: script.time_interval[1]]
+    exp = pd.read_csv(os.path.join(GOLDEN, "reference_experimental_conditions.csv"), index_col=0)
+    assert [str(t) for t in window.index] == list(exp.index)
