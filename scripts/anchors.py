@@ -16,13 +16,16 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np
 import pandas as pd
 
 import lscpm_b200
 
 lscpm_b200.install()
-from miniplant.full_simulation import yearlong_simulation
+from helpers import binomial_z, frame_epoch, reference_counts
+from lscpm_b200 import lights
+from miniplant.full_simulation import trace_time_points, yearlong_simulation
 from miniplant.locations import LOCATIONS
 from miniplant.solar_data import solar_data_for_place_and_time
 
@@ -64,19 +67,18 @@ for key in sorted({name.split("|")[0] for name in GOLD.files}):
     res = yearlong_simulation(tilt, site, num_photons_per_simulation=N, include_dye=dye, target_file=os.path.join(tmp, "y.csv"),
                               solar_data=data, seed=2)
     dt = time.time() - t0
-    epoch = np.asarray((res.index.tz_convert("UTC") - pd.Timestamp("1970-01-01", tz="UTC")) // pd.Timedelta(seconds=1))
     ours = pd.DataFrame({"pd": res["simulation_direct"].values, "ps": res["simulation_diffuse"].values,
                          "el": res["apparent_elevation"].values, "id": res["direct_irradiance"].values,
-                         "is": res["diffuse_irradiance"].values}, index=epoch)
-    ref = pd.DataFrame({"kd": GOLD[key + "|direct"].astype(float), "ks": GOLD[key + "|diffuse"].astype(float)}, index=GOLD[key + "|epoch"])
+                         "is": res["diffuse_irradiance"].values}, index=frame_epoch(res))
+    ref = reference_counts(GOLD, key).rename(columns={"direct": "kd", "diffuse": "ks"})
     both = ours.join(ref, how="inner")
-    zd, zs = z_score(both.kd.values, both.pd.values), z_score(both.ks.values, both.ps.values)
+    zd, zs = binomial_z(both.kd.values, both.pd.values, 120), binomial_z(both.ks.values, both.ps.values, 120)
     all_z += [zd, zs]
     bands = []
     for lo, hi in BANDS:
         m = (both.el.values >= lo) & (both.el.values < hi)
         if m.sum() > 20:
-            z = z_score(both.kd.values[m], both.pd.values[m])
+            z = binomial_z(both.kd.values[m], both.pd.values[m], 120)
             all_z.append(z)
             bands.append(f"{lo}-{hi}:{z:+.1f}")
     # irradiance-weighted yearly yield (what the reference's analysis scripts sum): ours / reference
@@ -87,3 +89,30 @@ for key in sorted({name.split("|")[0] for name in GOLD.files}):
           f" | yearly yield ours/ref {y_our / y_ref:.4f} | traced {2 * len(res) * N / 1e6:.0f} Mphotons in {dt:.1f}s")
 all_z = np.array(all_z)
 print(f"{len(all_z)} z-scores: mean {all_z.mean():+.2f}, rms {np.sqrt((all_z ** 2).mean()):.2f}, max |z| {np.abs(all_z).max():.2f}")
+
+
+# ---- the committed tilt sweeps (angle_optimization_simulation.py: 100 photons per point, direct light only) ------------
+SWEEP = np.load(os.path.join(ROOT, "tests", "golden", "reference_sweep_counts.npz"))
+print("\ntilt sweeps (100 photons per point): file, rows, mean ours vs reference, z, yearly sum(direct_reacted) ours/ref")
+sweep_z = {True: [], False: []}
+pooled = {True: [0.0, 0.0, 0.0], False: [0.0, 0.0, 0.0]}
+for key in sorted({name.split("|")[0] for name in SWEEP.files}):
+    dye = "_no_dye_" not in key
+    site = SITES[key.split("_")[0]]
+    tilt = int(key.split("_")[-1].replace("deg", ""))
+    if site.name == "Townsville":
+        tilt = -tilt                      # swept over range(0, -40, -5), file names carry |tilt|
+    data = solar_data_for_place_and_time(site, tilt, 1800, write_csv=False)
+    batch = [lights.direct_light(tilt, r["apparent_elevation"], r["azimuth"], r["direct_spectrum"]) for _, r in data.iterrows()]
+    p = trace_time_points(tilt, batch, N, include_dye=dye, seed=3)
+    both = pd.DataFrame({"p": p, "irr": data["direct_irradiance"].values}, index=frame_epoch(data)).join(reference_counts(SWEEP, key), how="inner")
+    z = binomial_z(both.direct.values, both.p.values, 100)
+    sweep_z[dye].append(z)
+    pooled[dye][0] += both.direct.sum(); pooled[dye][1] += 100 * both.p.sum(); pooled[dye][2] += 100 * (both.p * (1 - both.p)).sum()
+    print(f"{key:44s} rows {len(data)}/{len(SWEEP[key + '|direct'])} | {both.p.mean():.4f} vs {both.direct.mean() / 100:.4f} z {z:+.2f}"
+          f" | yield {(both.p * both.irr).sum() / (both.direct / 100 * both.irr).sum():.4f}")
+for dye in (True, False):
+    zs = np.array(sweep_z[dye])
+    k, e, v = pooled[dye]
+    print(f"{'dye' if dye else 'no dye'}: {len(zs)} files, z mean {zs.mean():+.2f} rms {np.sqrt((zs ** 2).mean()):.2f} max |z| {np.abs(zs).max():.2f};"
+          f" pooled reference photons {e / 1:.0f} expected vs {k:.0f} counted: ratio ours/ref {e / k:.5f}, pooled z {(k - e) / np.sqrt(v):+.2f}")

@@ -65,16 +65,44 @@ print(len(irr), "irradiance rows")
 # own Monte-Carlo output, row by row, for the chi-square style comparison in tests/test_gpu_drivers.py
 import numpy as np
 
+EPOCH0 = 1577800800   # 2019-12-31T14:00Z, the earliest local midnight of 1 Jan 2020 among the sites; time points are
+                      # stored as delta-coded half-hour slots after it (uint16)
+
+
+def slots(index):
+    epoch = np.asarray((pd.to_datetime(index, utc=True) - pd.Timestamp("1970-01-01", tz="UTC")) // pd.Timedelta(seconds=1), dtype=np.int64)
+    assert np.all((epoch - EPOCH0) % 1800 == 0) and epoch.min() >= EPOCH0 and (epoch.max() - EPOCH0) // 1800 < 65536
+    return np.diff((epoch - EPOCH0) // 1800, prepend=0).astype(np.uint16)   # delta-coded: cumsum() restores the slots
+
+
 counts = {}
 for path in sorted(glob.glob(os.path.join(REF, "*", "*.csv"))):
     frame = pd.read_csv(path, index_col=0)
     key = os.path.basename(path)[:-4]
-    epoch = (pd.to_datetime(frame.index, utc=True) - pd.Timestamp("1970-01-01", tz="UTC")) // pd.Timedelta(seconds=1)
     k_direct = np.rint(frame.simulation_direct.values * 120)
     k_diffuse = np.rint(frame.simulation_diffuse.values * 120)
     assert np.allclose(k_direct, frame.simulation_direct.values * 120, atol=1e-6) and k_direct.max() <= 120
-    counts[key + "|epoch"] = np.asarray(epoch, dtype=np.int64)
+    counts[key + "|slot"] = slots(frame.index)
     counts[key + "|direct"] = k_direct.astype(np.uint8)
     counts[key + "|diffuse"] = k_diffuse.astype(np.uint8)
 np.savez_compressed(os.path.join(HERE, "reference_yearly_counts.npz"), **counts)
 print(len(counts) // 3, "yearly count tables")
+
+# per-time-point counts of the committed tilt-sweep runs (angle_optimization_simulation.py, 100 photons per point, direct
+# light only): file name carries |tilt| (Townsville is swept over negative tilts, angle_optimization_simulation.py:116)
+SWEEP = "/root/reference/miniplant/simulation_results"
+sweep = {}
+for site in ("Eindhoven", "North Cape", "Plataforma Solar de Almería", "Townsville"):
+    for path in sorted(glob.glob(os.path.join(SWEEP, site, f"{site}_*deg_results.csv"))):
+        frame = pd.read_csv(path, index_col=0)
+        if "simulation_direct" not in frame.columns or len(frame) == 0:
+            continue
+        k = np.rint(frame.simulation_direct.values * 100)
+        if not np.allclose(k, frame.simulation_direct.values * 100, atol=1e-6) or k.max() > 100:
+            print("skipped (not 100 photons per point):", os.path.basename(path))
+            continue
+        key = os.path.basename(path)[:-len("_results.csv")]
+        sweep[key + "|slot"] = slots(frame.index)
+        sweep[key + "|direct"] = k.astype(np.uint8)
+np.savez_compressed(os.path.join(HERE, "reference_sweep_counts.npz"), **sweep)
+print(len(sweep) // 2, "tilt-sweep count tables")

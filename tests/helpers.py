@@ -69,3 +69,30 @@ def assert_tallies_agree(names, a, b, label="", resample=None, z=Z_999):
         again = failing(np.asarray(resample(), dtype=np.int64))
         bad = {k: v for k, v in bad.items() if k in again}
     assert not bad, f"{label}: outside the 99.9% band (also after one independent re-draw): {sorted(bad.values())}"
+
+
+# ---- the reference's committed per-time-point counts (tests/golden/make_ephemerides.py) ---------------------------
+REFERENCE_EPOCH0 = 1577800800   # 2019-12-31T14:00Z
+
+
+def reference_counts(npz, key):
+    """DataFrame of the reference's counts for one result file, indexed by UTC epoch seconds."""
+    import pandas as pd
+
+    epoch = REFERENCE_EPOCH0 + 1800 * np.cumsum(npz[key + "|slot"].astype(np.int64))
+    columns = {name.split("|")[1]: npz[name].astype(float) for name in npz.files
+               if name.startswith(key + "|") and not name.endswith("|slot")}
+    return pd.DataFrame(columns, index=epoch)
+
+
+def frame_epoch(frame):
+    """UTC epoch seconds of a tz-aware DatetimeIndex'ed frame"""
+    import pandas as pd
+
+    return np.asarray((frame.index.tz_convert("UTC") - pd.Timestamp("1970-01-01", tz="UTC")) // pd.Timedelta(seconds=1))
+
+
+def binomial_z(k, p, n_ref):
+    """z-score of reference counts k_i ~ Binomial(n_ref, p_i) against high-statistics p_i"""
+    var = n_ref * np.sum(p * (1 - p))
+    return float((k.sum() - n_ref * p.sum()) / np.sqrt(var)) if var > 0 else 0.0

@@ -69,11 +69,6 @@ def test_tilt_sweep_driver(tmp_path, built_library):
     assert totals[0] != totals[40] != totals[80]
 
 
-def _binomial_z(k, p, n_ref=120):
-    """z-score of the reference's counts k_i ~ Binomial(n_ref, p_i) against our high-statistics p_i"""
-    return (k.sum() - n_ref * p.sum()) / np.sqrt(n_ref * np.sum(p * (1 - p)))
-
-
 @pytest.mark.parametrize("site_name,tilt,dye,csv", [
     ("Eindhoven", 0, True, "Eindhoven_0deg_results"),
     ("Eindhoven", 40, True, "Eindhoven_40deg_results"),
@@ -91,6 +86,7 @@ def test_yearly_counts_against_the_reference_results(site_name, tilt, dye, csv, 
     counts must be Binomial(120, p_i): z of the yearly totals and of three elevation bands within +-4.5, yearly means
     within 0.8 % (measured over the ten files, scripts/anchors.py: no-dye z = -0.9...+1.3, dye z = -1.1...-1.9, i.e. ours
     +0.3 % above pvtrace with dye, inside the north star's 99.9 % band at 1e6 photons)."""
+    from helpers import binomial_z, frame_epoch, reference_counts
     from miniplant.full_simulation import yearlong_simulation
     from miniplant.locations import LOCATIONS
     from miniplant.solar_data import solar_data_for_place_and_time
@@ -100,19 +96,39 @@ def test_yearly_counts_against_the_reference_results(site_name, tilt, dye, csv, 
     data = solar_data_for_place_and_time(site, tilt, 1800, write_csv=False)
     res = yearlong_simulation(tilt, site, num_photons_per_simulation=20000, include_dye=dye, target_file=tmp_path / "y.csv",
                               solar_data=data, seed=9)
-    epoch = np.asarray((res.index.tz_convert("UTC") - pd.Timestamp("1970-01-01", tz="UTC")) // pd.Timedelta(seconds=1))
     ours = pd.DataFrame({"pd": res["simulation_direct"].values, "ps": res["simulation_diffuse"].values,
-                         "el": res["apparent_elevation"].values}, index=epoch)
-    ref = pd.DataFrame({"kd": gold[csv + "|direct"].astype(float), "ks": gold[csv + "|diffuse"].astype(float)},
-                       index=gold[csv + "|epoch"])
+                         "el": res["apparent_elevation"].values}, index=frame_epoch(res))
+    ref = reference_counts(gold, csv).rename(columns={"direct": "kd", "diffuse": "ks"})
     both = ours.join(ref, how="inner")
     assert len(both) >= len(ref) - 1 and abs(len(res) - len(ref)) <= 1
     tol = 0.008 if dye else 0.012      # the reference's yearly means carry 0.2 % (dye) / 0.4 % (no dye) of Monte-Carlo noise
     assert abs(both.pd.mean() / (both.kd.mean() / 120) - 1) < tol
     assert abs(both.ps.mean() / (both.ks.mean() / 120) - 1) < tol
-    assert abs(_binomial_z(both.kd.values, both.pd.values)) < 4.5
-    assert abs(_binomial_z(both.ks.values, both.ps.values)) < 4.5
+    assert abs(binomial_z(both.kd.values, both.pd.values, 120)) < 4.5
+    assert abs(binomial_z(both.ks.values, both.ps.values, 120)) < 4.5
     for lo, hi in ((0, 15), (15, 35), (35, 91)):
         m = (both.el.values >= lo) & (both.el.values < hi)
         if m.sum() > 200:
-            assert abs(_binomial_z(both.kd.values[m], both.pd.values[m])) < 4.5, (lo, hi)
+            assert abs(binomial_z(both.kd.values[m], both.pd.values[m], 120)) < 4.5, (lo, hi)
+
+
+def test_tilt_sweep_counts_against_the_reference_results(built_library):
+    """The reference's committed tilt sweeps (angle_optimization_simulation.py, 100 photons per point, direct light):
+    Eindhoven at 0 / 30 / 60 / 90 degrees with dye and 60 / 90 degrees without.  Same binomial test as above."""
+    from helpers import binomial_z, frame_epoch, reference_counts
+    from lscpm_b200 import lights
+    from miniplant.full_simulation import trace_time_points
+    from miniplant.locations import EINDHOVEN
+    from miniplant.solar_data import solar_data_for_place_and_time
+
+    gold = np.load(os.path.join(GOLDEN, "reference_sweep_counts.npz"))
+    for key, tilt, dye in (("Eindhoven_0deg", 0, True), ("Eindhoven_30deg", 30, True), ("Eindhoven_60deg", 60, True),
+                           ("Eindhoven_90deg", 90, True), ("Eindhoven_no_dye_60deg", 60, False),
+                           ("Eindhoven_no_dye_90deg", 90, False)):
+        data = solar_data_for_place_and_time(EINDHOVEN, tilt, 1800, write_csv=False)
+        batch = [lights.direct_light(tilt, r["apparent_elevation"], r["azimuth"], r["direct_spectrum"]) for _, r in data.iterrows()]
+        p = trace_time_points(tilt, batch, 20000, include_dye=dye, seed=13)
+        both = pd.DataFrame({"p": p}, index=frame_epoch(data)).join(reference_counts(gold, key), how="inner")
+        assert len(both) >= len(gold[key + "|direct"]) - 2, key
+        assert abs(binomial_z(both.direct.values, both.p.values, 100)) < 4.5, key
+        assert abs(both.p.mean() / (both.direct.mean() / 100) - 1) < (0.01 if dye else 0.015), key
