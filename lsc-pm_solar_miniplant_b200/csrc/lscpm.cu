@@ -1252,6 +1252,10 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
         for (int c = 0; c < s->dev.med[MED_PLATE].n_comp; ++c)
             if (s->dev.med[MED_PLATE].comp[c].kind == COMP_LUMINOPHORE) s->flight = true;
     if (const char* f = getenv("LSCPM_PLATE_FLIGHTS")) s->flight = s->dev.n_ext == 0 && f[0] == '1';
+#ifdef LSCPM_DIAG
+    s->dev.diag_emit = getenv("LSCPM_DIAG_EMIT") ? atoi(getenv("LSCPM_DIAG_EMIT")) : 0;
+    s->dev.diag_no_sibling = getenv("LSCPM_DIAG_NO_SIBLING") ? atoi(getenv("LSCPM_DIAG_NO_SIBLING")) : 0;
+#endif
     s->trace_smem = (size_t)(TRACE_THREADS / 32) * (size_t)(s->dev.n_bins + LSCPM_N_COUNTERS) * sizeof(unsigned int);
     if (s->trace_smem > 200 * 1024) return bail(fail(LSCPM_EUNSUPPORTED, "too many tally bins for the per-warp shared rows"));
     if (s->trace_smem > 48 * 1024 &&

@@ -133,6 +133,10 @@ struct DevScene {
     const int* abs_base_outer; // [n_ch]
     const int* abs_base_inner; // [n_ch]
     float w2l[9];              // rotation world -> plate-local (row-major)
+#ifdef LSCPM_DIAG              // diagnostic build only (scripts/dye_bias.py): alternatives to the restated pvtrace rules
+    int diag_emit;             // 0 kT window (the rule), 1 redshift (no thermal allowance), 2 full emission spectrum, 3 window of 3 kT
+    int diag_no_sibling;       // leaving a tube wall always sees the plate as adjacent
+#endif
 };
 
 struct DevBatch {
@@ -649,8 +653,13 @@ __device__ __forceinline__ void source_emit(const DevScene& S, const uint4 v, Ph
     p.dx = st * cp; p.dy = st * sp; p.dz = mu;
     const int t = (p.aux >> 16) & 0xff;
     const DevTable& T = S.tab[t];
+#ifdef LSCPM_DIAG
+    const float ev = fdiv(HC_EV_NM, p.wl) + (S.diag_emit == 1 ? 0.f : (S.diag_emit == 3 ? 3.f : 1.5f) * KB_EV * 300.f);
+    const float p1 = S.diag_emit == 2 ? 0.f : table_at(S, t, fdiv(HC_EV_NM, ev), S.tab_cdf);
+#else
     const float ev = fdiv(HC_EV_NM, p.wl) + 1.5f * KB_EV * 300.f;
     const float p1 = table_at(S, t, fdiv(HC_EV_NM, ev), S.tab_cdf);
+#endif
     wd.cdf = S.tab_cdf + T.begin; wd.xs = S.tab_x + T.begin; wd.guide = S.tab_inv + T.inv_begin;
     wd.n = T.n; wd.buckets = INV_CDF_BUCKETS; wd.u = fmaf(1.f - p1, u01(v.z), p1); wd.constant = p.wl;
     p.aux = (p.aux & 0xffff) | 256;     // has emitted
@@ -1102,6 +1111,9 @@ __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, in
         const float inv = frsqrt(fmaf(p.xr, p.xr, p.z * p.z));
         nx = p.xr * inv; ny = 0.f; nz = p.z * inv;
         // leaving the tube wall: pvtrace's adjacent is whatever the straight continuation meets next
+#ifdef LSCPM_DIAG
+        if (S.diag_no_sibling) maybe_sibling = false;
+#endif
         if (maybe_sibling && sibling_ahead(S, p.kc, p.xr, p.y, p.z, p.dx, p.dy, p.dz) >= 0) adj = MED_OUTER;
     }
     float n2 = S.med[adj].n;
