@@ -396,7 +396,7 @@ trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ 
             n_events += 1u;
             int ev;
             bin = interact_surface<EXT>(S, p, pending_kind(pend), pending_face(pend), pending_container(pend), pending_adj(pend),
-                                        pending_sibling(pend), u_surf, ev);
+                                        u_surf, ev);
             fly = bin < 0;
         } else if (cls == CLS_CELL) {
             fly = true;
@@ -489,7 +489,7 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
     p.xr = q.xr; p.y = q.y; p.z = q.z - S.zc; p.dx = q.dx; p.dy = q.dy; p.dz = q.dz; p.kc = q.kc; p.medium = q.medium;
     p.wl = 555.f; p.a_plate = p.a_outer = p.a_inner = 0.f; p.steps = 0; p.aux = 0;
     float nx, ny, nz;
-    int ext_node = 0;      // probe bookkeeping: outside box hit (i+1) or lending its index as adjacent (-(i+1))
+    int ext_node = 0;      // probe bookkeeping: outside box hit (i+1)
     if (q.medium == MED_AIR && S.n_ext > 0) {
         float t; int node, face;
         const bool inside = outside_hit(S, abs_x(S, p), p.y, q.z, p.dx, p.dy, p.dz, -1, t, node, face);
@@ -543,23 +543,15 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
         o.found = 1; o.t = travelled + h.t; o.kind = h.kind; o.face = h.face; o.ch = p.kc; o.container = h.container; o.adj = h.adj;
         if (h.kind == SURF_BOX || h.kind == SURF_CAP) {
             box_normal(h.face, nx, ny, nz);
-            if (S.n_ext > 0) {
-                const int e = ext_ahead(S, h.face, axis_x(S, p.kc) + xr, yy, zz + S.zc, p.dx, p.dy, p.dz);
-                if (e >= 0) ext_node = -(e + 1);
-            }
         } else {
             const float inv = rsqrtf(xr * xr + zz * zz);
             nx = xr * inv; ny = 0.f; nz = zz * inv;
-            if (h.kind == SURF_OUTER && p.medium == MED_OUTER) {
-                const int j = sibling_ahead(S, p.kc, xr, yy, zz, p.dx, p.dy, p.dz);
-                if (j >= 0) { o.adj = MED_OUTER; o.ch = j; }
-            }
         }
+        (void)yy;
     }
     o.n1 = S.med[o.container].n; o.n2 = S.med[o.adj].n;
     if (ext_node > 0) o.n2 = S.ext[ext_node - 1].n;
     if (ext_node > 0 && o.found == 2) { o.n1 = S.ext[ext_node - 1].n; o.n2 = S.med[MED_AIR].n; }
-    if (ext_node < 0) o.n2 = S.ext[-ext_node - 1].n;
     o.ext = ext_node;
     const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, o.n1, o.n2);
     o.R = I.R; o.cosi = I.cosi; o.nx = I.nx; o.ny = I.ny; o.nz = I.nz;
@@ -967,16 +959,6 @@ int lower_scene(const LscpmSceneDesc* d, LscpmScene* s) {
         b.abs_bin = s->layout.abs_base[node];
         b.exit_base = s->layout.exit_base[node];
     }
-    for (int f = 0; f < 6; ++f) {
-        D.ext_beyond[f] = 0u;
-        const double plate_half[3] = {(double)D.hx, (double)D.hy, (double)D.hz};
-        const int ax = f / 2;
-        for (int e = 0; e < D.n_ext; ++e) {
-            const double c[3] = {ext_centres[e].x, ext_centres[e].y, ext_centres[e].z}, h[3] = {ext_halves[e].x, ext_halves[e].y, ext_halves[e].z};
-            const bool beyond = (f & 1) ? (c[ax] + h[ax] > plate_half[ax] + (double)EXT_TOL) : (c[ax] - h[ax] < -plate_half[ax] - (double)EXT_TOL);
-            if (beyond) D.ext_beyond[f] |= 1u << e;
-        }
-    }
     s->bin_names.resize(D.n_bins);
     for (int b = 0; b < D.n_bins; ++b) s->bin_names[b] = bin_name(d, b);
     return LSCPM_OK;
@@ -1254,7 +1236,6 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
     if (const char* f = getenv("LSCPM_PLATE_FLIGHTS")) s->flight = s->dev.n_ext == 0 && f[0] == '1';
 #ifdef LSCPM_DIAG
     s->dev.diag_emit = getenv("LSCPM_DIAG_EMIT") ? atoi(getenv("LSCPM_DIAG_EMIT")) : 0;
-    s->dev.diag_no_sibling = getenv("LSCPM_DIAG_NO_SIBLING") ? atoi(getenv("LSCPM_DIAG_NO_SIBLING")) : 0;
 #endif
     s->trace_smem = (size_t)(TRACE_THREADS / 32) * (size_t)(s->dev.n_bins + LSCPM_N_COUNTERS) * sizeof(unsigned int);
     if (s->trace_smem > 200 * 1024) return bail(fail(LSCPM_EUNSUPPORTED, "too many tally bins for the per-warp shared rows"));
@@ -1567,14 +1548,18 @@ int lscpm_probe(LscpmScene* s, int64_t n, const double* pos, const double* dir, 
             if (o.found == 2) { c_node = h_node; a_node = 0; }      // already inside that box (zero-distance entry dropped)
             else { c_node = 0; a_node = h_node; }
         }
-        else if (o.kind == SURF_BOX) { h_node = c_node = s->node_plate; a_node = o.ext < 0 ? s->node_ext[-o.ext - 1] : 0; }
-        else if (o.kind == SURF_CAP) { h_node = c_node = s->node_plate; a_node = o.ext < 0 ? s->node_ext[-o.ext - 1] : s->node_outer[q.kc]; }
+        else if (o.kind == SURF_BOX) { h_node = c_node = s->node_plate; a_node = 0; }   // beyond the plate: the world
+        else if (o.kind == SURF_CAP) {
+            // the cap coincides with the plate's face, which sorts first: hit = plate, entered from the tube / the mixture
+            h_node = a_node = s->node_plate;
+            c_node = q.medium == MED_OUTER ? s->node_outer[q.kc] : s->node_inner[q.kc];
+        }
         else if (o.kind == SURF_OUTER) {
             if (q.medium == MED_PLATE) { h_node = a_node = s->node_outer[o.ch]; c_node = s->node_plate; }
-            else { h_node = c_node = s->node_outer[q.kc]; a_node = o.adj == MED_OUTER ? s->node_outer[o.ch] : s->node_plate; }
+            else { h_node = c_node = s->node_outer[q.kc]; a_node = s->node_plate; }
         } else {
-            if (q.medium == MED_OUTER) { h_node = a_node = s->node_inner[q.kc]; c_node = o.container == MED_PLATE ? s->node_plate : s->node_outer[q.kc]; }
-            else { h_node = c_node = s->node_inner[q.kc]; a_node = o.adj == MED_PLATE ? s->node_plate : s->node_outer[q.kc]; }
+            if (q.medium == MED_OUTER) { h_node = a_node = s->node_inner[q.kc]; c_node = s->node_outer[q.kc]; }
+            else { h_node = c_node = s->node_inner[q.kc]; a_node = s->node_outer[q.kc]; }
         }
         hit[i] = h_node; container[i] = c_node; adjacent[i] = a_node;
         face[i] = (o.kind == SURF_BOX || o.kind == SURF_CAP) ? o.face : 0;

@@ -13,13 +13,13 @@
 //   OUTER -> in the tube wall of capillary k: inner cylinder, outer cylinder, or the +-y caps
 //   INNER -> in the reaction mixture of capillary k: inner cylinder or the +-y caps
 //
-// including the literal consequences of pvtrace's adjacency rule (DESIGN.md "literal quirks"):
-//   * leaving a tube wall with a sibling capillary ahead takes n2 from the sibling (adjacent = intersections[1]);
-//   * leaving the inner cylinder when the straight continuation reaches a cap first takes n2 from the plate;
-//   * the capillary caps coincide with the plate's +-y faces; ties resolve in scene-graph order, plate first.  A photon
-//     in a tube wall whose straight line leaves the tube through the cap therefore has the PLATE as container (the
-//     nearest node hit exactly once): plate material for absorption and n1 = plate, whether the segment ends on the
-//     cap (n2 = tube) or on the inner cylinder first (n2 = mixture); likewise a mixture segment that ends on the cap.
+// with pvtrace's bookkeeping for every interface (DESIGN.md "container and adjacent"): container = the deepest scene-graph
+// node the ray leaves exactly once; adjacent = the hit node when the photon enters it, and the container of what lies
+// beyond (the same rule applied to the remaining intersections) when it leaves its own container - i.e. always the
+// enclosing node: plate for a tube wall, tube wall for the mixture, air for the plate, whatever else lies ahead.
+// The capillary caps coincide with the plate's +-y faces; ties resolve in scene-graph order, plate first, so a photon
+// in a tube wall or in the mixture that reaches a cap hits the PLATE's face from its own container (n1 = tube or
+// mixture, n2 = plate) and, once transmitted, has nothing but the world sphere ahead: it leaves through that face.
 //
 // Divergence control (what the ncu profile of the first version asked for):
 //   * ONE code path computes every candidate distance (three slabs, near/far roots of both cylinders about
@@ -31,7 +31,7 @@
 //   * photon generation and luminophore re-emission share ONE "source" block at the end of the iteration (new
 //     direction + wavelength by inverse CDF + attenuation refresh), and a fresh photon's entry Fresnel test runs
 //     in the common step of the next iteration;
-//   * rare paths (sky-diffuse rejection loop, generic plate entry, sibling search, irregular tables) are out of line
+//   * rare paths (sky-diffuse rejection loop, generic plate entry, irregular tables) are out of line
 //     and exchange scalars only, so the photon state never leaves registers.
 #pragma once
 #include <cuda_runtime.h>
@@ -120,7 +120,6 @@ struct DevScene {
     DevMedium med[5];          // indexed by MED_*; med[MED_AIR] and med[MED_OUT] carry the world's refractive index only
     int n_ext;                 // outside boxes (0 for the standard scene: none of the MED_OUT code runs then)
     DevExtBox ext[MAX_EXT];
-    unsigned ext_beyond[6];    // per plate face: bit i set when outside box i reaches beyond that face's plane
     DevTable tab[MAX_TABLES];
     const float* tab_x;        // concatenated knot tables (scene spectra)
     const float* tab_y;
@@ -135,7 +134,6 @@ struct DevScene {
     float w2l[9];              // rotation world -> plate-local (row-major)
 #ifdef LSCPM_DIAG              // diagnostic build only (scripts/dye_bias.py): alternatives to the restated pvtrace rules
     int diag_emit;             // 0 kT window (the rule), 1 redshift (no thermal allowance), 2 full emission spectrum, 3 window of 3 kT
-    int diag_no_sibling;       // leaving a tube wall always sees the plate as adjacent
 #endif
 };
 
@@ -172,10 +170,9 @@ struct Hit {
     float t;
     int kind;                  // SURF_*
     int face;                  // box face for SURF_BOX / SURF_CAP; direction (+1/-1) for SURF_CELL
-    int ch;                    // sibling capillary (probe only)
+    int ch;                    // capillary of the event
     int container;             // medium whose material governs the segment
     int adj;                   // medium on the far side of the interface (pvtrace's `adjacent`)
-    bool maybe_sibling;        // tube-wall exit whose continuation could reach a neighbouring capillary
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -388,24 +385,21 @@ __device__ __forceinline__ Hit compute_hit(const DevScene& S, const Photon& p) {
         }
         if (o_near < t_pl) { t_pl = o_near; k_pl = SURF_OUTER; f_pl = 0; adj_pl = MED_OUTER; }
     }
-    // OUTER: inner cylinder, else cap (coincides with the plate face: plate sorts first and becomes container and
-    // hit node), else the tube's own outer surface (adjacent provisional: sibling search may upgrade it)
-    // Container: whenever the straight line leaves the tube through its CAP (ty <= o_far) the tube's only remaining
-    // intersection ties with the plate face, the plate sorts first and is the nearest node hit exactly once — also
-    // when the inner cylinder is hit before the cap (then n1 is the plate's index at the inner surface).
+    // OUTER: inner cylinder, else cap (coincides with the plate face, which sorts first and is the hit node: adjacent =
+    // plate), else the tube's own outer surface (adjacent = container of what lies beyond = plate).  The container is
+    // the tube throughout: it is the deepest node the ray leaves exactly once.
     const bool ou_inner = i_near < o_far && i_near < ty;
-    const bool ou_exit_cap = ty <= o_far;
-    const bool ou_cap = !ou_inner && ou_exit_cap;
+    const bool ou_cap = !ou_inner && ty <= o_far;
     const float t_ou = ou_inner ? i_near : (ou_cap ? ty : o_far);
     const int k_ou = ou_inner ? SURF_INNER : (ou_cap ? SURF_CAP : SURF_OUTER);
-    const int c_ou = ou_exit_cap ? MED_PLATE : MED_OUTER;
-    const int adj_ou = ou_inner ? MED_INNER : (ou_cap ? MED_OUTER : MED_PLATE);
-    // INNER: cap, else the inner surface with adjacent = second intersection (tube wall, unless the cap comes first)
+    const int c_ou = MED_OUTER;
+    const int adj_ou = ou_inner ? MED_INNER : MED_PLATE;
+    // INNER: cap (the plate's face again), else the inner surface with the tube wall beyond
     const bool in_cap = ty <= i_far;
     const float t_in = in_cap ? ty : i_far;
     const int k_in = in_cap ? SURF_CAP : SURF_INNER;
-    const int c_in = in_cap ? MED_PLATE : MED_INNER;
-    const int adj_in = in_cap ? MED_OUTER : ((ty <= o_far) ? MED_PLATE : MED_OUTER);
+    const int c_in = MED_INNER;
+    const int adj_in = in_cap ? MED_PLATE : MED_OUTER;
 
     const bool is_pl = PLATE_TOO && p.medium == MED_PLATE, is_ou = p.medium == MED_OUTER;
     h.t = fmaxf(is_pl ? t_pl : (is_ou ? t_ou : t_in), 0.f);
@@ -413,40 +407,7 @@ __device__ __forceinline__ Hit compute_hit(const DevScene& S, const Photon& p) {
     h.face = is_pl ? f_pl : ((h.kind == SURF_CAP) ? yface : 0);
     h.container = is_pl ? MED_PLATE : (is_ou ? c_ou : c_in);
     h.adj = is_pl ? adj_pl : (is_ou ? adj_ou : adj_in);
-    // a tube-wall exit may have a sibling capillary ahead only if the straight continuation travels far enough in x
-    // before it leaves the plate through a y or z face (x faces can only come earlier)
-    h.maybe_sibling = is_ou && h.kind == SURF_OUTER &&
-                      fabsf(p.dx) * (fminf(ty, tz) - o_far) > (S.pitch - S.r_o - fabsf(fmaf(p.dx, o_far, p.xr)));
     return h;
-}
-
-// pvtrace's adjacent for a photon leaving tube wall kc through its side at (xr, y, z): does the straight
-// continuation enter a sibling capillary before it leaves the plate?  Rare (tube-wall exits), so a plain loop.
-__device__ __noinline__ int sibling_ahead(const DevScene& S, int kc, float xr, float y, float z, float dx, float dy, float dz) {
-    const float a = fmaf(dx, dx, dz * dz);
-    if (!(a > 1e-30f) || dx == 0.f) return -1;
-    const float ty = dy > 0.f ? fdiv(S.hy - y, dy) : (dy < 0.f ? fdiv(-S.hy - y, dy) : LSCPM_INF);
-    const float tz = dz > 0.f ? fdiv(S.hz - S.zc - z, dz) : (dz < 0.f ? fdiv(-S.hz - S.zc - z, dz) : LSCPM_INF);
-    const float x_abs = axis_x(S, kc) + xr;
-    const float tx = dx > 0.f ? fdiv(S.hx - x_abs, dx) : fdiv(-S.hx - x_abs, dx);
-    const float t_box = fminf(fminf(ty, tz), tx);
-    const int step = dx > 0.f ? 1 : -1;
-    const float ar2 = a * S.r_o2;
-    for (int j = kc + step; j >= 0 && j < S.n_ch; j += step) {
-        const float ox = xr - (float)(j - kc) * S.pitch;
-        // capillary j starts at |ox| - r_o along x: beyond the plate exit -> no sibling
-        if ((fabsf(ox) - S.r_o) > fabsf(dx) * t_box) return -1;
-        const float b = fmaf(ox, dx, z * dz);
-        if (b >= 0.f) continue;
-        const float cross = fmaf(ox, dz, -z * dx);
-        const float disc = fmaf(-cross, cross, ar2);
-        if (disc <= 0.f) continue;
-        const float c = fmaf(ox, ox, z * z) - S.r_o2;
-        const float t = fdiv(c, fsqrt(disc) - b);
-        if (t >= t_box) return -1;
-        if (t > 0.f) return j;
-    }
-    return -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -708,28 +669,6 @@ __device__ __forceinline__ float normal_gap(float t, int f, float dx, float dy, 
     return t * fabsf(f < 2 ? dx : (f < 4 ? dy : dz));
 }
 
-// first outside box met by the straight line from (ox,oy,oz) along d, a box starting at distance ~0 included
-// (pvtrace's `adjacent = intersections[1]` for a photon leaving the plate: ties sort the plate first).  `face` is the
-// plate face the photon is on: only boxes reaching beyond that face's plane can lie ahead (S.ext_beyond[face]; for the
-// photovoltaic variants none beyond the top face, one beyond each of the others).
-__device__ __noinline__ int ext_ahead(const DevScene& S, int face, float ox, float oy, float oz, float dx, float dy, float dz) {
-    int best = -1; float tbest = LSCPM_INF;
-    unsigned todo = S.ext_beyond[face];
-    if (!todo) return best;
-    const RayInv inv = ray_inverse(dx, dy, dz);
-    while (todo) {
-        const int i = __ffs(todo) - 1;
-        todo &= todo - 1u;
-        const DevExtBox& b = S.ext[i];
-        float tmin, tmax; int f, fx;
-        slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, ox, oy, oz, dx, dy, dz, inv, tmin, tmax, f, fx);
-        if (tmin <= tmax && tmax > 0.f && normal_gap(tmin, f, dx, dy, dz) > -EXT_TOL && tmin < tbest) {
-            tbest = tmin; best = i;
-        }
-    }
-    return best;
-}
-
 // Nearest surface for a ray in the air around the plate: node 0 = plate, i+1 = outside box i, -1 = none.
 // `skip` is the convex body the photon has just left or bounced off (0 plate, i+1 box i, -1 none): it cannot be met
 // again before another interaction, so it is excluded by logic rather than by a distance tolerance (a tolerance on the
@@ -851,16 +790,15 @@ struct StepOut {
 // class order = deal order: FLAT and CYL share the Fresnel code, CELL has no work of its own, ABSORB and FRESH share the source code
 constexpr int CLS_FLAT = 0, CLS_CYL = 1, CLS_CELL = 2, CLS_ABSORB = 3, CLS_FRESH = 4, CLS_OUT = 5, CLS_IDLE = 6, N_CLS = 7;
 
-// pending-interaction word: class | surface kind | face + 1 | container | adjacent | sibling flag
-__device__ __forceinline__ unsigned pack_pending(int cls, int kind, int face, int container, int adj, bool sibling) {
+// pending-interaction word: class | surface kind | face + 1 | container | adjacent
+__device__ __forceinline__ unsigned pack_pending(int cls, int kind, int face, int container, int adj) {
     return (unsigned)cls | ((unsigned)kind << 4) | ((unsigned)(face + 1) << 7) | ((unsigned)container << 11) |
-           ((unsigned)adj << 14) | ((sibling ? 1u : 0u) << 17);
+           ((unsigned)adj << 14);
 }
 __device__ __forceinline__ int pending_kind(unsigned w) { return (w >> 4) & 7; }
 __device__ __forceinline__ int pending_face(unsigned w) { return (int)((w >> 7) & 15) - 1; }
 __device__ __forceinline__ int pending_container(unsigned w) { return (w >> 11) & 7; }
 __device__ __forceinline__ int pending_adj(unsigned w) { return (w >> 14) & 7; }
-__device__ __forceinline__ bool pending_sibling(unsigned w) { return (w >> 17) & 1; }
 
 // ------------------------------------------------------------------------------------------------
 // Plate flight (standard scene, photon in the PMMA): straight to the next REAL event.
@@ -1004,7 +942,7 @@ __device__ __forceinline__ void plate_flight(const DevScene& S, Photon& p, const
     if (m & 1) { z = __fsub_rn(image ? 0.f : delta, z); dz_out = -dz; }
     p.z = __fmul_rn(sgn, z); p.dz = __fmul_rn(sgn, dz_out);
     bounces = m;                                        // the mirrored photon only ever moves up: m >= 0
-    h.t = t; h.ch = p.kc; h.container = MED_PLATE; h.maybe_sibling = false;
+    h.t = t; h.ch = p.kc; h.container = MED_PLATE;
     h.kind = image ? SURF_OUTER : (crossing ? SURF_CELL : SURF_BOX);
     h.face = image ? 0 : (crossing ? step : face);
     h.adj = image ? MED_OUTER : (crossing ? MED_PLATE : MED_AIR);
@@ -1031,11 +969,11 @@ __device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const u
         return p.steps > MAXSTEPS ? BIN_KILL : -1;
     }
     if (BRANCH_ENTRY) {
-        if (p.medium == MED_AIR) { h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false; }
+        if (p.medium == MED_AIR) { h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; }
         else h = compute_hit<!FLIGHT>(S, p);
     } else {
         h = compute_hit<!FLIGHT>(S, p);
-        if (p.medium == MED_AIR) { h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; h.maybe_sibling = false; }
+        if (p.medium == MED_AIR) { h.t = 0.f; h.kind = SURF_BOX; h.face = p.aux & 7; h.container = MED_AIR; h.adj = MED_PLATE; }
     }
     // a virtual crossing is not a follow() iteration
     p.steps += h.kind != SURF_CELL ? 1 : 0;
@@ -1068,7 +1006,7 @@ __device__ __forceinline__ int advance(const DevScene& S, Photon& p, const uint3
     Hit h; int cls, extra;
     const int killed = advance_hit<true, FLIGHT, true>(S, p, w_x, h, cls, extra);
     n_events += (unsigned)extra;
-    pend = pack_pending(cls, h.kind, h.face, h.container, h.adj, h.maybe_sibling);
+    pend = pack_pending(cls, h.kind, h.face, h.container, h.adj);
     return killed;
 }
 
@@ -1096,7 +1034,7 @@ __device__ __forceinline__ int interact_absorb(const DevScene& S, Photon& p, int
 
 // Fresnel test at the interface the photon has been moved to; returns the tally bin or -1
 template <bool EXT>
-__device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, int kind, int face, int container, int adj, bool maybe_sibling,
+__device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, int kind, int face, int container, int adj,
                                                 float u_surf, int& event) {
     const bool flat = kind == SURF_BOX || kind == SURF_CAP;
     float nx, ny, nz;
@@ -1110,18 +1048,11 @@ __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, in
     } else {
         const float inv = frsqrt(fmaf(p.xr, p.xr, p.z * p.z));
         nx = p.xr * inv; ny = 0.f; nz = p.z * inv;
-        // leaving the tube wall: pvtrace's adjacent is whatever the straight continuation meets next
-#ifdef LSCPM_DIAG
-        if (S.diag_no_sibling) maybe_sibling = false;
-#endif
-        if (maybe_sibling && sibling_ahead(S, p.kc, p.xr, p.y, p.z, p.dx, p.dy, p.dz) >= 0) adj = MED_OUTER;
     }
-    float n2 = S.med[adj].n;
+    // leaving the plate the photon meets the world's medium even when an outside box lies straight ahead or shares the
+    // face: adjacent is the container of what lies beyond the face, and a box that is entered and left again is not one
+    const float n2 = S.med[adj].n;
     const bool leaving = flat && p.medium != MED_AIR;
-    if (EXT && leaving) {
-        const int e = ext_ahead(S, face, abs_x(S, p), p.y, p.z + S.zc, p.dx, p.dy, p.dz);
-        if (e >= 0) n2 = S.ext[e].n;
-    }
     const float n1 = S.med[container].n;
     const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, n1, n2);
     const bool reflected = u_surf < I.R;
@@ -1174,7 +1105,7 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
         return bin < 0 ? STEP_EMIT : bin;
     }
     if (cls == CLS_CELL) { out.event = EV_NONE; return -1; }
-    return interact_surface<EXT>(S, p, h.kind, h.face, h.container, h.adj, h.maybe_sibling, u01(w.y), out.event);
+    return interact_surface<EXT>(S, p, h.kind, h.face, h.container, h.adj, u01(w.y), out.event);
 }
 
 }  // namespace lscpm

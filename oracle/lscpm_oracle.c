@@ -7,7 +7,8 @@
  * /root/reference and not installable offline); tallies are pinned statistically on the full-year results the
  * reference committed (tests/test_solar_stage.py).  This file is the fast twin of
  * oracle/pvtrace_oracle.py — the same generic algorithm (every geometry node intersected in its own
- * local frame, stable distance sort, container = nearest node hit exactly once, Beer-Lambert free
+ * local frame, stable distance sort, container = deepest node hit exactly once, adjacent = the hit node or, when the
+ * photon leaves its container, the container of what lies beyond (pinned on reference output), Beer-Lambert free
  * path, Fresnel reflect/refract, kT-restricted re-emission), working on the flattened description of
  * include/lscpm.h instead of the scene graph.  tests/test_oracle_golden.py checks the two against
  * each other ray by ray; the Python twin is checked against the reference's own test bands and the
@@ -62,6 +63,7 @@ static double rng_uniform(Rng* r) { return (double)(rng_next(r) >> 11) * (1.0 / 
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
     int geom, material;
+    int depth;             /* depth in the scene graph (root = 0), pvtrace Node.depth */
     double size[3];
     double R[9], T[3];     /* local -> world rotation and translation */
 } ONode;
@@ -111,6 +113,8 @@ static int oscene_init(OScene* s, const LscpmSceneDesc* d) {
         const double* p = d->node_pose + 16 * i;
         n->geom = d->node_geom[i];
         n->material = d->node_material[i];
+        n->depth = 0;
+        for (int a = d->node_parent[i]; a >= 0; a = d->node_parent[a]) n->depth++;
         for (int k = 0; k < 3; ++k) n->size[k] = d->node_size[3 * i + k];
         for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) n->R[3 * r + c] = p[4 * r + c]; n->T[r] = p[4 * r + 3]; }
     }
@@ -241,6 +245,18 @@ static int scene_intersections(const OScene* s, const double* p, const double* v
 
 typedef struct { int hit, container, adjacent, face; double distance; } NextHit;
 
+/* pvtrace find_container: of the nodes that appear exactly once in hits[0..n) (the ray is inside them) the deepest in the
+ * scene graph; sorted(pairs, key=depth)[-1], i.e. the later entry wins among equal depths. */
+static int find_container(const OScene* s, const Hit* hits, int n, int* counts) {
+    if (n == 1) return hits[0].node;
+    memset(counts, 0, sizeof(int) * (size_t)s->n_nodes);
+    for (int i = 0; i < n; ++i) counts[hits[i].node]++;
+    int best = -1;
+    for (int i = 0; i < n; ++i)
+        if (counts[hits[i].node] == 1 && (best < 0 || s->nodes[hits[i].node].depth >= s->nodes[best].depth)) best = hits[i].node;
+    return best;
+}
+
 /* literal next_hit; returns 0 when the ray leaves the scene */
 static int next_hit(const OScene* s, const double* p, const double* v, Hit* scratch, int* counts, NextHit* nh) {
     int n_all = scene_intersections(s, p, v, scratch), n = 0;
@@ -248,12 +264,11 @@ static int next_hit(const OScene* s, const double* p, const double* v, Hit* scra
     if (n == 0) return 0;
     nh->hit = scratch[0].node; nh->face = scratch[0].face; nh->distance = scratch[0].t;
     if (n == 1) { nh->container = nh->hit; nh->adjacent = -1; return 1; }
-    memset(counts, 0, sizeof(int) * (size_t)s->n_nodes);
-    for (int i = 0; i < n; ++i) counts[scratch[i].node]++;
-    nh->container = -1;
-    for (int i = 0; i < n; ++i) if (counts[scratch[i].node] == 1) { nh->container = scratch[i].node; break; }
+    nh->container = find_container(s, scratch, n, counts);
     if (nh->container < 0) nh->container = nh->hit;   /* cannot happen inside the world sphere */
-    nh->adjacent = nh->container == nh->hit ? scratch[1].node : nh->hit;
+    /* leaving the container: adjacent = container of what lies beyond the surface (the rule applied to the rest) */
+    nh->adjacent = nh->container == nh->hit ? find_container(s, scratch + 1, n - 1, counts) : nh->hit;
+    if (nh->adjacent < 0) nh->adjacent = 0;
     return 1;
 }
 

@@ -28,8 +28,14 @@ Algorithm restated (pvtrace 2.1, ``pvtrace/algorithm/photon_tracer.py`` and frie
 ``next_hit``     all intersections of the ray with every geometry node, each computed in the node's
                  local frame, expressed in the root frame and sorted by distance (stable sort, i.e.
                  exact ties keep scene-graph traversal order); intersections at distance ~0 are
-                 dropped; ``container`` = nearest node hit exactly once; ``hit`` = first intersection's
-                 node; ``adjacent`` = second intersection's node if ``container is hit`` else ``hit``.
+                 dropped; ``container`` = ``find_container(intersections)``: of the nodes hit exactly once (the
+                 ray is inside them) the deepest in the scene graph; ``hit`` = first intersection's node;
+                 ``adjacent`` = ``find_container(intersections[1:])`` if ``container is hit`` (what encloses the
+                 point just beyond the surface) else ``hit``.  The adjacency rule is pinned on reference output:
+                 with ``adjacent = intersections[1].hit`` (a photon leaving a tube wall then sees a sibling
+                 capillary's index when one lies straight ahead) the dye scenes react 0.39 % too much against the
+                 reference's committed tilt sweeps (z = -6.5 over 1.1e7 reference photons), with this rule the
+                 ratio is 0.9995 (z = +0.8) - DESIGN.md section 5.
 ``follow``       loop (<= ``maxsteps``): ``next_hit``; none -> EXIT; hit is the root -> EXIT; sample a free
                  path ``-ln(1-U)/alpha(lambda)`` in the container's material; if shorter than the distance to
                  the surface: absorb there, pick the component ~ alpha_i, radiative (``U < QY``) -> re-emit
@@ -213,6 +219,7 @@ class _ONode:
     refractive_index: float
     components: list
     source: object = None
+    depth: int = 0  # depth of the node in the scene graph (anytree ``Node.depth``: root = 0)
 
 
 @dataclass
@@ -245,11 +252,11 @@ class OracleScene:
     def __init__(self, scene):
         self.scene = scene
         self.nodes: list[_ONode] = []
-        self._walk(scene.root, np.identity(4))
+        self._walk(scene.root, np.identity(4), 0)
         if not self.nodes or self.nodes[0].source is not scene.root:
             raise ValueError("scene root must carry the world geometry")
 
-    def _walk(self, node, parent_world):
+    def _walk(self, node, parent_world, depth):
         pose = np.asarray(getattr(node, "pose", np.identity(4)), dtype=float)
         world = parent_world @ pose
         geometry = getattr(node, "geometry", None)
@@ -269,11 +276,11 @@ class OracleScene:
                     index=len(self.nodes), name=str(node.name), kind=kind, params=params,
                     to_world=world, to_local=np.linalg.inv(world),
                     refractive_index=float(material.refractive_index),
-                    components=list(material.components), source=node,
+                    components=list(material.components), source=node, depth=depth,
                 )
             )
         for child in node.children:
-            self._walk(child, world)
+            self._walk(child, world, depth + 1)
 
     # -- intersections -------------------------------------------------------------
     def intersections(self, position, direction):
@@ -314,11 +321,24 @@ class OracleScene:
         first = inter[0]
         if len(inter) == 1:
             return first[1], first[1], None, first[3], first[0], first[2]
-        counts = Counter(x[1] for x in inter)
-        container = next(x[1] for x in inter if counts[x[1]] == 1)
+        container = self.find_container(inter)
         hit = first[1]
-        adjacent = inter[1][1] if container == hit else hit
+        adjacent = self.find_container(inter[1:]) if container == hit else hit
         return hit, container, adjacent, first[3], first[0], first[2]
+
+    def find_container(self, inter):
+        """pvtrace ``find_container``: of the nodes that appear exactly once in the list (the ray is inside them) the one
+        deepest in the scene graph (``sorted(pairs, key=depth)[-1]``: the later entry wins among equal depths)."""
+        if len(inter) == 1:
+            return inter[0][1]
+        counts = Counter(x[1] for x in inter)
+        best = None
+        for x in inter:
+            if counts[x[1]] == 1 and (best is None or self.nodes[x[1]].depth >= self.nodes[best].depth):
+                best = x[1]
+        if best is None:
+            raise RuntimeError("no container: the ray is outside every node (pvtrace raises here as well)")
+        return best
 
     # -- materials -----------------------------------------------------------------
     def coefficients(self, node_index, wavelength):

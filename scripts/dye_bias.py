@@ -10,8 +10,9 @@ FILES = ["Eindhoven_0deg", "Eindhoven_20deg", "Eindhoven_40deg", "Eindhoven_60de
          "North Cape_40deg", "North Cape_55deg", "North Cape_70deg"]
 CACHE = "/tmp/dye_bias_inputs.pkl"
 VARIANTS = [("base", {}), ("redshift", {"LSCPM_DIAG_EMIT": "1"}), ("full", {"LSCPM_DIAG_EMIT": "2"}), ("3kT", {"LSCPM_DIAG_EMIT": "3"}),
-            ("no_sibling", {"LSCPM_DIAG_NO_SIBLING": "1"}), ("qy0.94", {"DIAG_QY": "0.94"}), ("ems_trapz", {"DIAG_EMS_TRAPZ": "1"}),
-            ("pmma_bg0.3", {"DIAG_BG": "0.3"})]
+            ("qy0.94", {"DIAG_QY": "0.94"}), ("ems_trapz", {"DIAG_EMS_TRAPZ": "1"}), ("pmma_bg0.3", {"DIAG_BG": "0.3"})]
+if os.path.exists(os.path.join(ROOT, "variants", "diag_old.so")):   # the library before the adjacency rule was corrected
+    VARIANTS += [("old_rules", {"DIAG_LIB": "diag_old.so"}), ("old_no_sibling", {"DIAG_LIB": "diag_old.so", "LSCPM_DIAG_NO_SIBLING": "1"})]
 
 if "--child" in sys.argv:
     import numpy as np, pandas as pd
@@ -59,6 +60,7 @@ for key in FILES:
                    frame_epoch(data))
 pickle.dump(inputs, open(CACHE, "wb"))
 for name, env in VARIANTS:
-    e = dict(os.environ, LSCPM_LIBRARY=os.path.join(ROOT, "variants", "diag.so"), **env)
+    e = dict(os.environ, **env)
+    e["LSCPM_LIBRARY"] = os.path.join(ROOT, "variants", e.pop("DIAG_LIB", "diag.so"))
     r = subprocess.run([sys.executable, __file__, "--child", str(N)], env=e, capture_output=True, text=True)
     print(f"{name:12s} {r.stdout.strip() or r.stderr.strip()[-600:]}", flush=True)

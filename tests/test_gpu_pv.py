@@ -65,7 +65,9 @@ def test_pv_probe_matches_oracle(native, built_library):
     in_air_to_pv = clear & same & np.isin(ref["hit"], [i for i, name in enumerate(arrays.node_name) if "PV" in name])
     assert in_air_to_pv.sum() > 20
     lending = clear & same & (ref["hit"] == 1) & np.isin(ref["adjacent"], [i for i, name in enumerate(arrays.node_name) if "PV" in name])
-    assert lending.sum() > 20                                  # plate faces whose adjacent is a PV box across the gap
+    assert lending.sum() == 0      # a photon leaving the plate meets the world's medium, whatever box lies beyond the face
+    leaving = clear & same & (ref["hit"] == 1) & (ref["container"] == 1)
+    assert leaving.sum() > 100 and np.all(ref["adjacent"][leaving] == 0)
     ok = clear & same & (ref["hit"] > 0)
     rel = np.abs(gpu["distance"][ok] - ref["distance"][ok]) / ref["distance"][ok]
     assert np.quantile(rel, 0.99) < 1e-5
@@ -81,7 +83,8 @@ def test_runner_returns_the_reference_tuple(built_library):
                                 num_photons=20_000, seed=1)
     assert isinstance(res, tuple) and len(res) == 5
     fraction, scene, photon_path, bottom, side = res
-    assert 0.08 < fraction < 0.18 and 0.35 * 20_000 < bottom < 0.46 * 20_000 and 0.05 * 20_000 < side < 0.11 * 20_000
+    # C oracle at 4e5 photons: reacted 0.306, bottom PV 0.169, side PVs 0.099 (total internal reflection survives over the PVs)
+    assert 0.28 < fraction < 0.33 and 0.15 * 20_000 < bottom < 0.19 * 20_000 and 0.08 * 20_000 < side < 0.12 * 20_000
     assert hasattr(scene, "light_nodes") and photon_path == []
     plain = run_direct_simulation(tilt_angle=40, solar_elevation=50, solar_azimuth=180, num_photons=2000, seed=1)
     assert isinstance(plain, float)

@@ -124,3 +124,42 @@ def test_philox_known_answers(built_library):
     assert philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_container_and_adjacent_bookkeeping():
+    """pvtrace ``next_hit`` / ``find_container``: container = deepest node hit exactly once; adjacent = the hit node, or
+    - when the photon leaves its container - the container of what lies beyond the surface.  The adjacency rule is pinned
+    on the reference's committed results; these are its consequences in the scenes of the path."""
+    scene = po.OracleScene(standard_scene(tilt=0, elevation=90, wavelength=585.0))
+    names = [n.name for n in scene.nodes]
+    plate, world = "LSC-PM Reactor 47x47 cm^2", "World (air)"
+    x4, zc, r_o, r_i = -0.105, -0.004, 0.0015875, 0.00079375
+
+    def hit(p, d):
+        d = np.asarray(d, dtype=float)
+        h, c, a = scene.next_hit(np.asarray(p, dtype=float), d / np.linalg.norm(d))[:3]
+        return names[h], names[c], None if a is None else names[a]
+
+    # in the tube wall of capillary 4, leaving sideways with capillary 5 straight ahead (30 mm on, same height): the
+    # adjacent node is the plate, not the sibling
+    assert hit([x4 + 0.5 * (r_o + r_i), 0.0, zc], [1.0, 0.0, 0.0]) == ("Capillary_PFA_4", "Capillary_PFA_4", plate)
+    # in the tube wall heading for the mixture, and in the mixture heading out
+    assert hit([x4 + 0.5 * (r_o + r_i), 0.0, zc], [-1.0, 0.0, 0.0]) == ("Reaction_mixture_4", "Capillary_PFA_4", "Reaction_mixture_4")
+    assert hit([x4, 0.0, zc], [1.0, 0.0, 0.2]) == ("Reaction_mixture_4", "Reaction_mixture_4", "Capillary_PFA_4")
+    # in the plate: capillary ahead / top face ahead
+    assert hit([x4 + 0.01, 0.0, zc], [-1.0, 0.0, 0.0]) == ("Capillary_PFA_4", plate, "Capillary_PFA_4")
+    assert hit([x4 + 0.01, 0.0, zc], [0.0, 0.0, 1.0]) == (plate, plate, world)
+    # along the tube wall to its end cap, which coincides with the plate's +y face: the plate's face sorts first and is
+    # the hit node, the container stays the tube (deepest node left exactly once)
+    assert hit([x4 + 0.5 * (r_o + r_i), 0.2, zc], [0.0, 1.0, 0.0]) == (plate, "Capillary_PFA_4", plate)
+    assert hit([x4, 0.2, zc], [0.0, 1.0, 0.0]) == (plate, "Reaction_mixture_4", plate)
+
+    # photovoltaic box under the plate (air gap) and side boxes sharing the plate's edge faces: a photon leaving the plate
+    # meets air, whatever lies beyond
+    pv = po.OracleScene(standard_scene(tilt=0, elevation=90, wavelength=585.0, add_bottom_PV=True, add_side_PV=True))
+    names = [n.name for n in pv.nodes]
+    scene = pv
+    assert hit([x4 + 0.01, 0.0, zc], [0.0, 0.0, -1.0]) == (plate, plate, world)
+    assert hit([0.2, 0.0, zc], [1.0, 0.0, 0.1]) == (plate, plate, world)
+    # ... and in the air gap the box ahead is entered from the world
+    assert hit([0.0, 0.0, -0.0085], [0.0, 0.0, -1.0])[1:] == (world, "bottomPV")
