@@ -83,9 +83,9 @@ def test_yearly_counts_against_the_reference_results(site_name, tilt, dye, csv, 
     """The whole chain (solar position, SPECTRL2 restatement, scene, CUDA tracing) against the reference's own pvtrace
     output: the per-time-point counts of its committed full-year runs (120 photons per point, ~1e6 photons per file and
     light source; tests/golden/reference_yearly_counts.npz).  Our p_i come from 2e4 photons per point; the reference's
-    counts must be Binomial(120, p_i): z of the yearly totals and of three elevation bands within +-4.5, yearly means
-    within 0.8 % (measured over the ten files, scripts/anchors.py: no-dye z = -0.9...+1.3, dye z = -1.1...-1.9, i.e. ours
-    +0.3 % above pvtrace with dye, inside the north star's 99.9 % band at 1e6 photons)."""
+    counts must be Binomial(120, p_i): z of the yearly totals and of three elevation bands within +-4, yearly means
+    within 0.6 % (dye) / 1.2 % (no dye).  Measured over the ten files (scripts/anchors.py): |z| <= 1.8 except the
+    Eindhoven 45 degree file, which disagrees with the reference's own sweep for the same tilt; DESIGN.md section 5."""
     from helpers import binomial_z, frame_epoch, reference_counts
     from miniplant.full_simulation import yearlong_simulation
     from miniplant.locations import LOCATIONS
@@ -101,15 +101,15 @@ def test_yearly_counts_against_the_reference_results(site_name, tilt, dye, csv, 
     ref = reference_counts(gold, csv).rename(columns={"direct": "kd", "diffuse": "ks"})
     both = ours.join(ref, how="inner")
     assert len(both) >= len(ref) - 1 and abs(len(res) - len(ref)) <= 1
-    tol = 0.008 if dye else 0.012      # the reference's yearly means carry 0.2 % (dye) / 0.4 % (no dye) of Monte-Carlo noise
+    tol = 0.006 if dye else 0.012      # the reference's yearly means carry 0.2 % (dye) / 0.4 % (no dye) of Monte-Carlo noise
     assert abs(both.pd.mean() / (both.kd.mean() / 120) - 1) < tol
     assert abs(both.ps.mean() / (both.ks.mean() / 120) - 1) < tol
-    assert abs(binomial_z(both.kd.values, both.pd.values, 120)) < 4.5
-    assert abs(binomial_z(both.ks.values, both.ps.values, 120)) < 4.5
+    assert abs(binomial_z(both.kd.values, both.pd.values, 120)) < 4.0
+    assert abs(binomial_z(both.ks.values, both.ps.values, 120)) < 4.0
     for lo, hi in ((0, 15), (15, 35), (35, 91)):
         m = (both.el.values >= lo) & (both.el.values < hi)
         if m.sum() > 200:
-            assert abs(binomial_z(both.kd.values[m], both.pd.values[m], 120)) < 4.5, (lo, hi)
+            assert abs(binomial_z(both.kd.values[m], both.pd.values[m], 120)) < 4.0, (lo, hi)
 
 
 def test_tilt_sweep_counts_against_the_reference_results(built_library):
@@ -130,5 +130,5 @@ def test_tilt_sweep_counts_against_the_reference_results(built_library):
         p = trace_time_points(tilt, batch, 20000, include_dye=dye, seed=13)
         both = pd.DataFrame({"p": p}, index=frame_epoch(data)).join(reference_counts(gold, key), how="inner")
         assert len(both) >= len(gold[key + "|direct"]) - 2, key
-        assert abs(binomial_z(both.direct.values, both.p.values, 100)) < 4.5, key
-        assert abs(both.p.mean() / (both.direct.mean() / 100) - 1) < (0.01 if dye else 0.015), key
+        assert abs(binomial_z(both.direct.values, both.p.values, 100)) < 4.0, key
+        assert abs(both.p.mean() / (both.direct.mean() / 100) - 1) < (0.008 if dye else 0.015), key
