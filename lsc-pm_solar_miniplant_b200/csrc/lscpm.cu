@@ -531,12 +531,13 @@ __global__ void probe_kernel(const __grid_constant__ DevScene S, const ProbeIn* 
             // the flight moved the photon onto the interface: step back so that the common code below finds it at h.t
             p.xr = fmaf(-dx0, h.t, p.xr); p.y = fmaf(-dy0, h.t, p.y); p.z = fmaf(-dz0, h.t, p.z);
         } else {
-            h = compute_hit(S, p);
+            // coincident faces in scene-graph order (plate, tube, mixture), like the oracle's probe
+            h = compute_hit<true, false>(S, p);
             while (h.kind == SURF_CELL) {
                 travelled += h.t;
                 p.y = fmaf(p.dy, h.t, p.y); p.z = fmaf(p.dz, h.t, p.z);
                 p.kc += h.face; p.xr = h.face > 0 ? -0.5f * S.pitch : 0.5f * S.pitch;
-                h = compute_hit(S, p);
+                h = compute_hit<true, false>(S, p);
             }
         }
         const float xr = fmaf(p.dx, h.t, p.xr), yy = fmaf(p.dy, h.t, p.y), zz = fmaf(p.dz, h.t, p.z);
@@ -745,7 +746,8 @@ struct LscpmScene {
     // device allocations
     float *d_tab_x = nullptr, *d_tab_y = nullptr, *d_tab_cdf = nullptr;
     unsigned short *d_tab_fwd = nullptr, *d_tab_inv = nullptr;
-    int *d_abs_outer = nullptr, *d_abs_inner = nullptr;
+    int *d_abs_outer = nullptr, *d_abs_inner = nullptr, *d_exit_outer = nullptr, *d_exit_inner = nullptr;
+    int axis_sign = 0;              // +1: the capillaries' local +z axis points along the plate's +y
     unsigned long long* d_counters = nullptr;   // ring of work counters
     std::atomic<unsigned> next_counter{0};
     int n_sm = 0, blocks_per_sm = 0;
@@ -865,6 +867,9 @@ int lower_scene(const LscpmSceneDesc* d, LscpmScene* s) {
             return fail(LSCPM_EUNSUPPORTED, "capillaries must run along the plate's y axis");
         if (std::fabs(centre.y) > tol || std::fabs(d->node_size[3 * i] - 2 * s->hy) > tol)
             return fail(LSCPM_EUNSUPPORTED, "capillaries must span the plate exactly (end caps on the +-y faces)");
+        const int sign = axis.y > 0 ? 1 : -1;
+        if (s->axis_sign != 0 && s->axis_sign != sign) return fail(LSCPM_EUNSUPPORTED, "capillaries must share the orientation of their axis");
+        s->axis_sign = sign;
         Channel c{centre.x, centre.z, i, -1};
         for (int j = i + 1; j < d->n_nodes; ++j) {
             if (d->node_parent[j] != i) continue;
@@ -1210,19 +1215,26 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
         }
         if ((rc = add_table(ux, uy, &m.alpha_table))) return bail(rc);
     }
-    std::vector<int> abs_outer, abs_inner;
+    std::vector<int> abs_outer, abs_inner, exit_outer, exit_inner;
     for (int k = 0; k < s->n_ch; ++k) {
         abs_outer.push_back(s->layout.abs_base[s->node_outer[k]]);
         abs_inner.push_back(s->node_inner[k] >= 0 ? s->layout.abs_base[s->node_inner[k]] : 0);
+        exit_outer.push_back(s->layout.exit_base[s->node_outer[k]]);
+        exit_inner.push_back(s->node_inner[k] >= 0 ? s->layout.exit_base[s->node_inner[k]] : 0);
     }
+    // cylinder face slots: 0 side, 1 -cap (local -z), 2 +cap (local +z); which of them lies in the plate's +y face
+    s->dev.cap_slot_hi = s->axis_sign >= 0 ? 2 : 1;
+    s->dev.cap_slot_lo = s->axis_sign >= 0 ? 1 : 2;
     if ((rc = upload(tx, &s->d_tab_x)) || (rc = upload(ty, &s->d_tab_y)) || (rc = upload(tc, &s->d_tab_cdf)) ||
         (rc = upload(fwd, &s->d_tab_fwd)) || (rc = upload(inv, &s->d_tab_inv)) ||
-        (rc = upload(abs_outer, &s->d_abs_outer)) || (rc = upload(abs_inner, &s->d_abs_inner)))
+        (rc = upload(abs_outer, &s->d_abs_outer)) || (rc = upload(abs_inner, &s->d_abs_inner)) ||
+        (rc = upload(exit_outer, &s->d_exit_outer)) || (rc = upload(exit_inner, &s->d_exit_inner)))
         return bail(rc);
     if ((e = cudaMalloc((void**)&s->d_counters, sizeof(unsigned long long) * COUNTER_RING)) != cudaSuccess) return bail(cuda_fail(e, "cudaMalloc counters"));
     s->dev.tab_x = s->d_tab_x; s->dev.tab_y = s->d_tab_y; s->dev.tab_cdf = s->d_tab_cdf;
     s->dev.tab_fwd = s->d_tab_fwd; s->dev.tab_inv = s->d_tab_inv;
     s->dev.abs_base_outer = s->d_abs_outer; s->dev.abs_base_inner = s->d_abs_inner;
+    s->dev.exit_base_outer = s->d_exit_outer; s->dev.exit_base_inner = s->d_exit_inner;
     cudaDeviceProp prop;
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(cuda_fail(e, "cudaGetDeviceProperties"));
     s->n_sm = prop.multiProcessorCount;
@@ -1271,7 +1283,7 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
 int lscpm_scene_destroy(LscpmScene* s) {
     if (!s) return LSCPM_OK;
     cudaFree(s->d_tab_x); cudaFree(s->d_tab_y); cudaFree(s->d_tab_cdf); cudaFree(s->d_tab_fwd); cudaFree(s->d_tab_inv);
-    cudaFree(s->d_abs_outer); cudaFree(s->d_abs_inner); cudaFree(s->d_counters);
+    cudaFree(s->d_abs_outer); cudaFree(s->d_abs_inner); cudaFree(s->d_exit_outer); cudaFree(s->d_exit_inner); cudaFree(s->d_counters);
     delete s;
     return LSCPM_OK;
 }
@@ -1550,16 +1562,16 @@ int lscpm_probe(LscpmScene* s, int64_t n, const double* pos, const double* dir, 
         }
         else if (o.kind == SURF_BOX) { h_node = c_node = s->node_plate; a_node = 0; }   // beyond the plate: the world
         else if (o.kind == SURF_CAP) {
-            // the cap coincides with the plate's face, which sorts first: hit = plate, entered from the tube / the mixture
-            h_node = a_node = s->node_plate;
-            c_node = q.medium == MED_OUTER ? s->node_outer[q.kc] : s->node_inner[q.kc];
+            // the cap coincides with the plate's face; in scene-graph order the plate comes first (hit node and nearest
+            // node left once), the tube second
+            h_node = c_node = s->node_plate; a_node = s->node_outer[q.kc];
         }
         else if (o.kind == SURF_OUTER) {
             if (q.medium == MED_PLATE) { h_node = a_node = s->node_outer[o.ch]; c_node = s->node_plate; }
             else { h_node = c_node = s->node_outer[q.kc]; a_node = s->node_plate; }
         } else {
-            if (q.medium == MED_OUTER) { h_node = a_node = s->node_inner[q.kc]; c_node = s->node_outer[q.kc]; }
-            else { h_node = c_node = s->node_inner[q.kc]; a_node = s->node_outer[q.kc]; }
+            if (q.medium == MED_OUTER) { h_node = a_node = s->node_inner[q.kc]; c_node = o.container == MED_PLATE ? s->node_plate : s->node_outer[q.kc]; }
+            else { h_node = c_node = s->node_inner[q.kc]; a_node = o.adj == MED_PLATE ? s->node_plate : s->node_outer[q.kc]; }
         }
         hit[i] = h_node; container[i] = c_node; adjacent[i] = a_node;
         face[i] = (o.kind == SURF_BOX || o.kind == SURF_CAP) ? o.face : 0;

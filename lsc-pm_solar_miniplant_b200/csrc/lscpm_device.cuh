@@ -13,13 +13,16 @@
 //   OUTER -> in the tube wall of capillary k: inner cylinder, outer cylinder, or the +-y caps
 //   INNER -> in the reaction mixture of capillary k: inner cylinder or the +-y caps
 //
-// with pvtrace's bookkeeping for every interface (DESIGN.md "container and adjacent"): container = the deepest scene-graph
-// node the ray leaves exactly once; adjacent = the hit node when the photon enters it, and the container of what lies
-// beyond (the same rule applied to the remaining intersections) when it leaves its own container - i.e. always the
+// with pvtrace's bookkeeping for every interface (DESIGN.md "container and adjacent"): container = the nearest node the ray
+// leaves exactly once; adjacent = the hit node when the photon enters it, and the container of what lies beyond (the
+// same rule applied to the remaining intersections) when it leaves its own container - in generic position always the
 // enclosing node: plate for a tube wall, tube wall for the mixture, air for the plate, whatever else lies ahead.
-// The capillary caps coincide with the plate's +-y faces; ties resolve in scene-graph order, plate first, so a photon
-// in a tube wall or in the mixture that reaches a cap hits the PLATE's face from its own container (n1 = tube or
-// mixture, n2 = plate) and, once transmitted, has nothing but the world sphere ahead: it leaves through that face.
+// Coincident faces: the capillary caps coincide with the plate's +-y faces (and the side PV boxes share its edge faces).
+// pvtrace sorts distances each node computed in its own frame, so float64 round-off orders such ties; here the order is
+// drawn from a hash of the photon's position (tie_bits).  The first of the tied nodes is hit node and - being left
+// exactly once - container of the whole segment, the second is adjacent: a photon that enters the mixture within a
+// millimetre of a tube end has the plate or the tube wall as container two times in three and then leaves through the
+// cap instead of reacting.  Probes keep scene-graph order (plate, tube, mixture), like the oracle without a generator.
 //
 // Divergence control (what the ncu profile of the first version asked for):
 //   * ONE code path computes every candidate distance (three slabs, near/far roots of both cylinders about
@@ -131,6 +134,9 @@ struct DevScene {
     int abs_base_plate;        // + component
     const int* abs_base_outer; // [n_ch]
     const int* abs_base_inner; // [n_ch]
+    const int* exit_base_outer;// [n_ch] exit/<tube>/<side, -cap, +cap>: a photon can leave through a cap it ties with the plate's face
+    const int* exit_base_inner;// [n_ch]
+    int cap_slot_lo, cap_slot_hi;   // cylinder face slot (1 = -cap, 2 = +cap) of the cap in the plate's -y / +y face
     float w2l[9];              // rotation world -> plate-local (row-major)
 #ifdef LSCPM_DIAG              // diagnostic build only (scripts/dye_bias.py): alternatives to the restated pvtrace rules
     int diag_emit;             // 0 kT window (the rule), 1 redshift (no thermal allowance), 2 full emission spectrum, 3 window of 3 kT
@@ -169,7 +175,8 @@ struct Photon {
 struct Hit {
     float t;
     int kind;                  // SURF_*
-    int face;                  // box face for SURF_BOX / SURF_CAP; direction (+1/-1) for SURF_CELL
+    int face;                  // box face for SURF_BOX / SURF_CAP (bits 3..: exit-bin offset of a cap hit by the tube or the
+                               // mixture, see cap_tie); direction (+1/-1) for SURF_CELL
     int ch;                    // capillary of the event
     int container;             // medium whose material governs the segment
     int adj;                   // medium on the far side of the interface (pvtrace's `adjacent`)
@@ -343,7 +350,48 @@ __device__ __forceinline__ void cylinder_roots(float a, float inv_a, float b, fl
 // virtual cell crossing (SURF_CELL) for plate flights.  One code path for all media.
 // PLATE_TOO = false: the caller never asks for a photon in the plastic (plate flights handle those), so the plate's own
 // candidates are left out.
-template <bool PLATE_TOO = true>
+// pseudo-random bits that stand for float64 round-off ordering the intersections of coincident faces
+__device__ __forceinline__ unsigned tie_bits(const Photon& p) {
+    unsigned h = (__float_as_uint(p.xr) * 2654435761u) ^ (__float_as_uint(p.z) * 2246822519u) ^ (__float_as_uint(p.y) * 3266489917u);
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    return h;
+}
+
+// Container and adjacent (packed 3 bits each) of a segment in a tube wall or in the mixture whose straight line
+// ends in the cap plane.  There the tube's (and the mixture's) only remaining intersection ties with the plate's face; the
+// first of the tied nodes is the nearest node left exactly once - the container of the WHOLE segment, also when the inner
+// cylinder is hit before the cap - and, if the segment ends on the cap, the hit node as well (so for a SURF_CAP event the
+// hit node is the container), with the second as adjacent.
+// `ties`: order drawn from tb (two-way tie {plate, tube}: bit 0; three-way {plate, tube, mixture}: bits 8.. mod 6);
+// otherwise scene-graph order (plate, tube, mixture).
+// Bits 6..: for a cap that is hit by the tube or the mixture, the offset that turns `exit_base_plate + yface` into that
+// node's own exit bin (exit/<tube or mixture>/<cap>); it travels in the upper bits of Hit::face.
+__device__ __noinline__ unsigned cap_tie(const DevScene& S, unsigned tb, bool ties, bool is_ou, bool ou_inner, bool ou_cap, bool in_cap,
+                                         bool tube_exit_cap, int kc, int yface) {
+    const bool plate_first = ties ? (tb & 1u) != 0u : true;
+    int container, adj;
+    if (is_ou) {
+        container = plate_first ? MED_PLATE : MED_OUTER;
+        adj = ou_inner ? MED_INNER : (ou_cap ? (plate_first ? MED_OUTER : MED_PLATE) : MED_PLATE);
+    } else if (in_cap) {
+        const unsigned perm = ties ? (tb >> 8) % 6u : 0u;          // (first, second): PT PX TP TX XP XT
+        container = perm < 2u ? MED_PLATE : (perm < 4u ? MED_OUTER : MED_INNER);
+        adj = (perm == 2u || perm == 4u) ? MED_PLATE : ((perm == 0u || perm == 5u) ? MED_OUTER : MED_INNER);
+    } else {   // leaves the mixture through its side; beyond it the tube's exit ties with the plate's face
+        container = MED_INNER;
+        adj = (tube_exit_cap && plate_first) ? MED_PLATE : MED_OUTER;
+    }
+    unsigned off = 0u;
+    if ((is_ou ? ou_cap : in_cap) && container != MED_PLATE) {
+        const int base = container == MED_OUTER ? __ldg(S.exit_base_outer + kc) : __ldg(S.exit_base_inner + kc);
+        const int delta = base + (yface == 3 ? S.cap_slot_hi : S.cap_slot_lo) - (S.exit_base_plate + yface);
+        LSCPM_CHECK(delta > 0);
+        off = (unsigned)max(delta, 0);
+    }
+    return (unsigned)container | ((unsigned)adj << 3) | (off << 6);
+}
+
+template <bool PLATE_TOO = true, bool TIES = true>
 __device__ __forceinline__ Hit compute_hit(const DevScene& S, const Photon& p) {
     Hit h;
     h.ch = p.kc;
@@ -385,28 +433,30 @@ __device__ __forceinline__ Hit compute_hit(const DevScene& S, const Photon& p) {
         }
         if (o_near < t_pl) { t_pl = o_near; k_pl = SURF_OUTER; f_pl = 0; adj_pl = MED_OUTER; }
     }
-    // OUTER: inner cylinder, else cap (coincides with the plate face, which sorts first and is the hit node: adjacent =
-    // plate), else the tube's own outer surface (adjacent = container of what lies beyond = plate).  The container is
-    // the tube throughout: it is the deepest node the ray leaves exactly once.
+    // OUTER: inner cylinder, else cap, else the tube's own outer surface (adjacent = container of what lies beyond = plate)
     const bool ou_inner = i_near < o_far && i_near < ty;
-    const bool ou_cap = !ou_inner && ty <= o_far;
+    const bool tube_exit_cap = ty <= o_far;                  // the straight line leaves the TUBE through the cap plane
+    const bool ou_cap = !ou_inner && tube_exit_cap;
     const float t_ou = ou_inner ? i_near : (ou_cap ? ty : o_far);
     const int k_ou = ou_inner ? SURF_INNER : (ou_cap ? SURF_CAP : SURF_OUTER);
-    const int c_ou = MED_OUTER;
-    const int adj_ou = ou_inner ? MED_INNER : MED_PLATE;
-    // INNER: cap (the plate's face again), else the inner surface with the tube wall beyond
+    // INNER: cap, else the inner surface with the tube wall beyond
     const bool in_cap = ty <= i_far;
     const float t_in = in_cap ? ty : i_far;
     const int k_in = in_cap ? SURF_CAP : SURF_INNER;
-    const int c_in = MED_INNER;
-    const int adj_in = in_cap ? MED_PLATE : MED_OUTER;
 
     const bool is_pl = PLATE_TOO && p.medium == MED_PLATE, is_ou = p.medium == MED_OUTER;
     h.t = fmaxf(is_pl ? t_pl : (is_ou ? t_ou : t_in), 0.f);
     h.kind = is_pl ? k_pl : (is_ou ? k_ou : k_in);
     h.face = is_pl ? f_pl : ((h.kind == SURF_CAP) ? yface : 0);
-    h.container = is_pl ? MED_PLATE : (is_ou ? c_ou : c_in);
-    h.adj = is_pl ? adj_pl : (is_ou ? adj_ou : adj_in);
+    // generic position: the photon's own node is the nearest node left exactly once
+    h.container = is_pl ? MED_PLATE : (is_ou ? MED_OUTER : MED_INNER);
+    h.adj = is_pl ? adj_pl : (is_ou ? (ou_inner ? MED_INNER : MED_PLATE) : MED_OUTER);
+    // the segment's straight line ends in the cap plane, where the faces of plate, tube (and mixture) coincide: rare
+    if (!is_pl && (tube_exit_cap || (!is_ou && in_cap))) {
+        const unsigned r = cap_tie(S, TIES ? tie_bits(p) : 0u, TIES, is_ou, ou_inner, ou_cap, in_cap, tube_exit_cap, p.kc, yface);
+        h.container = r & 7u; h.adj = (r >> 3) & 7u;
+        h.face |= (int)(r >> 6) << 3;
+    }
     return h;
 }
 
@@ -669,6 +719,19 @@ __device__ __forceinline__ float normal_gap(float t, int f, float dx, float dy, 
     return t * fabsf(f < 2 ? dx : (f < 4 ? dy : dz));
 }
 
+// outside box whose entry face coincides with plate face `face` where the photon leaves through it (the side PV boxes share
+// the plate's edge faces): its entry ties with the plate's exit
+__device__ __noinline__ int ext_touching(const DevScene& S, int face, float ox, float oy, float oz, float dx, float dy, float dz) {
+    const RayInv inv = ray_inverse(dx, dy, dz);
+    for (int i = 0; i < S.n_ext; ++i) {
+        const DevExtBox& b = S.ext[i];
+        float tmin, tmax; int f, fx;
+        slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, ox, oy, oz, dx, dy, dz, inv, tmin, tmax, f, fx);
+        if (tmin <= tmax && tmax > 0.f && (f ^ 1) == face && fabsf(normal_gap(tmin, f, dx, dy, dz)) <= EXT_TOL) return i;
+    }
+    return -1;
+}
+
 // Nearest surface for a ray in the air around the plate: node 0 = plate, i+1 = outside box i, -1 = none.
 // `skip` is the convex body the photon has just left or bounced off (0 plate, i+1 box i, -1 none): it cannot be met
 // again before another interaction, so it is excluded by logic rather than by a distance tolerance (a tolerance on the
@@ -704,6 +767,11 @@ __device__ __forceinline__ int exit_bin(const DevScene& S, int aux) {
     if (n_surface == 0) return BIN_MISS;
     if (n_surface == 1 && (aux & (1 << 11)) && !(aux & 256)) return BIN_ENTRY_REFLECT;
     const int node = (aux >> 12) & 7, face = (aux >> 24) & 7;
+    if (node == 7) {   // left through a capillary end cap that was the hit node: cap node in bits 27-28, capillary in bits 16-23
+        const int kc = (aux >> 16) & 0xff;
+        const int base = ((aux >> 27) & 3) == MED_OUTER ? __ldg(S.exit_base_outer + kc) : __ldg(S.exit_base_inner + kc);
+        return base + (face == 3 ? S.cap_slot_hi : S.cap_slot_lo);
+    }
     return (node == 0 ? S.exit_base_plate : S.ext[node - 1].exit_base) + face;
 }
 
@@ -790,15 +858,14 @@ struct StepOut {
 // class order = deal order: FLAT and CYL share the Fresnel code, CELL has no work of its own, ABSORB and FRESH share the source code
 constexpr int CLS_FLAT = 0, CLS_CYL = 1, CLS_CELL = 2, CLS_ABSORB = 3, CLS_FRESH = 4, CLS_OUT = 5, CLS_IDLE = 6, N_CLS = 7;
 
-// pending-interaction word: class | surface kind | face + 1 | container | adjacent
+// pending-interaction word: class | surface kind | container | adjacent | face + 1 (the rest of the word)
 __device__ __forceinline__ unsigned pack_pending(int cls, int kind, int face, int container, int adj) {
-    return (unsigned)cls | ((unsigned)kind << 4) | ((unsigned)(face + 1) << 7) | ((unsigned)container << 11) |
-           ((unsigned)adj << 14);
+    return (unsigned)cls | ((unsigned)kind << 4) | ((unsigned)container << 7) | ((unsigned)adj << 10) | ((unsigned)(face + 1) << 13);
 }
 __device__ __forceinline__ int pending_kind(unsigned w) { return (w >> 4) & 7; }
-__device__ __forceinline__ int pending_face(unsigned w) { return (int)((w >> 7) & 15) - 1; }
-__device__ __forceinline__ int pending_container(unsigned w) { return (w >> 11) & 7; }
-__device__ __forceinline__ int pending_adj(unsigned w) { return (w >> 14) & 7; }
+__device__ __forceinline__ int pending_container(unsigned w) { return (w >> 7) & 7; }
+__device__ __forceinline__ int pending_adj(unsigned w) { return (w >> 10) & 7; }
+__device__ __forceinline__ int pending_face(unsigned w) { return (int)(w >> 13) - 1; }
 
 // ------------------------------------------------------------------------------------------------
 // Plate flight (standard scene, photon in the PMMA): straight to the next REAL event.
@@ -1037,6 +1104,8 @@ template <bool EXT>
 __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, int kind, int face, int container, int adj,
                                                 float u_surf, int& event) {
     const bool flat = kind == SURF_BOX || kind == SURF_CAP;
+    const int exit_offset = face >> 3;      // non-zero for a cap hit by the tube or the mixture (cap_tie)
+    face &= 7;
     float nx, ny, nz;
     box_normal(face, nx, ny, nz);
     if (flat) {
@@ -1049,10 +1118,15 @@ __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, in
         const float inv = frsqrt(fmaf(p.xr, p.xr, p.z * p.z));
         nx = p.xr * inv; ny = 0.f; nz = p.z * inv;
     }
-    // leaving the plate the photon meets the world's medium even when an outside box lies straight ahead or shares the
-    // face: adjacent is the container of what lies beyond the face, and a box that is entered and left again is not one
-    const float n2 = S.med[adj].n;
+    // leaving the plate the photon meets the world's medium even when an outside box lies straight ahead: adjacent is the
+    // container of what lies beyond the face, and a box that is entered and left again is not one.  A box that SHARES the
+    // face ties with it: when its entry sorts first it is the hit node and adjacent (tie_bits, evaluated on arrival)
+    float n2 = S.med[adj].n;
     const bool leaving = flat && p.medium != MED_AIR;
+    if (EXT && leaving && kind == SURF_BOX && (tie_bits(p) & 2u)) {
+        const int e = ext_touching(S, face, abs_x(S, p), p.y, p.z + S.zc, p.dx, p.dy, p.dz);
+        if (e >= 0) n2 = S.ext[e].n;
+    }
     const float n1 = S.med[container].n;
     const Interface I = interface_eval(p.dx, p.dy, p.dz, nx, ny, nz, n1, n2);
     const bool reflected = u_surf < I.R;
@@ -1063,7 +1137,11 @@ __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, in
         p.medium = (p.aux >> 4) & 3;
         return -1;
     }
-    if (EXT) p.aux = note_surface(p.aux, false, 0, face, leaving && !reflected);
+    if (EXT) {
+        const bool cap_hit = kind == SURF_CAP && container != MED_PLATE;    // hit node (= container at a cap) is the tube or the mixture
+        p.aux = note_surface(p.aux, false, cap_hit ? 7 : 0, face, leaving && !reflected);
+        if (cap_hit && leaving && !reflected) p.aux = (p.aux & ~((0xff << 16) | (3 << 27))) | (min(p.kc, 255) << 16) | (container << 27);
+    }
     if (reflected) return -1;
     if (flat) {
         if (EXT) {
@@ -1073,7 +1151,7 @@ __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, in
             return -1;
         }
         p.medium = MED_AIR;
-        return (p.steps + 1 > MAXSTEPS) ? BIN_KILL : S.exit_base_plate + face;
+        return (p.steps + 1 > MAXSTEPS) ? BIN_KILL : S.exit_base_plate + face + exit_offset;
     }
     if (kind == SURF_OUTER) p.medium = (p.medium == MED_PLATE) ? MED_OUTER : MED_PLATE;
     else p.medium = (p.medium == MED_OUTER) ? MED_INNER : MED_OUTER;
@@ -1098,7 +1176,7 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
     out.ch = p.kc;
     Hit h; int cls;
     const int killed = advance_hit<false, FLIGHT, FOLD>(S, p, w.x, h, cls, out.extra);
-    out.medium = h.container; out.kind = h.kind; out.face = h.face;
+    out.medium = h.container; out.kind = h.kind; out.face = h.kind == SURF_CAP ? (h.face & 7) : h.face;
     if (killed >= 0) { out.event = EV_KILL; return killed; }
     if (cls == CLS_ABSORB) {
         const int bin = interact_absorb(S, p, h.container, u01(w.y), w.z, out.event);

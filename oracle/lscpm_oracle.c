@@ -7,8 +7,9 @@
  * /root/reference and not installable offline); tallies are pinned statistically on the full-year results the
  * reference committed (tests/test_solar_stage.py).  This file is the fast twin of
  * oracle/pvtrace_oracle.py — the same generic algorithm (every geometry node intersected in its own
- * local frame, stable distance sort, container = deepest node hit exactly once, adjacent = the hit node or, when the
- * photon leaves its container, the container of what lies beyond (pinned on reference output), Beer-Lambert free
+ * local frame, distance sort with exact ties in random order, container = nearest node hit exactly once, adjacent = the hit
+ * node or, when the photon leaves its container, the container of what lies beyond (both pinned on reference output,
+ * DESIGN.md section 5), Beer-Lambert free
  * path, Fresnel reflect/refract, kT-restricted re-emission), working on the flattened description of
  * include/lscpm.h instead of the scene graph.  tests/test_oracle_golden.py checks the two against
  * each other ray by ray; the Python twin is checked against the reference's own test bands and the
@@ -219,8 +220,10 @@ static void to_local(const ONode* n, const double* p, const double* v, double* o
     }
 }
 
-/* All intersections sorted by distance; ties (within ZERO_TOL) keep node (pre-order) order. */
-static int scene_intersections(const OScene* s, const double* p, const double* v, Hit* out) {
+/* All intersections sorted by distance.  Exact ties (coincident faces, within ZERO_TOL): pvtrace sorts distances that each
+ * node computed in its own frame, so float64 round-off decides their order - restated as a uniformly random order when a
+ * generator is given (the photon loop), node (pre-order) order otherwise (probes). */
+static int scene_intersections(const OScene* s, const double* p, const double* v, Hit* out, Rng* rng) {
     int total = 0;
     Hit local[MAX_HITS_PER_NODE];
     for (int i = 0; i < s->n_nodes; ++i) {
@@ -240,26 +243,36 @@ static int scene_intersections(const OScene* s, const double* p, const double* v
             out[pos] = h; ++total;
         }
     }
+    if (rng) {
+        int start = 0;
+        for (int end = 1; end <= total; ++end) {
+            if (end == total || out[end].t - out[start].t > ZERO_TOL) {
+                for (int i = end - 1; i > start; --i) {           /* Fisher-Yates over the tied group */
+                    int j = start + (int)(rng_uniform(rng) * (double)(i - start + 1));
+                    if (j > i) j = i;
+                    Hit tmp = out[i]; out[i] = out[j]; out[j] = tmp;
+                }
+                start = end;
+            }
+        }
+    }
     return total;
 }
 
 typedef struct { int hit, container, adjacent, face; double distance; } NextHit;
 
-/* pvtrace find_container: of the nodes that appear exactly once in hits[0..n) (the ray is inside them) the deepest in the
- * scene graph; sorted(pairs, key=depth)[-1], i.e. the later entry wins among equal depths. */
+/* pvtrace find_container: the nearest of the nodes that appear exactly once in hits[0..n) (the ray is inside them) */
 static int find_container(const OScene* s, const Hit* hits, int n, int* counts) {
     if (n == 1) return hits[0].node;
     memset(counts, 0, sizeof(int) * (size_t)s->n_nodes);
     for (int i = 0; i < n; ++i) counts[hits[i].node]++;
-    int best = -1;
-    for (int i = 0; i < n; ++i)
-        if (counts[hits[i].node] == 1 && (best < 0 || s->nodes[hits[i].node].depth >= s->nodes[best].depth)) best = hits[i].node;
-    return best;
+    for (int i = 0; i < n; ++i) if (counts[hits[i].node] == 1) return hits[i].node;
+    return -1;
 }
 
 /* literal next_hit; returns 0 when the ray leaves the scene */
-static int next_hit(const OScene* s, const double* p, const double* v, Hit* scratch, int* counts, NextHit* nh) {
-    int n_all = scene_intersections(s, p, v, scratch), n = 0;
+static int next_hit(const OScene* s, const double* p, const double* v, Hit* scratch, int* counts, NextHit* nh, Rng* rng) {
+    int n_all = scene_intersections(s, p, v, scratch, rng), n = 0;
     for (int i = 0; i < n_all; ++i) if (!(fabs(scratch[i].t) <= ZERO_TOL)) scratch[n++] = scratch[i];
     if (n == 0) return 0;
     nh->hit = scratch[0].node; nh->face = scratch[0].face; nh->distance = scratch[0].t;
@@ -340,7 +353,7 @@ static int follow(const OScene* s, double* p, double* v, double wl, Rng* rng, Hi
         ++count;
         if (count > MAXSTEPS) { record(rec, photon, &k, LSCPM_EV_KILL, -1, p, v, wl); bin = 0; break; }
         NextHit nh;
-        int found = next_hit(s, p, v, scratch, counts, &nh);
+        int found = next_hit(s, p, v, scratch, counts, &nh, rng);
         if (found && nh.hit == 0) for (int c = 0; c < 3; ++c) p[c] += nh.distance * v[c];
         if (!found || nh.hit == 0) {
             record(rec, photon, &k, LSCPM_EV_EXIT, found ? 0 : -1, p, v, wl);
@@ -501,7 +514,7 @@ int oracle_probe(const LscpmSceneDesc* d, int64_t n, const double* pos, const do
         hit[i] = container[i] = adjacent[i] = face[i] = -1;
         distance[i] = reflectivity[i] = 0.0;
         for (int c = 0; c < 3; ++c) point[3 * i + c] = normal[3 * i + c] = reflected[3 * i + c] = refracted[3 * i + c] = 0.0;
-        if (!next_hit(&s, p, v, scratch, counts, &nh)) continue;
+        if (!next_hit(&s, p, v, scratch, counts, &nh, NULL)) continue;
         hit[i] = nh.hit; container[i] = nh.container; adjacent[i] = nh.adjacent; face[i] = nh.face; distance[i] = nh.distance;
         for (int c = 0; c < 3; ++c) point[3 * i + c] = p[c] + nh.distance * v[c];
         if (nh.adjacent < 0 || nh.hit == 0) continue;

@@ -28,14 +28,14 @@ Algorithm restated (pvtrace 2.1, ``pvtrace/algorithm/photon_tracer.py`` and frie
 ``next_hit``     all intersections of the ray with every geometry node, each computed in the node's
                  local frame, expressed in the root frame and sorted by distance (stable sort, i.e.
                  exact ties keep scene-graph traversal order); intersections at distance ~0 are
-                 dropped; ``container`` = ``find_container(intersections)``: of the nodes hit exactly once (the
-                 ray is inside them) the deepest in the scene graph; ``hit`` = first intersection's node;
-                 ``adjacent`` = ``find_container(intersections[1:])`` if ``container is hit`` (what encloses the
-                 point just beyond the surface) else ``hit``.  The adjacency rule is pinned on reference output:
-                 with ``adjacent = intersections[1].hit`` (a photon leaving a tube wall then sees a sibling
-                 capillary's index when one lies straight ahead) the dye scenes react 0.39 % too much against the
-                 reference's committed tilt sweeps (z = -6.5 over 1.1e7 reference photons), with this rule the
-                 ratio is 0.9995 (z = +0.8) - DESIGN.md section 5.
+                 dropped; ``container`` = ``find_container(intersections)``: the nearest of the nodes hit exactly
+                 once (the ray is inside them); ``hit`` = first intersection's node; ``adjacent`` =
+                 ``find_container(intersections[1:])`` if ``container is hit`` (what encloses the point just beyond
+                 the surface) else ``hit``.  Both details are pinned on reference output, the 41 committed dye tilt
+                 sweeps (3.2e7 reference photons): with ``adjacent = intersections[1].hit`` (a
+                 photon leaving a tube wall then sees a sibling capillary's index when one lies straight ahead) the
+                 scenes react 0.34 % too much (z = -9.7); with the deepest instead of the nearest node as container
+                 0.13 % too much (z = -3.6); as restated here 0.9999 of the reference (z = +0.2).
 ``follow``       loop (<= ``maxsteps``): ``next_hit``; none -> EXIT; hit is the root -> EXIT; sample a free
                  path ``-ln(1-U)/alpha(lambda)`` in the container's material; if shorter than the distance to
                  the surface: absorb there, pick the component ~ alpha_i, radiative (``U < QY``) -> re-emit
@@ -43,10 +43,12 @@ Algorithm restated (pvtrace 2.1, ``pvtrace/algorithm/photon_tracer.py`` and frie
                  ABSORB / REACT; otherwise move to the surface, reflect with probability ``R_fresnel`` else
                  refract (Snell).
 
-Two deliberate idealisations (documented in DESIGN.md): the distance~0 filter and the tie order are
-evaluated with a tolerance (``ZERO_TOL``) that stands for exact arithmetic — real pvtrace applies
-``10*DBL_EPSILON`` to float64 round-off, which makes its behaviour at coincident faces depend on
-noise; the restatement takes the noise-free limit (stable order = scene-graph pre-order).
+Coincident faces (documented in DESIGN.md): the distance~0 filter and "distances tie" are evaluated with a
+tolerance (``ZERO_TOL``) that stands for exact arithmetic.  Real pvtrace applies ``10*DBL_EPSILON`` to
+float64 round-off, so the ORDER of tied intersections (the capillary end caps coincide with the plate's
++-y faces, the side PV boxes with its edge faces) is decided by noise: the photon loop draws it uniformly
+at random, which is also what the reference's committed results favour (plate-first order: z = +2.1,
+random order: z = +0.2); probes without a generator keep scene-graph pre-order.
 """
 from __future__ import annotations
 
@@ -283,8 +285,10 @@ class OracleScene:
             self._walk(child, world, depth + 1)
 
     # -- intersections -------------------------------------------------------------
-    def intersections(self, position, direction):
-        """[(distance, node_index, face, point_world)] sorted by distance, ties in traversal order."""
+    def intersections(self, position, direction, rng=None):
+        """[(distance, node_index, face, point_world)] sorted by distance.  Exact ties (coincident faces): pvtrace sorts
+        distances that each node computed in its own frame, so float64 round-off decides; restated as a uniformly
+        random order when ``rng`` is given (the photon loop), as scene-graph traversal order otherwise (probes)."""
         position = np.asarray(position, dtype=float)
         direction = np.asarray(direction, dtype=float)
         found = []
@@ -311,11 +315,18 @@ class OracleScene:
                 else:
                     break
             ordered.insert(pos, item)
+        if rng is not None:
+            start = 0
+            for end in range(1, len(ordered) + 1):
+                if end == len(ordered) or ordered[end][0] - ordered[start][0] > ZERO_TOL:
+                    if end - start > 1:
+                        ordered[start:end] = [ordered[start + int(k)] for k in rng.permutation(end - start)]
+                    start = end
         return [(t, idx, face, position + t * direction) for t, idx, face in ordered]
 
-    def next_hit(self, position, direction):
+    def next_hit(self, position, direction, rng=None):
         """Literal ``next_hit``: returns None or (hit, container, adjacent, point, distance, face)."""
-        inter = [x for x in self.intersections(position, direction) if not abs(x[0]) <= ZERO_TOL]
+        inter = [x for x in self.intersections(position, direction, rng) if not abs(x[0]) <= ZERO_TOL]
         if not inter:
             return None
         first = inter[0]
@@ -327,18 +338,15 @@ class OracleScene:
         return hit, container, adjacent, first[3], first[0], first[2]
 
     def find_container(self, inter):
-        """pvtrace ``find_container``: of the nodes that appear exactly once in the list (the ray is inside them) the one
-        deepest in the scene graph (``sorted(pairs, key=depth)[-1]``: the later entry wins among equal depths)."""
+        """pvtrace ``find_container``: the nearest of the nodes that appear exactly once in the list (the ray is inside
+        a convex node iff it leaves it once)."""
         if len(inter) == 1:
             return inter[0][1]
         counts = Counter(x[1] for x in inter)
-        best = None
         for x in inter:
-            if counts[x[1]] == 1 and (best is None or self.nodes[x[1]].depth >= self.nodes[best].depth):
-                best = x[1]
-        if best is None:
-            raise RuntimeError("no container: the ray is outside every node (pvtrace raises here as well)")
-        return best
+            if counts[x[1]] == 1:
+                return x[1]
+        raise RuntimeError("no container: the ray is outside every node (pvtrace raises here as well)")
 
     # -- materials -----------------------------------------------------------------
     def coefficients(self, node_index, wavelength):
@@ -361,7 +369,7 @@ class OracleScene:
             if count > maxsteps:
                 history.append(Step(position, direction, wavelength, KILL))
                 break
-            info = self.next_hit(position, direction)
+            info = self.next_hit(position, direction, rng)
             if info is None:
                 history.append(Step(position, direction, wavelength, EXIT))
                 break

@@ -5,6 +5,7 @@ import os, pickle, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 N = int(float(sys.argv[1])) if len(sys.argv) > 1 and sys.argv[1] != "--child" else 20000
+ALL = os.environ.get("DIAG_ALL_FILES")   # every committed dye sweep instead of the 14-file subset
 FILES = ["Eindhoven_0deg", "Eindhoven_20deg", "Eindhoven_40deg", "Eindhoven_60deg", "Eindhoven_80deg", "Plataforma Solar de Almería_15deg",
          "Plataforma Solar de Almería_30deg", "Plataforma Solar de Almería_45deg", "Townsville_0deg", "Townsville_15deg", "Townsville_30deg",
          "North Cape_40deg", "North Cape_55deg", "North Cape_70deg"]
@@ -51,6 +52,11 @@ from lscpm_b200 import lights
 from miniplant.locations import LOCATIONS
 from miniplant.solar_data import solar_data_for_place_and_time
 sites = {s.name: s for s in LOCATIONS}
+if ALL:
+    import numpy as _np
+    _g = _np.load(os.path.join(ROOT, "tests", "golden", "reference_sweep_counts.npz"))
+    FILES = sorted({n.split("|")[0] for n in _g.files if "_no_dye_" not in n})
+    VARIANTS = VARIANTS[:1]
 inputs = {}
 for key in FILES:
     site = sites[key.split("_")[0]]

@@ -83,8 +83,9 @@ def test_runner_returns_the_reference_tuple(built_library):
                                 num_photons=20_000, seed=1)
     assert isinstance(res, tuple) and len(res) == 5
     fraction, scene, photon_path, bottom, side = res
-    # C oracle at 4e5 photons: reacted 0.306, bottom PV 0.169, side PVs 0.099 (total internal reflection survives over the PVs)
-    assert 0.28 < fraction < 0.33 and 0.15 * 20_000 < bottom < 0.19 * 20_000 and 0.08 * 20_000 < side < 0.12 * 20_000
+    # C oracle at 4e5 photons: reacted 0.295, bottom PV 0.166, side PVs 0.120 (total internal reflection survives over the
+    # bottom PV; at the edge faces the side PVs share, the box's face sorts first half of the time and lends its index)
+    assert 0.27 < fraction < 0.32 and 0.15 * 20_000 < bottom < 0.185 * 20_000 and 0.105 * 20_000 < side < 0.135 * 20_000
     assert hasattr(scene, "light_nodes") and photon_path == []
     plain = run_direct_simulation(tilt_angle=40, solar_elevation=50, solar_azimuth=180, num_photons=2000, seed=1)
     assert isinstance(plain, float)

@@ -3,6 +3,7 @@ pvtrace formulas, not from reference output: the reference pins no per-ray value
 against the published Random123 vectors."""
 import ctypes as C
 import math
+from collections import Counter
 
 import numpy as np
 import pytest
@@ -127,9 +128,10 @@ def test_philox_known_answers(built_library):
 
 
 def test_container_and_adjacent_bookkeeping():
-    """pvtrace ``next_hit`` / ``find_container``: container = deepest node hit exactly once; adjacent = the hit node, or
-    - when the photon leaves its container - the container of what lies beyond the surface.  The adjacency rule is pinned
-    on the reference's committed results; these are its consequences in the scenes of the path."""
+    """pvtrace ``next_hit`` / ``find_container``: container = nearest node hit exactly once; adjacent = the hit node, or
+    - when the photon leaves its container - the container of what lies beyond the surface; coincident faces in random
+    order.  Pinned on the reference's committed results; these are the consequences in the scenes
+    of the path."""
     scene = po.OracleScene(standard_scene(tilt=0, elevation=90, wavelength=585.0))
     names = [n.name for n in scene.nodes]
     plate, world = "LSC-PM Reactor 47x47 cm^2", "World (air)"
@@ -149,13 +151,30 @@ def test_container_and_adjacent_bookkeeping():
     # in the plate: capillary ahead / top face ahead
     assert hit([x4 + 0.01, 0.0, zc], [-1.0, 0.0, 0.0]) == ("Capillary_PFA_4", plate, "Capillary_PFA_4")
     assert hit([x4 + 0.01, 0.0, zc], [0.0, 0.0, 1.0]) == (plate, plate, world)
-    # along the tube wall to its end cap, which coincides with the plate's +y face: the plate's face sorts first and is
-    # the hit node, the container stays the tube (deepest node left exactly once)
-    assert hit([x4 + 0.5 * (r_o + r_i), 0.2, zc], [0.0, 1.0, 0.0]) == (plate, "Capillary_PFA_4", plate)
-    assert hit([x4, 0.2, zc], [0.0, 1.0, 0.0]) == (plate, "Reaction_mixture_4", plate)
+    # along the tube wall / the mixture to the end cap, which coincides with the plate's +y face: without a generator the
+    # tied faces keep scene-graph order (plate, tube, mixture) ...
+    assert hit([x4 + 0.5 * (r_o + r_i), 0.2, zc], [0.0, 1.0, 0.0]) == (plate, plate, "Capillary_PFA_4")
+    assert hit([x4, 0.2, zc], [0.0, 1.0, 0.0]) == (plate, plate, "Capillary_PFA_4")
+    # ... and with one (the photon loop) every order occurs: the first of the tied nodes is hit node and container, the
+    # second is adjacent
+    rng = np.random.default_rng(5)
+    seen = Counter()
+    for _ in range(600):
+        h, c, a = scene.next_hit(np.array([x4, 0.2, zc]), np.array([0.0, 1.0, 0.0]), rng)[:3]
+        assert h == c and a != h
+        seen[(names[h], names[a])] += 1
+    assert len(seen) == 6 and set(n for pair in seen for n in pair) == {plate, "Capillary_PFA_4", "Reaction_mixture_4"}
+    assert min(seen.values()) > 60 and max(seen.values()) < 140           # 100 expected each
+    seen = Counter(names[scene.next_hit(np.array([x4 + 0.5 * (r_o + r_i), 0.2, zc]), np.array([0.0, 1.0, 0.0]), rng)[1]]
+                   for _ in range(400))
+    assert set(seen) == {plate, "Capillary_PFA_4"} and min(seen.values()) > 150
+    # away from the caps the generator changes nothing
+    assert scene.next_hit(np.array([x4, 0.0, zc]), np.array([1.0, 0.0, 0.2]), rng)[:3] == \
+        scene.next_hit(np.array([x4, 0.0, zc]), np.array([1.0, 0.0, 0.2]))[:3]
 
-    # photovoltaic box under the plate (air gap) and side boxes sharing the plate's edge faces: a photon leaving the plate
-    # meets air, whatever lies beyond
+    # photovoltaic box under the plate (air gap): a photon leaving the plate meets air.  Side boxes share the plate's edge
+    # faces: in scene-graph order the plate's face comes first and the photon meets air as well (with the box's face
+    # first - half of the time in the photon loop - it enters the box directly)
     pv = po.OracleScene(standard_scene(tilt=0, elevation=90, wavelength=585.0, add_bottom_PV=True, add_side_PV=True))
     names = [n.name for n in pv.nodes]
     scene = pv

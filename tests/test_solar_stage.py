@@ -177,28 +177,36 @@ def test_evaluate_tilt_angle_schema_and_skip(tmp_path):
 
 
 def test_oracle_against_the_reference_yearly_results():
-    """Pins the ORACLE on reference output: the full-year result CSVs the reference committed (column means in
-    tests/golden/reference_yearly_means.json).  Every 16th time point of the Eindhoven 40 deg year, 1500 photons each,
-    traced by the C oracle; yearly mean reacted fractions within 2.5 % (sub-sampling the year costs ~1 %)."""
-    import json
-
+    """Pins the ORACLE on reference output: the per-time-point counts of the full-year runs the reference committed
+    (tests/golden/reference_yearly_counts.npz, 120 photons per point).  Every 16th time point of the Eindhoven 40 deg
+    year, 1500 photons each, traced by the C oracle and compared on the SAME rows: the difference of the two summed
+    fractions in units of its binomial standard deviation (both sides' noise) stays within 4."""
+    from helpers import frame_epoch, reference_counts
     from lscpm_b200 import lights
     from miniplant.full_simulation import trace_time_points
     from miniplant.locations import EINDHOVEN
     from miniplant.solar_data import solar_data_for_place_and_time
 
-    with open(os.path.join(GOLDEN, "reference_yearly_means.json")) as fh:
-        ref = json.load(fh)["files"]
+    gold = np.load(os.path.join(GOLDEN, "reference_yearly_counts.npz"))
     data = solar_data_for_place_and_time(EINDHOVEN, 40, 1800, write_csv=False)
-    assert len(data) == ref["Eindhoven_40deg_results.csv"]["rows"]
     rows = data.iloc[3::16]
-    for dye, key in ((True, "Eindhoven_40deg_results.csv"), (False, "Eindhoven_40deg_results_no_dye.csv")):
+    n_ours = 1500
+    for dye, key in ((True, "Eindhoven_40deg_results"), (False, "Eindhoven_40deg_results_no_dye")):
+        ref = reference_counts(gold, key)
+        assert len(data) == len(ref)
         direct = [lights.direct_light(40, r["apparent_elevation"], r["azimuth"], r["direct_spectrum"]) for _, r in rows.iterrows()]
         diffuse = [lights.diffuse_light(40, r["diffuse_spectrum"]) for _, r in rows.iterrows()]
-        frac = trace_time_points(40, direct + diffuse, 1500, include_dye=dye, seed=4, tracer=_oracle_tracer)
+        frac = trace_time_points(40, direct + diffuse, n_ours, include_dye=dye, seed=4, tracer=_oracle_tracer)
         n = len(rows)
-        assert abs(frac[:n].mean() / ref[key]["simulation_direct_mean"] - 1) < 0.025, (dye, frac[:n].mean())
-        assert abs(frac[n:].mean() / ref[key]["simulation_diffuse_mean"] - 1) < 0.025, (dye, frac[n:].mean())
+        ours = pd.DataFrame({"direct": frac[:n], "diffuse": frac[n:]}, index=frame_epoch(rows))
+        both = ours.join(ref, how="inner", rsuffix="_ref")
+        assert len(both) == n
+        for column in ("direct", "diffuse"):
+            p_ours, p_ref = both[column].values, both[column + "_ref"].values / 120.0
+            pooled = 0.5 * (p_ours + p_ref)
+            sigma = np.sqrt(np.sum(pooled * (1 - pooled)) * (1 / 120.0 + 1 / n_ours))
+            z = (p_ours.sum() - p_ref.sum()) / sigma
+            assert abs(z) < 4.0, (dye, column, z, p_ours.mean(), p_ref.mean())
 
 
 def test_experimental_conditions_script_window():
