@@ -38,6 +38,21 @@ METRIC = "photons/sec traced to termination"
 
 
 WORKLOAD = "config2"
+_RESULT_FD = 1
+
+
+def claim_stdout() -> None:
+    """stdout carries exactly one JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    version banner there when NCCL_DEBUG is set), so the real stdout is kept aside for the result and descriptor 1 is
+    pointed at stderr for everything else."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
 
 
 def workload_scene():
@@ -174,7 +189,7 @@ def run_reference(args) -> None:
                          "sample": f"{sample} photons per step of the same workload, OpenMP over {cores} threads"},
         "e2e": {"value": value, "unit": "photons/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(args) -> str:
@@ -323,7 +338,7 @@ def run_cuda(args) -> None:
             line["cpu_baseline"] = {"value": rate, "unit": "photons/s", "cores": cores, "kind": "port",
                                     "sample": f"{n_cpu} photons of the same workload in {dt:.1f} s "
                                               f"(C float64 oracle, OpenMP {cores} threads)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -344,6 +359,7 @@ def main() -> None:
     args = ap.parse_args()
     global WORKLOAD
     WORKLOAD = args.workload
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
