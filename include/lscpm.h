@@ -58,8 +58,10 @@ extern "C" {
 
 /*
  * Flattened scene graph (what scene_creator.flatten() emits).  Geometry nodes only, in scene-graph
- * pre-order (parents before children, children in insertion order) — that order is the tie order of
- * coincident intersections.  Node 0 is the world node.  Replaces the pvtrace Scene object handed to
+ * pre-order (parents before children, children in insertion order).  Node 0 is the world node.
+ * Coincident faces (capillary end caps in the plate's faces, boxes sharing a plate face): the photon
+ * loop orders such tied intersections at random, as float64 round-off does in pvtrace; lscpm_probe
+ * reports them in this pre-order.  Replaces the pvtrace Scene object handed to
  * _common_simulation_runner (reference miniplant/simulation_runner.py:16-21).
  */
 typedef struct LscpmSceneDesc {
@@ -191,7 +193,9 @@ uint64_t lscpm_launch_count(void);
 /*
  * For n rays given in WORLD coordinates (pos[3n], dir[3n], unit directions): the next interface
  * exactly as pvtrace's next_hit reports it (reference call site miniplant/simulation_runner.py:45-48)
- * plus the deterministic part of the surface interaction.  All arrays are host memory.
+ * plus the deterministic part of the surface interaction (container = nearest node the ray leaves
+ * exactly once; adjacent = the hit node, or the container of what lies beyond when the ray leaves its
+ * own container; tied intersections in scene-graph pre-order).  All arrays are host memory.
  *   hit/container/adjacent[n]  node indices (-1: none; hit = -1 means the ray leaves the scene)
  *   face[n]                    face of the hit node (box: -x,+x,-y,+y,-z,+z = 0..5; cylinder: side,-cap,+cap)
  *   distance[n], point[3n], normal[3n] (facing along the ray), reflectivity[n],
