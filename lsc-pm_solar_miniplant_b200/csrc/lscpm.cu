@@ -964,6 +964,16 @@ int lower_scene(const LscpmSceneDesc* d, LscpmScene* s) {
         b.abs_bin = s->layout.abs_base[node];
         b.exit_base = s->layout.exit_base[node];
     }
+    for (int f = 0; f < 6; ++f) {   // boxes that share plate face f: their opposite face lies in its plane
+        D.ext_touch[f] = 0u;
+        const double plate_half[3] = {(double)D.hx, (double)D.hy, (double)D.hz};
+        const int ax = f / 2;
+        for (int e = 0; e < D.n_ext; ++e) {
+            const double c[3] = {ext_centres[e].x, ext_centres[e].y, ext_centres[e].z}, h[3] = {ext_halves[e].x, ext_halves[e].y, ext_halves[e].z};
+            const double gap = (f & 1) ? (c[ax] - h[ax]) - plate_half[ax] : -plate_half[ax] - (c[ax] + h[ax]);
+            if (std::fabs(gap) <= (double)EXT_TOL) D.ext_touch[f] |= 1u << e;
+        }
+    }
     s->bin_names.resize(D.n_bins);
     for (int b = 0; b < D.n_bins; ++b) s->bin_names[b] = bin_name(d, b);
     return LSCPM_OK;

@@ -123,6 +123,7 @@ struct DevScene {
     DevMedium med[5];          // indexed by MED_*; med[MED_AIR] and med[MED_OUT] carry the world's refractive index only
     int n_ext;                 // outside boxes (0 for the standard scene: none of the MED_OUT code runs then)
     DevExtBox ext[MAX_EXT];
+    unsigned ext_touch[6];     // per plate face: bit i set when outside box i has a face in that face's plane (shares it)
     DevTable tab[MAX_TABLES];
     const float* tab_x;        // concatenated knot tables (scene spectra)
     const float* tab_y;
@@ -723,7 +724,10 @@ __device__ __forceinline__ float normal_gap(float t, int f, float dx, float dy, 
 // the plate's edge faces): its entry ties with the plate's exit
 __device__ __noinline__ int ext_touching(const DevScene& S, int face, float ox, float oy, float oz, float dx, float dy, float dz) {
     const RayInv inv = ray_inverse(dx, dy, dz);
-    for (int i = 0; i < S.n_ext; ++i) {
+    unsigned todo = S.ext_touch[face];
+    while (todo) {
+        const int i = __ffs(todo) - 1;
+        todo &= todo - 1u;
         const DevExtBox& b = S.ext[i];
         float tmin, tmax; int f, fx;
         slab_interval(b.cx, b.cy, b.cz, b.hx, b.hy, b.hz, ox, oy, oz, dx, dy, dz, inv, tmin, tmax, f, fx);
@@ -1123,7 +1127,7 @@ __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, in
     // face ties with it: when its entry sorts first it is the hit node and adjacent (tie_bits, evaluated on arrival)
     float n2 = S.med[adj].n;
     const bool leaving = flat && p.medium != MED_AIR;
-    if (EXT && leaving && kind == SURF_BOX && (tie_bits(p) & 2u)) {
+    if (EXT && leaving && kind == SURF_BOX && S.ext_touch[face] != 0u && (tie_bits(p) & 2u)) {
         const int e = ext_touching(S, face, abs_x(S, p), p.y, p.z + S.zc, p.dx, p.dy, p.dz);
         if (e >= 0) n2 = S.ext[e].n;
     }
