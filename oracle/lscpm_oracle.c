@@ -64,7 +64,6 @@ static double rng_uniform(Rng* r) { return (double)(rng_next(r) >> 11) * (1.0 / 
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
     int geom, material;
-    int depth;             /* depth in the scene graph (root = 0), pvtrace Node.depth */
     double size[3];
     double R[9], T[3];     /* local -> world rotation and translation */
 } ONode;
@@ -114,8 +113,6 @@ static int oscene_init(OScene* s, const LscpmSceneDesc* d) {
         const double* p = d->node_pose + 16 * i;
         n->geom = d->node_geom[i];
         n->material = d->node_material[i];
-        n->depth = 0;
-        for (int a = d->node_parent[i]; a >= 0; a = d->node_parent[a]) n->depth++;
         for (int k = 0; k < 3; ++k) n->size[k] = d->node_size[3 * i + k];
         for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) n->R[3 * r + c] = p[4 * r + c]; n->T[r] = p[4 * r + 3]; }
     }

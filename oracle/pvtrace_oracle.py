@@ -221,7 +221,6 @@ class _ONode:
     refractive_index: float
     components: list
     source: object = None
-    depth: int = 0  # depth of the node in the scene graph (anytree ``Node.depth``: root = 0)
 
 
 @dataclass
@@ -254,11 +253,11 @@ class OracleScene:
     def __init__(self, scene):
         self.scene = scene
         self.nodes: list[_ONode] = []
-        self._walk(scene.root, np.identity(4), 0)
+        self._walk(scene.root, np.identity(4))
         if not self.nodes or self.nodes[0].source is not scene.root:
             raise ValueError("scene root must carry the world geometry")
 
-    def _walk(self, node, parent_world, depth):
+    def _walk(self, node, parent_world):
         pose = np.asarray(getattr(node, "pose", np.identity(4)), dtype=float)
         world = parent_world @ pose
         geometry = getattr(node, "geometry", None)
@@ -278,11 +277,11 @@ class OracleScene:
                     index=len(self.nodes), name=str(node.name), kind=kind, params=params,
                     to_world=world, to_local=np.linalg.inv(world),
                     refractive_index=float(material.refractive_index),
-                    components=list(material.components), source=node, depth=depth,
+                    components=list(material.components), source=node,
                 )
             )
         for child in node.children:
-            self._walk(child, world, depth + 1)
+            self._walk(child, world)
 
     # -- intersections -------------------------------------------------------------
     def intersections(self, position, direction, rng=None):
