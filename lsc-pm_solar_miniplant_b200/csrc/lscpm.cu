@@ -19,10 +19,11 @@ using namespace lscpm;
 // =================================================================================================
 // kernels
 // =================================================================================================
-constexpr int TRACE_THREADS = 128;
-#ifndef TRACE_MIN_BLOCKS
-#define TRACE_MIN_BLOCKS 8
-#endif
+// lane kernel block sizes: one 1024-thread block per SM is 4 % faster than eight 128-thread blocks on every workload
+// measured (same registers, same occupancy; profiles/r1_ab_block_size.txt); the small block remains for scenes whose
+// per-warp tally rows would not fit 32 times into shared memory
+constexpr int TRACE_BLOCK_BIG = 1024, TRACE_BLOCK_SMALL = 128;
+constexpr size_t TRACE_SMEM_BIG_LIMIT = 96 * 1024;
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 struct TraceArgs {
@@ -66,8 +67,8 @@ __device__ __forceinline__ void flush_row(unsigned int* hist, unsigned long long
 // EXT: the scene has boxes outside the plate (photovoltaic variants); the standard scene runs an EXT = false
 // instantiation, which contains none of that code.  FLIGHT: photons in the plastic go straight to their next real event
 // (plate_flight); chosen when the plate holds a luminophore, i.e. when there is trapped light to fold.
-template <bool EXT, bool FLIGHT>
-__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS)
+template <bool EXT, bool FLIGHT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 1024 / BLOCK)
 trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceArgs A) {
     extern __shared__ unsigned int smem_rows[];
     const int lane = threadIdx.x & 31;
@@ -751,6 +752,7 @@ struct LscpmScene {
     unsigned long long* d_counters = nullptr;   // ring of work counters
     std::atomic<unsigned> next_counter{0};
     int n_sm = 0, blocks_per_sm = 0;
+    int trace_block = TRACE_BLOCK_BIG;   // threads per block of the lane kernel
     size_t trace_smem = 0;
     bool sorted = false;                 // block-sorted kernel or the lane-per-photon kernel
     bool sorted_forced = false;
@@ -1052,8 +1054,12 @@ int lower_batch(const LscpmScene* s, const LscpmBatchDesc* b, const std::vector<
 
 typedef void (*TraceKernel)(const DevScene, const TraceArgs);
 TraceKernel lane_kernel(const LscpmScene* s) {
-    if (s->dev.n_ext > 0) return trace_kernel<true, false>;
-    return s->flight ? trace_kernel<false, true> : trace_kernel<false, false>;
+    if (s->trace_block == TRACE_BLOCK_BIG) {
+        if (s->dev.n_ext > 0) return trace_kernel<true, false, TRACE_BLOCK_BIG>;
+        return s->flight ? trace_kernel<false, true, TRACE_BLOCK_BIG> : trace_kernel<false, false, TRACE_BLOCK_BIG>;
+    }
+    if (s->dev.n_ext > 0) return trace_kernel<true, false, TRACE_BLOCK_SMALL>;
+    return s->flight ? trace_kernel<false, true, TRACE_BLOCK_SMALL> : trace_kernel<false, false, TRACE_BLOCK_SMALL>;
 }
 TraceKernel sorted_kernel(const LscpmScene* s) {
     if (s->dev.n_ext > 0) return trace_sorted_kernel<true, false, SORT_THREADS>;
@@ -1259,14 +1265,17 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
 #ifdef LSCPM_DIAG
     s->dev.diag_emit = getenv("LSCPM_DIAG_EMIT") ? atoi(getenv("LSCPM_DIAG_EMIT")) : 0;
 #endif
-    s->trace_smem = (size_t)(TRACE_THREADS / 32) * (size_t)(s->dev.n_bins + LSCPM_N_COUNTERS) * sizeof(unsigned int);
+    const size_t row_bytes = (size_t)(s->dev.n_bins + LSCPM_N_COUNTERS) * sizeof(unsigned int);
+    s->trace_block = (TRACE_BLOCK_BIG / 32) * row_bytes <= TRACE_SMEM_BIG_LIMIT ? TRACE_BLOCK_BIG : TRACE_BLOCK_SMALL;
+    if (const char* b = getenv("LSCPM_TRACE_BLOCK")) s->trace_block = atoi(b) == TRACE_BLOCK_SMALL ? TRACE_BLOCK_SMALL : TRACE_BLOCK_BIG;
+    s->trace_smem = (size_t)(s->trace_block / 32) * row_bytes;
     if (s->trace_smem > 200 * 1024) return bail(fail(LSCPM_EUNSUPPORTED, "too many tally bins for the per-warp shared rows"));
     if (s->trace_smem > 48 * 1024 &&
         (e = cudaFuncSetAttribute(lane_kernel(s),
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->trace_smem)) != cudaSuccess)
         return bail(cuda_fail(e, "cudaFuncSetAttribute"));
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, lane_kernel(s),
-                                                           TRACE_THREADS, s->trace_smem)) != cudaSuccess)
+                                                           s->trace_block, s->trace_smem)) != cudaSuccess)
         return bail(cuda_fail(e, "occupancy query (is the library built for this GPU's architecture?)"));
     if (s->blocks_per_sm < 1) return bail(fail(LSCPM_ECUDA, "trace kernel does not fit on an SM"));
     // The block-sorted kernel wins where photons do very different amounts of work per iteration (scenes with outside
@@ -1386,7 +1395,7 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
     const int per_sm = sorted ? s->sort_blocks_per_sm : s->blocks_per_sm;
     const int grid = s->n_sm * per_sm;
     // work items: claimed by a block (sorted kernel) or by a warp (lane kernel); ~8 items per claimer, within a batch
-    const unsigned long long claimers = sorted ? (unsigned long long)grid : (unsigned long long)grid * (TRACE_THREADS / 32);
+    const unsigned long long claimers = sorted ? (unsigned long long)grid : (unsigned long long)grid * (unsigned long long)(s->trace_block / 32);
     const unsigned long long lo = sorted ? (unsigned long long)SORT_THREADS : 32ULL, hi = sorted ? 16384ULL : 4096ULL;
     unsigned long long chunk = total / (claimers * 8ULL);
     chunk = std::min<unsigned long long>(std::max<unsigned long long>(chunk, lo), hi);
@@ -1402,8 +1411,9 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
         const int blocks = (int)std::max<unsigned long long>(1ULL, std::min<unsigned long long>((unsigned long long)grid, want));
         sorted_kernel(s)<<<blocks, SORT_THREADS, s->sort_smem, stream>>>(s->dev, a);
     } else {
-        const int blocks = (int)std::min<unsigned long long>((unsigned long long)grid, (a.n_chunks + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32));
-        lane_kernel(s)<<<std::max(blocks, 1), TRACE_THREADS, s->trace_smem, stream>>>(s->dev, a);
+        const unsigned long long warps = (unsigned long long)(s->trace_block / 32);
+        const int blocks = (int)std::min<unsigned long long>((unsigned long long)grid, (a.n_chunks + warps - 1) / warps);
+        lane_kernel(s)<<<std::max(blocks, 1), s->trace_block, s->trace_smem, stream>>>(s->dev, a);
     }
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
