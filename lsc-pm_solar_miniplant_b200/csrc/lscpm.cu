@@ -1270,9 +1270,11 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
     if (const char* b = getenv("LSCPM_TRACE_BLOCK")) s->trace_block = atoi(b) == TRACE_BLOCK_SMALL ? TRACE_BLOCK_SMALL : TRACE_BLOCK_BIG;
     s->trace_smem = (size_t)(s->trace_block / 32) * row_bytes;
     if (s->trace_smem > 200 * 1024) return bail(fail(LSCPM_EUNSUPPORTED, "too many tally bins for the per-warp shared rows"));
+    // the opt-in limit is a property of the kernel, shared by every scene handle of the process: raise it to the most any
+    // scene may ask of this instantiation, never to one scene's own need (a later, smaller scene would lower it again)
     if (s->trace_smem > 48 * 1024 &&
-        (e = cudaFuncSetAttribute(lane_kernel(s),
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->trace_smem)) != cudaSuccess)
+        (e = cudaFuncSetAttribute(lane_kernel(s), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  s->trace_block == TRACE_BLOCK_BIG ? (int)TRACE_SMEM_BIG_LIMIT : 200 * 1024)) != cudaSuccess)
         return bail(cuda_fail(e, "cudaFuncSetAttribute"));
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s->blocks_per_sm, lane_kernel(s),
                                                            s->trace_block, s->trace_smem)) != cudaSuccess)

@@ -171,3 +171,18 @@ def test_coincident_end_caps_match_oracle(dye, side_pv, native, built_library):
     assert_tallies_agree(names, row[:nb], ref[:nb], label=f"caps dye={dye} pv={side_pv}",
                          resample=lambda: backend.trace_lights(arrays, [light], n, seed=23, device=0)[0][:nb])
     assert abs(row[nb] - ref[nb]) / ref[nb] < 0.005                       # interaction events
+
+
+def test_scenes_with_many_bins_share_the_kernel(built_library):
+    """Two live scene handles whose per-warp tally rows both need the shared-memory opt-in (> 48 KB per block) but
+    different amounts: the opt-in limit belongs to the kernel, not to a handle, so creating the smaller one must not
+    break launches of the larger one."""
+    from lscpm_b200 import backend, flatten
+
+    big = flatten.flatten_scene(standard_scene(tilt=0, elevation=80, wavelength=585.0, capillary_count=46, capillary_pitch=0.01))
+    small = flatten.flatten_scene(standard_scene(tilt=0, elevation=80, wavelength=585.0, capillary_count=40, capillary_pitch=0.0115))
+    n = 50_000
+    first = backend.trace_lights(big, [big.light], n, seed=8, device=0)[0]
+    other = backend.trace_lights(small, [small.light], n, seed=8, device=0)[0]
+    again = backend.trace_lights(big, [big.light], n, seed=8, device=0)[0]
+    assert first[:-2].sum() == n and other[:-2].sum() == n and np.array_equal(first, again)
