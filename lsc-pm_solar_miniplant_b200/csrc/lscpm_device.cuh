@@ -5,8 +5,8 @@
 // scene family reference miniplant/scene_creator.py:52-274 builds: one plate Box holding parallel,
 // equally spaced capillary Cylinders (outer tube + optional coaxial inner cylinder) whose end caps are
 // coplanar with the plate's +-y faces.  The generic algorithm (brute force over every node, container =
-// nearest node hit exactly once, adjacent = second intersection) is kept as the CPU oracle in oracle/;
-// this file reproduces its outcomes with a medium state machine:
+// nearest node hit exactly once, adjacent = hit node or container of the remaining intersections) is kept as
+// the CPU oracle in oracle/; this file reproduces its outcomes with a medium state machine:
 //
 //   AIR   -> a fresh photon sitting on the plate face it is about to enter (entry Fresnel test)
 //   PLATE -> plate faces (container==hit -> adjacent = world) or the capillary of the current cell
@@ -30,11 +30,13 @@
 //   * in the plate the photon marches cell by cell (a cell = the x-interval owned by one capillary), so each
 //     iteration tests exactly one capillary; crossing a cell boundary is a virtual, uncounted step (free paths
 //     are memoryless, so re-sampling the Beer-Lambert depth per sub-segment leaves the statistics unchanged);
+//     scenes with a luminophore in the plate go further (plate_flight): straight to the next real event through
+//     the lattice of capillary images that unfolding the total internal reflections at the z faces produces;
 //   * table lookups are O(1) through bucket indices instead of binary searches;
 //   * photon generation and luminophore re-emission share ONE "source" block at the end of the iteration (new
-//     direction + wavelength by inverse CDF + attenuation refresh), and a fresh photon's entry Fresnel test runs
-//     in the common step of the next iteration;
-//   * rare paths (sky-diffuse rejection loop, generic plate entry, irregular tables) are out of line
+//     direction + wavelength by inverse CDF + attenuation refresh); a fresh photon's entry Fresnel test is made
+//     there as well (scenes without outside boxes), with the fourth word of the generation draw;
+//   * rare paths (sky-diffuse rejection loop, generic plate entry, irregular tables, cap ties) are out of line
 //     and exchange scalars only, so the photon state never leaves registers.
 #pragma once
 #include <cuda_runtime.h>
