@@ -349,10 +349,6 @@ __device__ __forceinline__ void cylinder_roots(float a, float inv_a, float b, fl
     t_far = fmaxf(far_, 0.f);
 }
 
-// Next interface for a photon in PLATE / OUTER / INNER (pvtrace next_hit, literal outcomes); also returns the
-// virtual cell crossing (SURF_CELL) for plate flights.  One code path for all media.
-// PLATE_TOO = false: the caller never asks for a photon in the plastic (plate flights handle those), so the plate's own
-// candidates are left out.
 // pseudo-random bits that stand for float64 round-off ordering the intersections of coincident faces
 __device__ __forceinline__ unsigned tie_bits(const Photon& p) {
     unsigned h = (__float_as_uint(p.xr) * 2654435761u) ^ (__float_as_uint(p.z) * 2246822519u) ^ (__float_as_uint(p.y) * 3266489917u);
@@ -394,6 +390,11 @@ __device__ __noinline__ unsigned cap_tie(const DevScene& S, unsigned tb, bool ti
     return (unsigned)container | ((unsigned)adj << 3) | (off << 6);
 }
 
+// Next interface for a photon in PLATE / OUTER / INNER (pvtrace next_hit, literal outcomes); also returns the
+// virtual cell crossing (SURF_CELL) for plate flights.  One code path for all media.
+// PLATE_TOO = false: the caller never asks for a photon in the plastic (plate flights handle those), so the plate's own
+// candidates are left out.
+// TIES = false (probes): coincident faces in scene-graph order instead of the hashed order.
 template <bool PLATE_TOO = true, bool TIES = true>
 __device__ __forceinline__ Hit compute_hit(const DevScene& S, const Photon& p) {
     Hit h;
