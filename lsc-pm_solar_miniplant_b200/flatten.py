@@ -210,6 +210,20 @@ def _world_pose(node) -> np.ndarray:
     return m
 
 
+def _mask_matrix(position) -> np.ndarray:
+    """Mask plane -> light-node frame, 4x4, of a ``LightPosition``.
+
+    The reference's class (``miniplant/utils.py:87-99``) exposes only ``tilt_angle`` and ``__call__``; the matrix it
+    builds per photon is ``inv(R_y(-tilt))`` (``utils.py:94``), i.e. a rotation by +tilt about y.  Derived here from
+    ``tilt_angle`` so the reference's unmodified objects flatten; a ``matrix()`` method is not required."""
+    try:
+        t = np.radians(float(position.tilt_angle))
+    except (AttributeError, TypeError, ValueError) as exc:
+        raise UnsupportedSceneError(f"light position {type(position).__name__} exposes no numeric tilt_angle") from exc
+    c, s = np.cos(t), np.sin(t)
+    return np.array([[c, 0.0, s, 0.0], [0.0, 1.0, 0.0, 0.0], [-s, 0.0, c, 0.0], [0.0, 0.0, 0.0, 1.0]])
+
+
 def _wavelength_source(fn, light: LightArrays) -> None:
     """Recognise the wavelength callable: a ``PhotonFactory`` over a ``Distribution`` (tabulated
     spectrum), or a callable returning a constant; anything else is sampled on the host."""
@@ -221,21 +235,52 @@ def _wavelength_source(fn, light: LightArrays) -> None:
             raise UnsupportedSceneError("histogram spectra are not on the LSC-PM path")
         light.spectrum = np.stack([x, y], axis=1)
         return
-    # A constant callable (``lambda: 555``) gives the same value every call and draws no random numbers.
-    state = np.random.get_state()
-    try:
-        first, second, third = float(fn()), float(fn()), float(fn())
-        untouched = all(np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b
-                        for a, b in zip(state, np.random.get_state()))
-    finally:
-        np.random.set_state(state)
-    if first == second == third and untouched:
-        light.wavelength_nm = first
+    # Only provably constant sources go to the device: plain numbers and functions whose bytecode is nothing
+    # but "return <literal or variable>" (the reference's default ``lambda: 555``, simulation_runner.py:87,111).  Any
+    # other callable may draw from a generator this module cannot see, so it is sampled on the host by the
+    # scene's own ``emit`` — never called here (no side effects, no guessing from a few samples).
+    constant = _constant_value(fn)
+    if constant is not None:
+        light.wavelength_nm = constant
     else:
         light.wavelength_callable = fn
 
 
+# Opcodes of a function body that is exactly ``return <literal | closure variable | global>``: no call, no
+# attribute access, no arithmetic — evaluating it once has no side effects and consumes no random numbers.
+_CONSTANT_OPS = frozenset({"RESUME", "LOAD_CONST", "RETURN_VALUE", "RETURN_CONST", "NOP", "CACHE", "COPY_FREE_VARS",
+                           "LOAD_DEREF", "LOAD_GLOBAL", "PUSH_NULL"})
+
+
+def _constant_value(fn) -> Optional[float]:
+    if isinstance(fn, (int, float, np.integer, np.floating)) and not isinstance(fn, bool):
+        return float(fn)
+    if "ConstantWavelength" in _mro_names(fn):  # workloads.ConstantWavelength declares itself constant
+        return float(fn.nm)
+    code = getattr(fn, "__code__", None)
+    if code is None or code.co_argcount or code.co_kwonlyargcount:
+        return None
+    import dis
+
+    if any(ins.opname not in _CONSTANT_OPS for ins in dis.get_instructions(code)):
+        return None
+    value = fn()
+    if isinstance(value, (int, float, np.integer, np.floating)) and not isinstance(value, bool):
+        return float(value)
+    return None
+
+
 def flatten_light(scene) -> LightArrays:
+    """Light node -> ``LightArrays``.  Anything that is not one of the reference's two light constructions raises
+    ``UnsupportedSceneError`` (also for objects that miss an expected attribute), which ``backend.simulate_scene``
+    answers by emitting on the host through the scene's own ``emit``."""
+    try:
+        return _flatten_light(scene)
+    except (AttributeError, TypeError, IndexError) as exc:
+        raise UnsupportedSceneError(f"unrecognised light: {exc}") from exc
+
+
+def _flatten_light(scene) -> LightArrays:
     lights = scene.light_nodes
     if len(lights) != 1:
         raise UnsupportedSceneError(f"the LSC-PM path expects exactly one light node, found {len(lights)}")
@@ -248,7 +293,7 @@ def flatten_light(scene) -> LightArrays:
 
     if joint is not None and "IsotropicPhotonGenerator" in _mro_names(joint):
         base = joint.base_position_generator
-        mask = world @ np.asarray(base.matrix(), dtype=np.float64)
+        mask = world @ _mask_matrix(base)
         light = LightArrays(kind=LIGHT_DIFFUSE, mask_half=np.array([0.47 / 2, 0.47 / 2]), mask_pose=mask[:3, :],
                             direction=np.zeros(3), back_off=1.0, tilt_deg=float(joint.tilt_angle))
         if not np.allclose(world[:3, :3], np.identity(3)):
@@ -260,7 +305,7 @@ def flatten_light(scene) -> LightArrays:
         norm = float(np.linalg.norm(d_world))
         if not np.isclose(norm, 1.0, atol=1e-9):
             raise UnsupportedSceneError("the beam direction must be a unit vector")
-        mask = world @ np.asarray(position.matrix(), dtype=np.float64)
+        mask = world @ _mask_matrix(position)
         # The light node is translated up-beam (scene_creator.py:304): express that as a back-off
         # along the ray so that the anchor points stay on the plate face.
         shift = world[:3, 3]
