@@ -37,6 +37,7 @@ struct TraceArgs {
     unsigned long long n_chunks;
     unsigned int chunk;                  // photons per work item
     uint2 key;
+    RoundKeys rk;                        // Philox round keys of `key` (constant-bank operands of the trace kernels)
     unsigned long long* work_counter;
     unsigned long long* tallies;         // [n_batches][n_bins + LSCPM_N_COUNTERS]
 };
@@ -57,6 +58,7 @@ __device__ __forceinline__ bool counts_as_event(int ev) {
 // memory directly.  Without this the per-batch counters serialise in L2 (one hot address per batch).
 __device__ __forceinline__ void flush_row(unsigned int* hist, unsigned long long* row, int stride, int lane) {
     __syncwarp();
+#pragma unroll 1
     for (int b = lane; b < stride; b += 32) {
         const unsigned int v = hist[b];
         if (v) { atomicAdd(row + b, (unsigned long long)v); hist[b] = 0u; }
@@ -95,7 +97,7 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
         // ---- step every live photon ---------------------------------------------------------------
         int status = -1;
         if (alive) {
-            const uint4 w = rng.next();
+            const uint4 w = rng.next(A.rk);
             StepOut so;
             status = photon_step<EXT, FLIGHT>(S, p, w, so);
             n_events += (unsigned)so.extra + (counts_as_event(so.event) ? 1u : 0u);
@@ -152,7 +154,7 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
         }
         // ---- source block: new photons and re-emissions ---------------------------------------------
         if (fresh || status == STEP_EMIT) {
-            const uint4 v = rng.next();
+            const uint4 v = rng.next(A.rk);
             WavelengthDraw wd;
             int bin = -1;
             if (fresh) {
@@ -415,7 +417,7 @@ trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ 
         // ---- source: a new photon or a re-emission --------------------------------------------------------
         if (source) {
             rng.batch = A.batches[batch].batch_id;
-            const uint4 v = rng.next();
+            const uint4 v = rng.next(A.rk);
             WavelengthDraw wd;
             if (fresh) bin = source_fresh<EXT, true>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr, n_events);
             else source_emit(S, v, p, wd);
@@ -429,7 +431,7 @@ trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ 
         // ---- common half of the next iteration ---------------------------------------------------------
         if (fly) {
             rng.batch = A.batches[batch].batch_id;
-            const uint4 w = rng.next();
+            const uint4 w = rng.next(A.rk);
             u_surf = u01(w.y); w_z = w.z;
             bin = advance<EXT, FLIGHT>(S, p, w.x, pend, n_events);
         }
@@ -451,6 +453,10 @@ trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ 
     }
 #endif
 }
+
+// K2p: warp-private photon pools, phase-major execution (lscpm_pool.cuh)
+#define LSCPM_POOL_KERNEL_BODY
+#include "lscpm_pool.cuh"
 
 // K1 (debug/emit): the rays a batch generates, in plate-local coordinates
 __global__ void emit_kernel(const __grid_constant__ DevScene S, const DevBatch* batch, const float* spec_x,
@@ -759,6 +765,8 @@ struct LscpmScene {
     bool flight = false;                 // plate flights (scenes without outside boxes whose plate holds a luminophore)
     int sort_blocks_per_sm = 0;
     size_t sort_smem = 0;
+    int pool = 0;                        // pool kernel configuration: 0 off, 1 = 24 warps x 96 records, 2 = 32 warps x 64 records
+    size_t pool_smem = 0;
 };
 constexpr int COUNTER_RING = 256;
 
@@ -1066,6 +1074,14 @@ TraceKernel sorted_kernel(const LscpmScene* s) {
     return s->flight ? trace_sorted_kernel<false, true, SORT_THREADS> : trace_sorted_kernel<false, false, SORT_THREADS>;
 }
 
+constexpr int POOL_A_WARPS = 24, POOL_A_SLOTS = 96, POOL_B_WARPS = 32, POOL_B_SLOTS = 64;
+int pool_warps(const LscpmScene* s) { return s->pool == 2 ? POOL_B_WARPS : POOL_A_WARPS; }
+int pool_slots(const LscpmScene* s) { return s->pool == 2 ? POOL_B_SLOTS : POOL_A_SLOTS; }
+TraceKernel pool_kernel(const LscpmScene* s) {
+    if (s->pool == 2) return s->flight ? trace_pool_kernel<true, POOL_B_WARPS, POOL_B_SLOTS> : trace_pool_kernel<false, POOL_B_WARPS, POOL_B_SLOTS>;
+    return s->flight ? trace_pool_kernel<true, POOL_A_WARPS, POOL_A_SLOTS> : trace_pool_kernel<false, POOL_A_WARPS, POOL_A_SLOTS>;
+}
+
 int pick_counter(LscpmScene* s, cudaStream_t stream, unsigned long long** out) {
     const unsigned slot = s->next_counter.fetch_add(1) % COUNTER_RING;
     *out = s->d_counters + slot;
@@ -1297,6 +1313,30 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
             return bail(cuda_fail(e, "occupancy query (sorted kernel)"));
         if (s->sort_blocks_per_sm < 1) return bail(fail(LSCPM_ECUDA, "sorted trace kernel does not fit on an SM"));
     }
+    // The pool kernel (warp-private photon pools, lscpm_pool.cuh) is the default for scenes without outside boxes whose
+    // plate re-emits: that is where photons live long enough for the phase lists to stay full.
+    // LSCPM_TRACE_KERNEL=pool|pool96|pool64 forces it (bit-identical tallies in every configuration).
+    s->pool = 0;
+    if (s->dev.n_ext == 0) {
+        if (s->flight) s->pool = 1;
+        if (which && (strcmp(which, "lanes") == 0 || strcmp(which, "sorted") == 0)) s->pool = 0;
+        if (which && (strcmp(which, "pool") == 0 || strcmp(which, "pool96") == 0)) s->pool = 1;
+        if (which && strcmp(which, "pool64") == 0) s->pool = 2;
+    }
+    if (s->pool) {
+        const int stride = s->dev.n_bins + LSCPM_N_COUNTERS;
+        s->pool_smem = pool_smem_bytes(pool_warps(s), pool_slots(s), stride);
+        if (s->pool_smem > (size_t)prop.sharedMemPerBlockOptin) s->pool = 0;    // too many tally bins for the per-warp rows: lane kernel
+    }
+    if (s->pool) {
+        if ((e = cudaFuncSetAttribute(pool_kernel(s), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) != cudaSuccess)
+            return bail(cuda_fail(e, "cudaFuncSetAttribute (pool kernel)"));
+        int fit = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, pool_kernel(s), pool_warps(s) * 32, s->pool_smem)) != cudaSuccess)
+            return bail(cuda_fail(e, "occupancy query (pool kernel)"));
+        if (fit < 1) s->pool = 0;
+        else s->sorted = false;
+    }
     *out = s;
     return LSCPM_OK;
 }
@@ -1390,14 +1430,17 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
     a.batches = p->d_batches; a.spec_x = p->d_spec_x; a.spec_cdf = p->d_spec_cdf; a.spec_guide = p->d_spec_guide;
     a.photon_begin = photon_begin; a.photon_count = photon_count;
     a.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    a.rk = philox_round_keys(a.key);
     a.tallies = (unsigned long long*)tallies_dev;
     const unsigned long long total = photon_count * (unsigned long long)p->n_batches;
     // launches too small to fill the sorted kernel's blocks a few times over go to the lane kernel
     const bool sorted = s->sorted && (s->sorted_forced || total >= 4ULL * (unsigned long long)(s->n_sm * s->sort_blocks_per_sm) * SORT_THREADS);
-    const int per_sm = sorted ? s->sort_blocks_per_sm : s->blocks_per_sm;
+    const bool pool = !sorted && s->pool != 0;
+    const int per_sm = sorted ? s->sort_blocks_per_sm : (pool ? 1 : s->blocks_per_sm);
     const int grid = s->n_sm * per_sm;
-    // work items: claimed by a block (sorted kernel) or by a warp (lane kernel); ~8 items per claimer, within a batch
-    const unsigned long long claimers = sorted ? (unsigned long long)grid : (unsigned long long)grid * (unsigned long long)(s->trace_block / 32);
+    const int lane_warps = pool ? pool_warps(s) : s->trace_block / 32;
+    // work items: claimed by a block (sorted kernel) or by a warp (lane / pool kernel); ~8 items per claimer, within a batch
+    const unsigned long long claimers = sorted ? (unsigned long long)grid : (unsigned long long)grid * (unsigned long long)lane_warps;
     const unsigned long long lo = sorted ? (unsigned long long)SORT_THREADS : 32ULL, hi = sorted ? 16384ULL : 4096ULL;
     unsigned long long chunk = total / (claimers * 8ULL);
     chunk = std::min<unsigned long long>(std::max<unsigned long long>(chunk, lo), hi);
@@ -1413,9 +1456,10 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
         const int blocks = (int)std::max<unsigned long long>(1ULL, std::min<unsigned long long>((unsigned long long)grid, want));
         sorted_kernel(s)<<<blocks, SORT_THREADS, s->sort_smem, stream>>>(s->dev, a);
     } else {
-        const unsigned long long warps = (unsigned long long)(s->trace_block / 32);
+        const unsigned long long warps = (unsigned long long)lane_warps;
         const int blocks = (int)std::min<unsigned long long>((unsigned long long)grid, (a.n_chunks + warps - 1) / warps);
-        lane_kernel(s)<<<std::max(blocks, 1), s->trace_block, s->trace_smem, stream>>>(s->dev, a);
+        if (pool) pool_kernel(s)<<<std::max(blocks, 1), lane_warps * 32, s->pool_smem, stream>>>(s->dev, a);
+        else lane_kernel(s)<<<std::max(blocks, 1), s->trace_block, s->trace_smem, stream>>>(s->dev, a);
     }
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());

@@ -208,11 +208,35 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
+// The ten round keys (key + round * Weyl constants) are the same for every call of a launch: the host computes them once
+// and the trace kernels read them from the kernel-parameter constant bank as immediate operands of the XORs, instead of
+// bumping two key registers per round and lane (2 of the ~7 instructions of a round).  Same function, same bits.
+struct RoundKeys { uint2 k[10]; };
+__host__ __device__ __forceinline__ RoundKeys philox_round_keys(uint2 key) {
+    RoundKeys r;
+    for (int round = 0; round < 10; ++round) {
+        r.k[round] = key;
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return r;
+}
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint4 c, const RoundKeys& R) {
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = mulhi32(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = mulhi32(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ R.k[round].x, lo1, hi0 ^ c.w ^ R.k[round].y, lo0);
+    }
+    return c;
+}
+
 struct Rng {
     uint2 key;
     uint32_t p_lo, p_hi, batch;
     uint32_t calls;
     __device__ __forceinline__ uint4 next() { return philox4x32_10(make_uint4(p_lo, p_hi, batch, calls++), key); }
+    __device__ __forceinline__ uint4 next(const RoundKeys& R) { return philox4x32_10_rk(make_uint4(p_lo, p_hi, batch, calls++), R); }
 };
 
 // 24-bit uniforms: u in [0,1) and its complement 1-u in (0,1], both exact in FP32
@@ -680,8 +704,11 @@ __device__ __forceinline__ void source_emit(const DevScene& S, const uint4 v, Ph
     p.aux = (p.aux & 0xffff) | 256;     // has emitted
 }
 
-__device__ __forceinline__ void source_finish(const DevScene& S, Photon& p, const WavelengthDraw& wd) {
+__device__ __forceinline__ void source_wavelength(Photon& p, const WavelengthDraw& wd) {
     p.wl = wd.n == 0 ? wd.constant : inverse_cdf(wd.u, wd.cdf, wd.xs, wd.n, wd.guide, wd.buckets);
+}
+__device__ __forceinline__ void source_finish(const DevScene& S, Photon& p, const WavelengthDraw& wd) {
+    source_wavelength(p, wd);
     refresh_alphas(S, p);
 }
 
@@ -1029,12 +1056,15 @@ __device__ __forceinline__ void plate_flight(const DevScene& S, Photon& p, const
 // BRANCH_ENTRY: skip the geometry for a photon still waiting for its entry Fresnel test (pays when whole warps are in
 // that state - the sorted kernel; the lane kernel computes and overrides, which costs no branch).
 // FLIGHT: plate flights (scenes without outside boxes); FOLD: fold total internal reflections into them.
-template <bool BRANCH_ENTRY, bool FLIGHT, bool FOLD>
-__device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const uint32_t w_x, Hit& h, int& cls, int& extra) {
+// LAZY (pool kernel): the photon record carries no attenuation coefficients; the container's is looked up from the
+// wavelength here (same function, same value as refresh_alphas stored) and handed back in `alpha` for the absorption.
+template <bool BRANCH_ENTRY, bool FLIGHT, bool FOLD, bool LAZY = false>
+__device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const uint32_t w_x, Hit& h, int& cls, int& extra, float& alpha_out) {
     extra = 0;
     cls = CLS_CELL;
     if (FLIGHT && p.medium == MED_PLATE) {
-        const float alpha = p.a_plate;
+        const float alpha = LAZY ? medium_alpha(S, MED_PLATE, p.wl) : p.a_plate;
+        alpha_out = alpha;
         const float depth = alpha <= ALPHA_ZERO ? LSCPM_INF : __fmul_rn(-flog(one_minus_u01(w_x)), frcp(alpha));
         int bounces;
         plate_flight<FOLD>(S, p, depth, h, cls, bounces);
@@ -1054,9 +1084,14 @@ __device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const u
     if (p.steps > MAXSTEPS) return BIN_KILL;
     // branch-free select of the container's attenuation (the compiler turned the ternary chain into a jump table)
     float alpha = 0.f;
-    alpha = h.container == MED_PLATE ? p.a_plate : alpha;
-    alpha = h.container == MED_OUTER ? p.a_outer : alpha;
-    alpha = h.container == MED_INNER ? p.a_inner : alpha;
+    if (LAZY) {
+        if (h.container == MED_PLATE || h.container == MED_OUTER || h.container == MED_INNER) alpha = medium_alpha(S, h.container, p.wl);
+    } else {
+        alpha = h.container == MED_PLATE ? p.a_plate : alpha;
+        alpha = h.container == MED_OUTER ? p.a_outer : alpha;
+        alpha = h.container == MED_INNER ? p.a_inner : alpha;
+    }
+    alpha_out = alpha;
     const float depth = alpha <= ALPHA_ZERO ? LSCPM_INF : fdiv(-flog(one_minus_u01(w_x)), alpha);
     const bool absorbed = depth < h.t;
     const float travel = absorbed ? depth : h.t;
@@ -1070,6 +1105,12 @@ __device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const u
         p.xr = h.face > 0 ? -0.5f * S.pitch : 0.5f * S.pitch;
     }
     return -1;
+}
+
+template <bool BRANCH_ENTRY, bool FLIGHT, bool FOLD>
+__device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const uint32_t w_x, Hit& h, int& cls, int& extra) {
+    float alpha;
+    return advance_hit<BRANCH_ENTRY, FLIGHT, FOLD, false>(S, p, w_x, h, cls, extra, alpha);
 }
 
 // the sorted kernel's form: the result packed into the pending word that travels with the photon record
@@ -1086,11 +1127,16 @@ __device__ __forceinline__ int advance(const DevScene& S, Photon& p, const uint3
 
 // absorbed inside the container: choose the component ~ alpha_i, radiative test.  Returns the tally bin, or -1 with
 // p.aux carrying the emission table when the luminophore re-emits.
+__device__ __forceinline__ int interact_absorb_alpha(const DevScene& S, Photon& p, int container, float alpha, float u_pick, uint32_t w_z, int& event);
 __device__ __forceinline__ int interact_absorb(const DevScene& S, Photon& p, int container, float u_pick, uint32_t w_z, int& event) {
     float alpha = 0.f;
     alpha = container == MED_PLATE ? p.a_plate : alpha;
     alpha = container == MED_OUTER ? p.a_outer : alpha;
     alpha = container == MED_INNER ? p.a_inner : alpha;
+    return interact_absorb_alpha(S, p, container, alpha, u_pick, w_z, event);
+}
+// the same with the container's attenuation coefficient handed in (pool kernel: advance_hit has just looked it up)
+__device__ __forceinline__ int interact_absorb_alpha(const DevScene& S, Photon& p, int container, float alpha, float u_pick, uint32_t w_z, int& event) {
     const DevMedium& m = S.med[container];
     const int index = pick_component(S, container, p.wl, alpha, u_pick * alpha);
     const DevComponent& comp = m.comp[index];

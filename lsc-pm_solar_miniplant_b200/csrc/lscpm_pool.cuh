@@ -1,0 +1,283 @@
+// lscpm_pool.cuh — K2p: the persistent photon kernel with a warp-private photon pool (phase-major execution).
+//
+// Why (profiles/r1_final_*): the lane-per-photon kernel K2 issues 84 % of its warp slots but only 14.7 of the
+// 32 lanes of an issued instruction do work, because the 32 photons of a warp want different things at every point of an
+// iteration (plate flight | tube geometry, then Fresnel | absorption, then generation | re-emission) and the warp runs all
+// of them one after the other.  A Markov model of the photon's phases reproduces that figure for 32 photons per warp (14.4)
+// and says what changes it: MORE PHOTONS THAN LANES per scheduling unit — 64 per warp give 26 lanes, 96 give 31.
+//
+// So a warp owns NSLOT (96) photon records in shared memory instead of 32 in registers.  Every record waits in exactly one
+// phase list; a warp iteration picks the fullest list, pops up to 32 records of it, runs THAT phase's code for them (all
+// lanes in the same code), stores what the phase changed and pushes each record onto the list of its next phase.  No
+// barrier, no atomics on the lists (one warp, warp-uniform counters), no hand-over between warps: what made the block-level
+// regrouping experiments of round 1 lose (K2s: the block waits for its slowest warp; page queues: queue management cost as
+// much as the photon work) does not exist here.  Cost: four 16-byte shared-memory loads / two or three stores per phase
+// execution and ~50 instructions of list bookkeeping (packed counters, one MATCH + two REDUX per push).
+//
+// What the first version's profile asked for (profiles/r2_pool_v1_*): it executed 25 % fewer warp instructions than K2 at
+// 25.0 active lanes but issued only 59 % of its slots - 18 % of the stall samples were instruction-cache misses (52 KB of
+// SASS against a 32 KB L1.5; warps in different phases fetch different code), 17 % waits on global loads (219 KB of
+// shared memory left 28 KB of L1 for the spectra, hit rate 83 %).  Hence the 64-byte record (the attenuation
+// coefficients are looked up from the wavelength when a flight needs them instead of travelling), at most 196 KB of
+// shared memory, and compact bookkeeping.
+//
+//   PH_FRESH  empty record: takes the next photon index of the warp's work item, generation draw, entry Fresnel test
+//   PH_PLATE  photon in the plastic (scenes with plate flights): step draw + plate_flight [+ absorption]
+//   PH_TUBE   photon in a tube wall / the mixture (every medium when the scene has no plate flights): step draw +
+//             compute_hit + free path + move [+ absorption]
+//   PH_SURF   photon on an interface: Fresnel test
+//   PH_EMIT   photon absorbed by the luminophore, to be re-emitted: emission draw
+//
+// The phase code is the very device code of K2 / K2s (advance_hit, interact_*, source_*) fed with the same Philox words in
+// the same order, so the tallies are bit-identical to K2's for every scene, batch shape and photon offset
+// (tests/test_gpu_sorted_kernel.py covers all three kernels).  Scenes with outside boxes stay on K2s / K2.
+#pragma once
+#include "lscpm_device.cuh"
+
+namespace lscpm {
+
+constexpr int PH_FRESH = 0, PH_PLATE = 1, PH_TUBE = 2, PH_SURF = 3, PH_EMIT = 4, N_PH = 5;
+
+// record = 4 x uint4 (SoA over the slots of a warp):
+//   G0: xr, y, z, kc | medium << 12 | steps << 16
+//   G1: dx, dy, dz, wl
+//   G2: photon index lo, hi, batch (index into the plan), batch id (Philox counter word)
+//   G3: event counters, pending interaction (PH_SURF) / emission table (PH_EMIT), raw Philox word for the pending
+//       interaction, Philox call counter
+constexpr int POOL_GROUPS = 4;
+
+__host__ __device__ constexpr int pool_list_u4(int nslot) { return (N_PH * nslot + 15) / 16; }
+__host__ __device__ constexpr size_t pool_smem_bytes(int warps, int nslot, int stride) {
+    return (size_t)warps * (size_t)(POOL_GROUPS * nslot + pool_list_u4(nslot) + (stride + 3) / 4) * 16u;
+}
+
+template <bool FLIGHT>
+__device__ __forceinline__ int fly_phase(int medium) { return (FLIGHT && medium == MED_PLATE) ? PH_PLATE : PH_TUBE; }
+
+// List lengths, warp-uniform, packed: phases 0..3 in the bytes of `a`, phase 4 in `b` (NSLOT <= 255).
+struct PoolCounts {
+    unsigned a, b;
+    __device__ __forceinline__ int get(int ph) const { return ph < 4 ? (int)((a >> (8 * ph)) & 0xffu) : (int)b; }
+};
+
+// Push the records the active lanes hold onto the lists of their next phases: lanes with the same target find each other
+// with one MATCH, rank themselves inside the group, and the group leaders' sizes are summed into the packed counters
+// with two REDUX - independent of how many different targets there are.
+template <int NSLOT>
+__device__ __forceinline__ void pool_push(unsigned char* __restrict__ lists, PoolCounts& cnt, bool act, int nph, int slot, unsigned lane_lt) {
+    const int key = act ? nph : 7;                       // idle lanes form a group of their own that is not counted
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    const int rank = __popc(grp & lane_lt);
+    if (act) lists[nph * NSLOT + cnt.get(nph) + rank] = (unsigned char)slot;
+    const unsigned size = (act && rank == 0) ? (unsigned)__popc(grp) : 0u;
+    cnt.a += __reduce_add_sync(0xffffffffu, nph < 4 ? size << (8 * (nph & 3)) : 0u);
+    cnt.b += __reduce_add_sync(0xffffffffu, nph == 4 ? size : 0u);
+}
+
+__device__ __noinline__ void pool_tally(unsigned long long* __restrict__ tallies, unsigned int* hist, int n_bins, int stride,
+                                        int hbatch, int batch, int bin, unsigned n_events) {
+    LSCPM_CHECK(bin >= 0 && bin < n_bins);
+    if (batch == hbatch) {
+        atomicAdd(hist + bin, 1u);
+        if (n_events & 0xffffu) atomicAdd(hist + n_bins, n_events & 0xffffu);
+        if (n_events >> 16) atomicAdd(hist + n_bins + 1, n_events >> 16);
+    } else {   // straggler of a batch the warp has moved on from
+        unsigned long long* row = tallies + (size_t)batch * stride;
+        atomicAdd(row + bin, 1ULL);
+        if (n_events & 0xffffu) atomicAdd(row + n_bins, (unsigned long long)(n_events & 0xffffu));
+        if (n_events >> 16) atomicAdd(row + n_bins + 1, (unsigned long long)(n_events >> 16));
+    }
+}
+
+}  // namespace lscpm
+
+// The kernel itself is compiled inside lscpm.cu, after TraceArgs / flush_row (this header is not stand-alone).
+#ifdef LSCPM_POOL_KERNEL_BODY
+
+template <bool FLIGHT, int WARPS, int NSLOT>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_constant__ TraceArgs A) {
+    using namespace lscpm;
+    static_assert(NSLOT % 16 == 0 && NSLOT <= 255, "slot numbers and list lengths travel as bytes");
+    extern __shared__ uint4 pool_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lane_lt = (1u << lane) - 1u;
+    const int stride = S.n_bins + LSCPM_N_COUNTERS;
+    const int per_warp = POOL_GROUPS * NSLOT + pool_list_u4(NSLOT) + (stride + 3) / 4;
+    uint4* G = pool_smem + (size_t)warp * per_warp;
+    unsigned char* lists = reinterpret_cast<unsigned char*>(G + POOL_GROUPS * NSLOT);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(G + POOL_GROUPS * NSLOT + pool_list_u4(NSLOT));
+    for (int b = lane; b < stride; b += 32) hist[b] = 0u;
+    for (int i = lane; i < NSLOT; i += 32) lists[PH_FRESH * NSLOT + i] = (unsigned char)i;
+    __syncwarp();
+
+    PoolCounts cnt;
+    cnt.a = (unsigned)NSLOT; cnt.b = 0u;    // every record starts empty
+    int hbatch = -1;                        // batch whose photons the shared row accumulates
+    unsigned long long chunk_base = 0;      // work item: photons chunk_base + [c_next, c_end) of batch `cbatch` are unclaimed
+    unsigned c_next = 0, c_end = 0;
+    int cbatch = 0;
+    bool more = true;
+    unsigned items_since_flush = 0;
+
+    for (;;) {
+        // ---- the fullest list whose phase can run: max over (length << 3 | phase) ---------------------------------
+        const unsigned fresh_len = (c_next < c_end || more) ? (cnt.a & 0xffu) : 0u;
+        unsigned key = fresh_len << 3;
+        key = max(key, (((cnt.a >> 8) & 0xffu) << 3) | 1u);
+        key = max(key, (((cnt.a >> 16) & 0xffu) << 3) | 2u);
+        key = max(key, ((cnt.a >> 24) << 3) | 3u);
+        key = max(key, (cnt.b << 3) | 4u);
+        const int best = (int)(key >> 3);
+        if (best == 0) break;
+        const int ph = (int)(key & 7u);
+
+        if (ph == PH_FRESH && c_next >= c_end) {   // claim the next work item
+            unsigned long long id = 0;
+            if (lane == 0) id = atomicAdd(A.work_counter, 1ULL);
+            id = __shfl_sync(FULL_MASK, id, 0);
+            if (id >= A.n_chunks) { more = false; continue; }
+            cbatch = (int)(id / A.chunks_per_batch);
+            const unsigned long long first = (id % A.chunks_per_batch) * (unsigned long long)A.chunk;
+            chunk_base = A.photon_begin + first;
+            c_next = 0;
+            c_end = (unsigned)min((unsigned long long)A.chunk, A.photon_count - first);
+            // the 32-bit shared row is flushed when the batch changes and, within one batch, often enough not to wrap
+            if (cbatch != hbatch || ++items_since_flush >= 256u) {
+                if (hbatch >= 0) flush_row(hist, A.tallies + (size_t)hbatch * stride, stride, lane);
+                hbatch = cbatch;
+                items_since_flush = 0;
+            }
+        }
+
+        // ---- pop up to 32 records of that list ---------------------------------------------------------------
+        int have = best;
+        if (ph == PH_FRESH) have = min(have, (int)(c_end - c_next));
+        const int n = min(32, have);
+        const bool act = lane < n;
+        int slot = 0;
+        if (act) slot = lists[ph * NSLOT + best - n + lane];
+        LSCPM_CHECK(slot >= 0 && slot < NSLOT);
+        if (ph < 4) cnt.a -= (unsigned)n << (8 * ph); else cnt.b -= (unsigned)n;
+        int nph = PH_FRESH;
+
+        if (ph == PH_PLATE || ph == PH_TUBE) {
+            // ---- step draw, nearest interface, free path, move; absorption is settled here as well ---------------
+            if (act) {
+                const uint4 g0 = G[0 * NSLOT + slot], g1 = G[1 * NSLOT + slot], g2 = G[2 * NSLOT + slot];
+                uint4 g3 = G[3 * NSLOT + slot];
+                Photon p;
+                p.xr = __uint_as_float(g0.x); p.y = __uint_as_float(g0.y); p.z = __uint_as_float(g0.z);
+                p.kc = g0.w & 0xfff; p.medium = (g0.w >> 12) & 15; p.steps = g0.w >> 16;
+                p.dx = __uint_as_float(g1.x); p.dy = __uint_as_float(g1.y); p.dz = __uint_as_float(g1.z); p.wl = __uint_as_float(g1.w);
+                p.a_plate = p.a_outer = p.a_inner = 0.f; p.aux = 0;
+                Rng rng; rng.key = A.key; rng.p_lo = g2.x; rng.p_hi = g2.y; rng.batch = g2.w; rng.calls = g3.w;
+                unsigned n_events = g3.x;
+                const uint4 w = rng.next(A.rk);
+                Hit h; int cls, extra; float alpha;
+                int bin = advance_hit<true, FLIGHT, true, true>(S, p, w.x, h, cls, extra, alpha);
+                n_events += (unsigned)extra;
+                unsigned pend = 0u;
+                if (bin < 0) {
+                    if (cls == CLS_ABSORB) {
+                        n_events += 1u;
+                        int ev;
+                        bin = interact_absorb_alpha(S, p, h.container, alpha, u01(w.y), w.z, ev);
+                        if (bin < 0) {   // re-emitted by the luminophore: the emission table travels in the pending word
+                            n_events += 0x10000u;
+                            nph = PH_EMIT;
+                            pend = (unsigned)(p.aux >> 16) & 0xffu;
+                        }
+                    } else if (cls == CLS_CELL) {
+                        nph = fly_phase<FLIGHT>(p.medium);
+                    } else {
+                        nph = PH_SURF;
+                        pend = pack_pending(cls, h.kind, h.face, h.container, h.adj);
+                    }
+                }
+                if (bin >= 0) {
+                    pool_tally(A.tallies, hist, S.n_bins, stride, hbatch, (int)g2.z, bin, n_events);
+                } else {
+                    G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
+                                                     (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
+                    if (FLIGHT) G[1 * NSLOT + slot].z = __float_as_uint(p.dz);    // a folded flight may end on a mirrored leg
+                    g3.x = n_events; g3.y = pend; g3.z = w.y; g3.w = rng.calls;
+                    G[3 * NSLOT + slot] = g3;
+                }
+            }
+        } else if (ph == PH_SURF) {
+            // ---- Fresnel test on the interface the photon was moved to -----------------------------------------
+            if (act) {
+                const uint4 g0 = G[0 * NSLOT + slot], g1 = G[1 * NSLOT + slot], g3 = G[3 * NSLOT + slot];
+                Photon p;
+                p.xr = __uint_as_float(g0.x); p.y = __uint_as_float(g0.y); p.z = __uint_as_float(g0.z);
+                p.kc = g0.w & 0xfff; p.medium = (g0.w >> 12) & 15; p.steps = g0.w >> 16;
+                p.dx = __uint_as_float(g1.x); p.dy = __uint_as_float(g1.y); p.dz = __uint_as_float(g1.z);
+                p.wl = 0.f; p.a_plate = p.a_outer = p.a_inner = 0.f; p.aux = 0;
+                const unsigned n_events = g3.x + 1u;
+                int ev;
+                const int bin = interact_surface<false>(S, p, pending_kind(g3.y), pending_face(g3.y), pending_container(g3.y),
+                                                        pending_adj(g3.y), u01(g3.z), ev);
+                if (bin >= 0) {
+                    pool_tally(A.tallies, hist, S.n_bins, stride, hbatch, (int)G[2 * NSLOT + slot].z, bin, n_events);
+                } else {
+                    nph = fly_phase<FLIGHT>(p.medium);
+                    G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
+                                                     (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
+                    G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), g1.w);
+                    G[3 * NSLOT + slot].x = n_events;
+                }
+            }
+        } else {
+            // ---- source: a new photon (PH_FRESH) or a re-emission (PH_EMIT) -------------------------------------
+            const bool fresh = ph == PH_FRESH;
+            if (act) {
+                Photon p;
+                p.a_plate = p.a_outer = p.a_inner = 0.f;
+                Rng rng; rng.key = A.key;
+                int batch;
+                unsigned n_events = 0;
+                unsigned packed = 0u;
+                if (fresh) {
+                    const unsigned long long g = chunk_base + c_next + (unsigned)lane;
+                    batch = cbatch;
+                    rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32); rng.batch = A.batches[batch].batch_id; rng.calls = 0;
+                    p.xr = p.y = p.z = p.wl = 0.f; p.kc = p.medium = p.steps = p.aux = 0;
+                } else {
+                    const uint4 g2 = G[2 * NSLOT + slot], g3 = G[3 * NSLOT + slot];
+                    packed = G[0 * NSLOT + slot].w;
+                    p.medium = (packed >> 12) & 15;
+                    p.wl = __uint_as_float(G[1 * NSLOT + slot].w);
+                    p.aux = (int)(g3.y << 16);
+                    rng.p_lo = g2.x; rng.p_hi = g2.y; batch = (int)g2.z; rng.batch = g2.w; rng.calls = g3.w;
+                }
+                const uint4 v = rng.next(A.rk);
+                WavelengthDraw wd;
+                int bin = -1;
+                if (fresh) bin = source_fresh<false, true>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr, n_events);
+                else source_emit(S, v, p, wd);
+                source_wavelength(p, wd);
+                if (bin >= 0) {   // reflected off the plate at first contact, or never touched it: the record stays empty
+                    pool_tally(A.tallies, hist, S.n_bins, stride, hbatch, batch, bin, n_events);
+                } else {
+                    nph = fly_phase<FLIGHT>(p.medium);
+                    if (fresh) {
+                        G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
+                                                         (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
+                        G[2 * NSLOT + slot] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.batch);
+                        G[3 * NSLOT + slot] = make_uint4(n_events, 0u, 0u, rng.calls);
+                    } else {
+                        G[3 * NSLOT + slot].w = rng.calls;
+                    }
+                    G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl));
+                }
+            }
+            if (fresh) c_next += (unsigned)n;
+        }
+        pool_push<NSLOT>(lists, cnt, act, nph, slot, lane_lt);
+        __syncwarp();   // records and lists written by one lane are read by another in a later iteration
+    }
+    if (hbatch >= 0) flush_row(hist, A.tallies + (size_t)hbatch * stride, stride, lane);
+}
+
+#endif  // LSCPM_POOL_KERNEL_BODY

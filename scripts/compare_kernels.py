@@ -37,22 +37,23 @@ def timed(plan, tallies, ppb, seed):
 for label, kw in CASES.items():
     arrays = flatten.flatten_scene(standard_scene(**kw))
     out = {}
-    for which in ("lanes", "sorted"):
+    variants = ("lanes", "sorted") if "pv" in label else ("lanes", "sorted", "pool96", "pool64")
+    for which in variants:
         scene = handle(arrays, which)
         for nb, ppb in ((3, 70_001), (64, 1_000_000)):
             plan = backend.Plan(scene, [arrays.light] * nb, list(range(nb)))
             tallies = plan.new_tallies()
             timed(plan, tallies, ppb, 7)
             tallies.zero_()
-            ms = min(timed(plan, tallies, ppb, 11) for _ in range(1))
+            ms = min(timed(plan, tallies, ppb, 11) for _ in range(2)); tallies.zero_(); timed(plan, tallies, ppb, 11)
             out[(which, nb)] = (tallies.cpu().numpy().copy(), ms)
-    for nb, ppb in ((3, 70_001), (64, 1_000_000)):
-        a, ms_a = out[("lanes", nb)]; b, ms_b = out[("sorted", nb)]
+    for nb, ppb, other in [(nb, ppb, o) for nb, ppb in ((3, 70_001), (64, 1_000_000)) for o in variants[1:]]:
+        a, ms_a = out[("lanes", nb)]; b, ms_b = out[(other, nb)]
         n = nb * ppb
         assert a[:, :scene.n_bins].sum() == n, "lanes kernel lost photons"
         assert b[:, :scene.n_bins].sum() == n, f"sorted kernel lost photons: {b[:, :scene.n_bins].sum()} vs {n}"
         assert (a[:, :scene.n_bins].sum(1) == ppb).all() and (b[:, :scene.n_bins].sum(1) == ppb).all()
         diff = np.abs(a - b)
-        print(f"{label} batches={nb} ppb={ppb}: lanes {ms_a:.2f} ms ({n/ms_a/1e3:.0f} Mph/s)  sorted {ms_b:.2f} ms ({n/ms_b/1e3:.0f} Mph/s)"
+        print(f"{label} batches={nb} ppb={ppb}: lanes {ms_a:.2f} ms ({n/ms_a/1e3:.0f} Mph/s)  {other} {ms_b:.2f} ms ({n/ms_b/1e3:.0f} Mph/s)"
               f"  speed-up {ms_a/ms_b:.2f}  bins differing {int((diff[:, :scene.n_bins] > 0).sum())}  photons moved {int(diff[:, :scene.n_bins].sum()) // 2}"
               f"  events {int(a[:, scene.n_bins].sum())} vs {int(b[:, scene.n_bins].sum())}", flush=True)

@@ -1,5 +1,18 @@
 """GPU parity, check #1: deterministic per-ray interactions (intersection distance, interface, Fresnel
-reflectivity, reflected and refracted directions) against the oracle for identical input rays, 1e-5 relative."""
+reflectivity, reflected and refracted directions) against the oracle for identical input rays.
+
+Tolerance on the distance, asserted on EVERY ray (maximum, not a percentile):
+
+    |t_gpu - t_oracle|  <=  1e-5 * t  +  ulp32(0.25 m) / |cos i|
+
+The first term is the north star's 1e-5 relative.  The second is one unit of FP32 resolution of a plate coordinate
+(2.98e-8 m at 0.25 m), taken along the surface normal: the kernels hold positions in FP32, so a hit point cannot be
+placed better than that, and a displacement delta along the normal moves the distance by delta / |cos i|.  It only
+matters for rays that start within micrometres of the surface they hit: scripts/probe_mismatch.py
+(profiles/r2_probe_tail.txt, 3.1e6 rays, 7 scene / light cases) finds 0.15 % of the rays beyond 1e-5 relative, all of
+them with t ~ 2e-5 m and |dt| ~ 7e-10 m (median), the IEEE-division build (-DLSCPM_PRECISE) giving the same numbers -
+the tail is FP32 position rounding on sub-millimetre segments, not the SFU approximations - and a largest normalised
+error of 0.53 against this bound."""
 import numpy as np
 import pytest
 
@@ -23,14 +36,31 @@ def _harvest_rays(scene, n_photons, seed):
     return np.array(pos), np.array(direc)
 
 
-@pytest.mark.parametrize("tilt,elevation", [(0, 90), (40, 50)])
-def test_probe_matches_oracle(tilt, elevation, native, built_library):
-    import c_oracle
-    from lscpm_b200 import backend, flatten
+ULP_PLATE = float(np.spacing(np.float32(0.25)))
 
-    scene = standard_scene(tilt=tilt, elevation=elevation, wavelength=585.0)
-    arrays = flatten.flatten_scene(scene)
-    pos, direc = _harvest_rays(scene, 400, seed=11)
+
+def _harvest_rays_c(arrays, native, n_photons, seed):
+    """Rays at every step of photons followed by the C oracle (large populations: ~9 rays per photon)."""
+    import c_oracle
+    from lscpm_b200 import backend
+
+    oracle = c_oracle.COracle(native, native.PackedScene(arrays))
+    batches, _ = backend.pack_batches([arrays.light])
+    pos, direc, wl = oracle.emit(batches[0], n_photons, seed=seed)
+    hist = oracle.follow(pos, direc, wl, seed=seed + 1, max_steps=48)
+    P, D = [], []
+    for i in range(len(pos)):
+        k = min(hist["n_steps"][i], 48)
+        keep = np.isin(hist["event"][i, :k - 1], (0, 1, 2, 4))
+        P.append(hist["pos"][i, :k - 1][keep])
+        D.append(hist["dir"][i, :k - 1][keep])
+    return np.concatenate(P), np.concatenate(D)
+
+
+def _check_rays(arrays, native, pos, direc, min_rays):
+    import c_oracle
+    from lscpm_b200 import backend
+
     # identical FP32-representable inputs on both sides
     pos = pos.astype(np.float32).astype(np.float64)
     direc = direc.astype(np.float32).astype(np.float64)
@@ -41,14 +71,19 @@ def test_probe_matches_oracle(tilt, elevation, native, built_library):
     # rays whose origin sits within float rounding of a surface are ambiguous after the cast; keep clear ones
     clear = ref["distance"] > 1e-6
     same_iface = (gpu["hit"] == ref["hit"]) & (gpu["container"] == ref["container"]) & (gpu["adjacent"] == ref["adjacent"])
-    frac = np.mean(same_iface[clear])
-    assert frac > 0.9995, f"interface bookkeeping agrees on {frac:.4f} of rays"
+    mismatches = int(np.sum(clear & ~same_iface))
+    assert mismatches <= 3, f"interface bookkeeping differs on {mismatches} of {int(clear.sum())} clear rays"
     ok = clear & same_iface & (ref["hit"] > 0)
-    assert ok.sum() > 1000
-    d_rel = np.abs(gpu["distance"][ok] - ref["distance"][ok]) / ref["distance"][ok]
-    tol = REL   # holds for the tilted plate too: the world->plate rotation is applied in double on the host
-    assert np.quantile(d_rel, 0.99) < tol, f"distance rel err p99 {np.quantile(d_rel, 0.99):.2e}"
-    assert np.median(d_rel) < 2e-6
+    assert ok.sum() > min_rays
+    t = ref["distance"][ok]
+    dt = np.abs(gpu["distance"][ok] - t)
+    cosi = np.abs(np.einsum("ij,ij->i", ref["normal"][ok], direc[ok]))
+    bound = REL * t + ULP_PLATE / np.maximum(cosi, 1e-12)
+    worst = int(np.argmax(dt / bound))
+    assert np.all(dt <= bound), (f"distance outside 1e-5*t + ulp/|cos i| on {int(np.sum(dt > bound))} rays; worst: t {t[worst]:.3e} "
+                                 f"dt {dt[worst]:.3e} cos i {cosi[worst]:.3e} normalised {dt[worst] / bound[worst]:.2f}")
+    d_rel = dt / t
+    assert np.quantile(d_rel, 0.99) < REL and np.median(d_rel) < 2e-6
     r_err = np.abs(gpu["reflectivity"][ok] - ref["reflectivity"][ok])
     steep = np.abs(ref["reflectivity"][ok] - 1.0) > 1e-9
     assert np.quantile(r_err[steep], 0.99) < 1e-4
@@ -59,6 +94,31 @@ def test_probe_matches_oracle(tilt, elevation, native, built_library):
     for key in ("reflected", "refracted", "normal"):
         err = np.linalg.norm(gpu[key][ok][both] - ref[key][ok][both], axis=1)
         assert np.quantile(err, 0.99) < 5e-5, (key, np.quantile(err, 0.99))
+
+
+@pytest.mark.parametrize("tilt,elevation", [(0, 90), (40, 50)])
+def test_probe_matches_oracle(tilt, elevation, native, built_library):
+    from lscpm_b200 import flatten
+
+    scene = standard_scene(tilt=tilt, elevation=elevation, wavelength=585.0)
+    arrays = flatten.flatten_scene(scene)
+    pos, direc = _harvest_rays(scene, 400, seed=11)
+    _check_rays(arrays, native, pos, direc, 1000)
+
+
+@pytest.mark.parametrize("label,kwargs", [
+    ("oblique", dict(tilt=0, elevation=25, azimuth=100, wavelength=585.0)),
+    ("diffuse", dict(tilt=20, wavelength=600.0, diffuse=True)),
+    ("pv_both", dict(tilt=0, elevation=70, azimuth=120, wavelength=585.0, add_bottom_PV=True, add_side_PV=True)),
+    ("dense46", dict(tilt=0, elevation=60, azimuth=140, wavelength=585.0, capillary_count=46, capillary_pitch=0.01)),
+])
+def test_probe_matches_oracle_on_every_ray_of_a_large_population(label, kwargs, native, built_library):
+    """~1.5e5 rays per case; the maximum error is asserted (the p99 gate could not see 1 ray in 500)."""
+    from lscpm_b200 import flatten
+
+    arrays = flatten.flatten_scene(standard_scene(**kwargs))
+    pos, direc = _harvest_rays_c(arrays, native, 20_000, seed=5)
+    _check_rays(arrays, native, pos, direc, 50_000)
 
 
 def test_known_answer_vectors(native, built_library):

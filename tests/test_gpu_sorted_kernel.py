@@ -1,6 +1,6 @@
-"""The block-sorted trace kernel against the lane-per-photon kernel (GPU).
+"""The block-sorted kernel (K2s) and the pool kernel (K2p, two configurations) against the lane-per-photon kernel (GPU).
 
-A photon's fate depends only on (seed, batch id, photon index) and both kernels run the same device functions on the same
+A photon's fate depends only on (seed, batch id, photon index) and all kernels run the same device functions on the same
 Philox draws, so their tallies must be IDENTICAL, bin for bin and counter for counter - whatever the scheduling.  The
 library picks one by scene and launch size (lscpm.cu: lscpm_scene_create / lscpm_trace_plan); LSCPM_TRACE_KERNEL forces one.
 """
@@ -53,6 +53,44 @@ def test_sorted_kernel_is_bit_identical(label):
         b, _ = _tallies(arrays, "sorted", n_batches, photons, seed=1234)
         assert (b[:, :n_bins].sum(axis=1) == photons).all(), f"{label}: sorted kernel lost or duplicated photons"
         np.testing.assert_array_equal(a, b, err_msg=f"{label} batches={n_batches} photons={photons}")
+
+
+POOL_CASES = sorted(k for k in CASES if not k.startswith("pv_"))   # scenes with outside boxes have no pool kernel
+
+
+@pytest.mark.parametrize("which", ["pool96", "pool64"])
+@pytest.mark.parametrize("label", POOL_CASES)
+def test_pool_kernel_is_bit_identical(label, which):
+    from lscpm_b200 import flatten
+    arrays = flatten.flatten_scene(standard_scene(**CASES[label]))
+    for n_batches, photons in ((1, 1), (3, 257), (2, 70_001), (5, 300_000)):
+        a, n_bins = _tallies(arrays, "lanes", n_batches, photons, seed=4321)
+        b, _ = _tallies(arrays, which, n_batches, photons, seed=4321)
+        assert (b[:, :n_bins].sum(axis=1) == photons).all(), f"{label}: pool kernel lost or duplicated photons"
+        np.testing.assert_array_equal(a, b, err_msg=f"{label} {which} batches={n_batches} photons={photons}")
+
+
+def test_pool_kernel_photon_offset_and_many_small_batches():
+    from lscpm_b200 import flatten
+    arrays = flatten.flatten_scene(standard_scene(tilt=20, elevation=50, spectrum=am15_like_photon_spectrum()))
+    a, n_bins = _tallies(arrays, "lanes", 400, 37, seed=5, photon_begin=(1 << 33) + 12345)
+    for which in ("pool96", "pool64"):
+        b, _ = _tallies(arrays, which, 400, 37, seed=5, photon_begin=(1 << 33) + 12345)
+        assert (b[:, :n_bins].sum(axis=1) == 37).all()
+        np.testing.assert_array_equal(a, b)
+
+
+def test_default_kernel_of_the_standard_scene_is_the_pool_kernel_and_agrees_with_lanes():
+    """What a user gets without any environment variable, against the lane kernel."""
+    from lscpm_b200 import backend, flatten
+    arrays = flatten.flatten_scene(standard_scene(tilt=0, elevation=90, spectrum=am15_like_photon_spectrum()))
+    a, n_bins = _tallies(arrays, "lanes", 4, 250_000, seed=99)
+    assert "LSCPM_TRACE_KERNEL" not in os.environ
+    scene = backend.SceneHandle(arrays, 0)
+    plan = backend.Plan(scene, [arrays.light] * 4, list(range(10, 14)))
+    tallies = plan.new_tallies()
+    plan.trace_into(tallies, 250_000, 99)
+    np.testing.assert_array_equal(a, tallies.cpu().numpy())
 
 
 def test_sorted_kernel_photon_offset_and_many_small_batches():
