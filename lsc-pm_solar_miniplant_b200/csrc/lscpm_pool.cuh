@@ -12,7 +12,7 @@
 // barrier, no atomics on the lists (one warp, warp-uniform counters), no hand-over between warps: what made the block-level
 // regrouping experiments of round 1 lose (K2s: the block waits for its slowest warp; page queues: queue management cost as
 // much as the photon work) does not exist here.  Cost: four 16-byte shared-memory loads / two or three stores per phase
-// execution and ~50 instructions of list bookkeeping (packed counters, one MATCH + two REDUX per push).
+// execution and ~50 instructions of list bookkeeping (one packed counter word, one MATCH + one REDUX per push).
 //
 // What the first version's profile asked for (profiles/r2_pool_v1_*): it executed 25 % fewer warp instructions than K2 at
 // 25.0 active lanes but issued only 59 % of its slots - 18 % of the stall samples were instruction-cache misses (52 KB of
@@ -54,28 +54,27 @@ __host__ __device__ constexpr size_t pool_smem_bytes(int warps, int nslot, int s
 template <bool FLIGHT>
 __device__ __forceinline__ int fly_phase(int medium) { return (FLIGHT && medium == MED_PLATE) ? PH_PLATE : PH_TUBE; }
 
-// List lengths, warp-uniform, packed: phases 0..3 in the bytes of `a`, phase 4 in `b` (NSLOT <= 255).
-struct PoolCounts {
-    unsigned a, b;
-    __device__ __forceinline__ int get(int ph) const { return ph < 4 ? (int)((a >> (8 * ph)) & 0xffu) : (int)b; }
-};
+// List lengths, warp-uniform, packed into ONE word: phases 0..3 in its bytes (NSLOT <= 255).  Between two phase
+// executions every record is in exactly one list, so the fifth length (PH_EMIT) is NSLOT minus the byte sum.
+__device__ __forceinline__ unsigned pool_byte_sum(unsigned a) { return __vsadu4(a, 0u); }
 
 // Push the records the active lanes hold onto the lists of their next phases: lanes with the same target find each other
-// with one MATCH, rank themselves inside the group, and the group leaders' sizes are summed into the packed counters
-// with two REDUX - independent of how many different targets there are.
+// with one MATCH and rank themselves inside the group; the group leaders' sizes are summed into the packed counters with
+// one REDUX - independent of how many different targets there are.  `emit_len`: current length of the PH_EMIT list.
 template <int NSLOT>
-__device__ __forceinline__ void pool_push(unsigned char* __restrict__ lists, PoolCounts& cnt, bool act, int nph, int slot, unsigned lane_lt) {
-    const int key = act ? nph : 7;                       // idle lanes form a group of their own that is not counted
-    const unsigned grp = __match_any_sync(0xffffffffu, key);
+__device__ __forceinline__ void pool_push(unsigned char* __restrict__ lists, unsigned& cnt, unsigned emit_len, bool act, int nph, int slot,
+                                          unsigned lane_lt) {
+    const unsigned grp = __match_any_sync(0xffffffffu, act ? nph : 7);   // idle lanes form a group of their own that is not counted
     const int rank = __popc(grp & lane_lt);
-    if (act) lists[nph * NSLOT + cnt.get(nph) + rank] = (unsigned char)slot;
-    const unsigned size = (act && rank == 0) ? (unsigned)__popc(grp) : 0u;
-    cnt.a += __reduce_add_sync(0xffffffffu, nph < 4 ? size << (8 * (nph & 3)) : 0u);
-    cnt.b += __reduce_add_sync(0xffffffffu, nph == 4 ? size : 0u);
+    const unsigned shift = 8u * (unsigned)nph;
+    const unsigned base = nph < 4 ? (cnt >> shift) & 0xffu : emit_len;
+    if (act) lists[nph * NSLOT + (int)base + rank] = (unsigned char)slot;
+    const unsigned contrib = (act && rank == 0 && nph < 4) ? (unsigned)__popc(grp) << shift : 0u;
+    cnt += __reduce_add_sync(0xffffffffu, contrib);
 }
 
-__device__ __noinline__ void pool_tally(unsigned long long* __restrict__ tallies, unsigned int* hist, int n_bins, int stride,
-                                        int hbatch, int batch, int bin, unsigned n_events) {
+__device__ __forceinline__ void pool_tally(unsigned long long* __restrict__ tallies, unsigned int* hist, int n_bins, int stride,
+                                           int hbatch, int batch, int bin, unsigned n_events) {
     LSCPM_CHECK(bin >= 0 && bin < n_bins);
     if (batch == hbatch) {
         atomicAdd(hist + bin, 1u);
@@ -111,8 +110,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
     for (int i = lane; i < NSLOT; i += 32) lists[PH_FRESH * NSLOT + i] = (unsigned char)i;
     __syncwarp();
 
-    PoolCounts cnt;
-    cnt.a = (unsigned)NSLOT; cnt.b = 0u;    // every record starts empty
+    unsigned cnt = (unsigned)NSLOT;         // packed list lengths: every record starts empty (PH_FRESH = byte 0)
     int hbatch = -1;                        // batch whose photons the shared row accumulates
     unsigned long long chunk_base = 0;      // work item: photons chunk_base + [c_next, c_end) of batch `cbatch` are unclaimed
     unsigned c_next = 0, c_end = 0;
@@ -122,12 +120,12 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
 
     for (;;) {
         // ---- the fullest list whose phase can run: max over (length << 3 | phase) ---------------------------------
-        const unsigned fresh_len = (c_next < c_end || more) ? (cnt.a & 0xffu) : 0u;
+        const unsigned fresh_len = (c_next < c_end || more) ? (cnt & 0xffu) : 0u;
         unsigned key = fresh_len << 3;
-        key = max(key, (((cnt.a >> 8) & 0xffu) << 3) | 1u);
-        key = max(key, (((cnt.a >> 16) & 0xffu) << 3) | 2u);
-        key = max(key, ((cnt.a >> 24) << 3) | 3u);
-        key = max(key, (cnt.b << 3) | 4u);
+        key = max(key, (__byte_perm(cnt, 0u, 0x4441) << 3) | 1u);
+        key = max(key, (__byte_perm(cnt, 0u, 0x4442) << 3) | 2u);
+        key = max(key, ((cnt >> 24) << 3) | 3u);
+        key = max(key, (((unsigned)NSLOT - pool_byte_sum(cnt)) << 3) | 4u);
         const int best = (int)(key >> 3);
         if (best == 0) break;
         const int ph = (int)(key & 7u);
@@ -158,8 +156,11 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
         int slot = 0;
         if (act) slot = lists[ph * NSLOT + best - n + lane];
         LSCPM_CHECK(slot >= 0 && slot < NSLOT);
-        if (ph < 4) cnt.a -= (unsigned)n << (8 * ph); else cnt.b -= (unsigned)n;
+        cnt -= ph < 4 ? (unsigned)n << (8 * ph) : 0u;
+        const unsigned emit_len = (unsigned)(NSLOT - n) - pool_byte_sum(cnt);
         int nph = PH_FRESH;
+        int tbin = -1, tbatch = 0;          // a photon that ended in this execution: tallied once, below
+        unsigned tevents = 0u;
 
         if (ph == PH_PLATE || ph == PH_TUBE) {
             // ---- step draw, nearest interface, free path, move; absorption is settled here as well ---------------
@@ -196,7 +197,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                     }
                 }
                 if (bin >= 0) {
-                    pool_tally(A.tallies, hist, S.n_bins, stride, hbatch, (int)g2.z, bin, n_events);
+                    tbin = bin; tbatch = (int)g2.z; tevents = n_events;
                 } else {
                     G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
                                                      (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
@@ -219,7 +220,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                 const int bin = interact_surface<false>(S, p, pending_kind(g3.y), pending_face(g3.y), pending_container(g3.y),
                                                         pending_adj(g3.y), u01(g3.z), ev);
                 if (bin >= 0) {
-                    pool_tally(A.tallies, hist, S.n_bins, stride, hbatch, (int)G[2 * NSLOT + slot].z, bin, n_events);
+                    tbin = bin; tbatch = (int)G[2 * NSLOT + slot].z; tevents = n_events;
                 } else {
                     nph = fly_phase<FLIGHT>(p.medium);
                     G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
@@ -258,7 +259,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                 else source_emit(S, v, p, wd);
                 source_wavelength(p, wd);
                 if (bin >= 0) {   // reflected off the plate at first contact, or never touched it: the record stays empty
-                    pool_tally(A.tallies, hist, S.n_bins, stride, hbatch, batch, bin, n_events);
+                    tbin = bin; tbatch = batch; tevents = n_events;
                 } else {
                     nph = fly_phase<FLIGHT>(p.medium);
                     if (fresh) {
@@ -274,7 +275,8 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
             }
             if (fresh) c_next += (unsigned)n;
         }
-        pool_push<NSLOT>(lists, cnt, act, nph, slot, lane_lt);
+        if (tbin >= 0) pool_tally(A.tallies, hist, S.n_bins, stride, hbatch, tbatch, tbin, tevents);
+        pool_push<NSLOT>(lists, cnt, emit_len, act, nph, slot, lane_lt);
         __syncwarp();   // records and lists written by one lane are read by another in a later iteration
     }
     if (hbatch >= 0) flush_row(hist, A.tallies + (size_t)hbatch * stride, stride, lane);
