@@ -71,6 +71,19 @@ class BatchDesc(C.Structure):
     ]
 
 
+# the same layout as a NumPy structured dtype: the drivers fill thousands of descriptors column-wise (lights.py)
+BATCH_DTYPE = np.dtype([("light_kind", "<i4"), ("spectrum", "<i4"), ("batch_id", "<u4"), ("reserved", "<u4"),
+                        ("wavelength_nm", "<f8"), ("mask_half", "<f8", (2,)), ("mask_pose", "<f8", (12,)),
+                        ("direction", "<f8", (3,)), ("back_off", "<f8"), ("tilt_deg", "<f8")], align=True)
+assert BATCH_DTYPE.itemsize == C.sizeof(BatchDesc), (BATCH_DTYPE.itemsize, C.sizeof(BatchDesc))
+
+
+def batch_pointer(table: np.ndarray):
+    """``LscpmBatchDesc*`` view of a C-contiguous ``BATCH_DTYPE`` array (the array must outlive the call)."""
+    assert table.dtype == BATCH_DTYPE and table.flags.c_contiguous
+    return table.ctypes.data_as(C.POINTER(BatchDesc))
+
+
 class SpectraDesc(C.Structure):
     _fields_ = [
         ("n_spectra", C.c_int32),
@@ -123,11 +136,20 @@ class PackedScene:
 
 
 class PackedSpectra:
-    def __init__(self, spectra: Sequence[np.ndarray]):
-        self.n = len(spectra)
-        begin = np.cumsum([0] + [len(s) for s in spectra]).astype(np.int32)
-        flat = np.concatenate([np.asarray(s, dtype=np.float64).reshape(-1, 2) for s in spectra], axis=0) \
-            if spectra else np.zeros((0, 2))
+    """Spectra as ``LscpmSpectraDesc``: a sequence of (N_i, 2) knot arrays, or one (M, N, 2) array of M spectra with N
+    knots each (the drivers' SPECTRL2 grid) which is packed without a Python loop."""
+
+    def __init__(self, spectra):
+        if isinstance(spectra, np.ndarray) and spectra.ndim == 3:
+            m, k = spectra.shape[0], spectra.shape[1]
+            self.n = m
+            begin = (np.arange(m + 1, dtype=np.int64) * k).astype(np.int32)
+            flat = np.ascontiguousarray(spectra, dtype=np.float64).reshape(-1, 2)
+        else:
+            self.n = len(spectra)
+            begin = np.cumsum([0] + [len(s) for s in spectra]).astype(np.int32)
+            flat = np.concatenate([np.asarray(s, dtype=np.float64).reshape(-1, 2) for s in spectra], axis=0) \
+                if len(spectra) else np.zeros((0, 2))
         self._begin = np.ascontiguousarray(begin)
         self._x = np.ascontiguousarray(flat[:, 0])
         self._y = np.ascontiguousarray(flat[:, 1])
@@ -136,6 +158,20 @@ class PackedSpectra:
         d.begin = _ptr(self._begin, C.c_int32)
         d.x = _ptr(self._x, C.c_double)
         d.y = _ptr(self._y, C.c_double)
+
+
+def fill_batch_row(row, light, batch_id: int = 0, spectrum_index: int = -1) -> None:
+    """``flatten.LightArrays`` -> one row of a ``BATCH_DTYPE`` array."""
+    row["light_kind"] = int(light.kind)
+    row["spectrum"] = int(spectrum_index)
+    row["batch_id"] = int(batch_id) & 0xFFFFFFFF
+    row["reserved"] = 0
+    row["wavelength_nm"] = float(light.wavelength_nm)
+    row["mask_half"] = np.asarray(light.mask_half, dtype=np.float64).reshape(2)
+    row["mask_pose"] = np.asarray(light.mask_pose, dtype=np.float64).reshape(12)
+    row["direction"] = np.asarray(light.direction, dtype=np.float64).reshape(3)
+    row["back_off"] = float(light.back_off)
+    row["tilt_deg"] = float(light.tilt_deg)
 
 
 def make_batch(light, batch_id: int = 0, spectrum_index: int = -1) -> BatchDesc:

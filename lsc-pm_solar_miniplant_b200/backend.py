@@ -87,12 +87,17 @@ def _scene_key(arrays: _flatten.SceneArrays, device: int) -> str:
 
 def scene_handle(arrays: _flatten.SceneArrays, device=None) -> SceneHandle:
     dev = device_index(device)
+    pinned = arrays.__dict__.setdefault("_handles", {})   # the same SceneArrays object asked again: no hashing
+    handle = pinned.get(dev)
+    if handle is not None:
+        return handle
     key = _scene_key(arrays, dev)
     handle = _scene_cache.get(key)
     if handle is None:
         if len(_scene_cache) > 64:
             _scene_cache.clear()
         handle = _scene_cache[key] = SceneHandle(arrays, dev)
+    pinned[dev] = handle
     return handle
 
 
@@ -101,32 +106,63 @@ def scene_handle(arrays: _flatten.SceneArrays, device=None) -> SceneHandle:
 # --------------------------------------------------------------------------------------
 
 
-def pack_batches(lights: Sequence[_flatten.LightArrays], batch_ids: Optional[Sequence[int]] = None):
-    """LightArrays -> (ctypes array of LscpmBatchDesc, PackedSpectra).  Spectra are de-duplicated."""
+def batch_table(lights, batch_ids: Optional[Sequence[int]] = None):
+    """Anything that describes batches -> ``lights.BatchTable``: a table passes through (``batch_ids`` override its
+    ids), a sequence of ``LightArrays`` is packed row by row with its spectra de-duplicated."""
+    from .lights import BatchTable
+
+    if isinstance(lights, BatchTable):
+        if batch_ids is None:
+            return lights
+        desc = lights.desc.copy()
+        desc["batch_id"] = np.asarray(batch_ids, dtype=np.uint32)
+        return BatchTable(desc, lights.spectra)
     n = len(lights)
-    batches = (nat.BatchDesc * n)()
+    desc = np.zeros(n, dtype=nat.BATCH_DTYPE)
     spectra, index = [], {}
     for i, light in enumerate(lights):
         if light.wavelength_callable is not None:
             raise _flatten.UnsupportedSceneError("host-sampled wavelength callables go through trace_rays()")
         spec = -1
         if light.spectrum is not None:
-            key = np.ascontiguousarray(light.spectrum, dtype=np.float64).tobytes()
+            knots = np.ascontiguousarray(light.spectrum, dtype=np.float64)
+            key = (id(light.spectrum), knots.shape) if n > 64 else knots.tobytes()
             if key not in index:
                 index[key] = len(spectra)
-                spectra.append(np.asarray(light.spectrum, dtype=np.float64))
+                spectra.append(knots)
             spec = index[key]
-        batches[i] = nat.make_batch(light, batch_id=(batch_ids[i] if batch_ids is not None else i), spectrum_index=spec)
-    return batches, nat.PackedSpectra(spectra)
+        nat.fill_batch_row(desc[i], light, batch_id=(batch_ids[i] if batch_ids is not None else i), spectrum_index=spec)
+    return BatchTable(desc, spectra or None)
+
+
+def pack_batches(lights, batch_ids: Optional[Sequence[int]] = None):
+    """-> (``LscpmBatchDesc*`` over the table's rows, ``PackedSpectra``, the table that owns the memory)."""
+    table = batch_table(lights, batch_ids)
+    spectra = nat.PackedSpectra(table.spectra if table.spectra is not None else [])
+    return _BatchPointer(table), spectra
+
+
+class _BatchPointer:
+    """ctypes view of a table's rows that keeps the table alive; indexable like the ctypes array it replaces."""
+
+    def __init__(self, table):
+        self.table = table
+        self._as_parameter_ = nat.batch_pointer(table.desc)
+
+    def __len__(self):
+        return len(self.table)
+
+    def __getitem__(self, i):
+        return self._as_parameter_[i]
 
 
 class Plan:
     """Batch descriptors and spectra resident on the device (``lscpm_plan_create``)."""
 
-    def __init__(self, scene: SceneHandle, lights: Sequence[_flatten.LightArrays], batch_ids=None):
+    def __init__(self, scene: SceneHandle, lights, batch_ids=None):
         self.scene = scene
-        self.n_batches = len(lights)
         self._batches, self._spectra = pack_batches(lights, batch_ids)
+        self.n_batches = len(self._batches)
         handle = C.c_void_p()
         nat.check(scene.lib, scene.lib.lscpm_plan_create(scene.handle, self._batches, self.n_batches,
                                                          C.byref(self._spectra.desc), C.byref(handle)))
@@ -154,18 +190,21 @@ def fresh_seed() -> int:
     return int.from_bytes(os.urandom(8), "little")
 
 
-def trace_lights(arrays: _flatten.SceneArrays, lights: Sequence[_flatten.LightArrays], photons_per_batch: int,
+def trace_lights(arrays: _flatten.SceneArrays, lights, photons_per_batch: int,
                  seed: Optional[int] = None, device=None, batch_ids=None, photon_begin: int = 0) -> np.ndarray:
-    """Trace ``photons_per_batch`` photons for every light configuration; returns int64
-    ``[n_batches, n_bins + N_COUNTERS]`` on the host."""
-    torch = _torch()
+    """Trace ``photons_per_batch`` photons for every light configuration (a sequence of ``LightArrays`` or a
+    ``lights.BatchTable``); returns int64 ``[n_batches, n_bins + N_COUNTERS]`` on the host.
+
+    One call of ``lscpm_trace_host``: host descriptors in, host tallies out, through the scene's pinned staging buffer
+    and device scratch — no allocation, no torch tensor, one stream synchronisation."""
     scene = scene_handle(arrays, device)
     seed = fresh_seed() if seed is None else int(seed)
-    with torch.cuda.device(scene.device):
-        plan = Plan(scene, lights, batch_ids)
-        tallies = plan.new_tallies()
-        plan.trace_into(tallies, photons_per_batch, seed, photon_begin)
-        out = tallies.cpu().numpy()
+    batches, spectra = pack_batches(lights, batch_ids)
+    out = np.zeros((len(batches), scene.stride), dtype=np.int64)
+    if len(batches) and int(photons_per_batch) > 0:
+        nat.check(scene.lib, scene.lib.lscpm_trace_host(scene.handle, batches, len(batches), C.byref(spectra.desc),
+                                                        int(photon_begin), int(photons_per_batch),
+                                                        seed & 0xFFFFFFFFFFFFFFFF, out.ctypes.data_as(nat.c_int64_p)))
     return out
 
 

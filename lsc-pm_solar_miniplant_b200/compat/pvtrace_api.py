@@ -130,6 +130,26 @@ class Distribution:
         return np.interp(u, self._cdf, self._x)
 
 
+class LazyDistribution(Distribution):
+    """A non-histogram ``Distribution`` over already validated knots whose CDF is built on first use.  The solar stage
+    creates two per time point (tens of thousands per year); the drivers only read ``_x`` / ``_y`` from them."""
+
+    def __init__(self, x, y):   # noqa: super().__init__ deliberately not called
+        self.hist = False
+        self._x = x
+        self._y = y
+
+    @property
+    def _cdf(self):
+        cdf = self.__dict__.get("_cdf_cache")
+        if cdf is None:
+            cdf = np.cumsum(self._y)
+            peak = cdf.max() if len(cdf) else 0.0
+            cdf = cdf / peak if peak > 0 else cdf
+            self.__dict__["_cdf_cache"] = cdf
+        return cdf
+
+
 # --------------------------------------------------------------------------------------
 # events, rays
 # --------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -767,16 +768,31 @@ struct LscpmScene {
     size_t sort_smem = 0;
     int pool = 0;                        // pool kernel configuration: 0 off, 1 = 24 warps x 96 records, 2 = 32 warps x 64 records
     size_t pool_smem = 0;
+    // scratch of the host-buffer entry points (lscpm_trace_host, plan staging): one pinned host buffer, one device
+    // buffer and one stream per scene, grown on demand and reused, so a call costs no allocation
+    std::mutex scratch_mutex;
+    unsigned char* h_scratch = nullptr;  // pinned
+    unsigned char* d_scratch = nullptr;
+    size_t h_scratch_bytes = 0, d_scratch_bytes = 0;
+    cudaStream_t scratch_stream = nullptr;
 };
 constexpr int COUNTER_RING = 256;
 
 struct LscpmPlan {
     LscpmScene* scene = nullptr;
     int n_batches = 0;
+    unsigned char* d_blob = nullptr;     // ONE device allocation: lowered batches | spectrum knots | CDFs | guide tables
+    bool owns_blob = true;
     DevBatch* d_batches = nullptr;
     float *d_spec_x = nullptr, *d_spec_cdf = nullptr;
     unsigned short* d_spec_guide = nullptr;
     uint64_t h2d_bytes = 0;
+};
+
+// host image of a plan: the four arrays laid out back to back (16-byte aligned sections) so that one copy uploads them
+struct PlanLayout {
+    size_t off_batches = 0, off_x = 0, off_cdf = 0, off_guide = 0, bytes = 0;
+    size_t n_knots = 0, n_guide = 0;
 };
 
 namespace {
@@ -1345,6 +1361,9 @@ int lscpm_scene_destroy(LscpmScene* s) {
     if (!s) return LSCPM_OK;
     cudaFree(s->d_tab_x); cudaFree(s->d_tab_y); cudaFree(s->d_tab_cdf); cudaFree(s->d_tab_fwd); cudaFree(s->d_tab_inv);
     cudaFree(s->d_abs_outer); cudaFree(s->d_abs_inner); cudaFree(s->d_exit_outer); cudaFree(s->d_exit_inner); cudaFree(s->d_counters);
+    if (s->h_scratch) cudaFreeHost(s->h_scratch);
+    if (s->d_scratch) cudaFree(s->d_scratch);
+    if (s->scratch_stream) cudaStreamDestroy(s->scratch_stream);
     delete s;
     return LSCPM_OK;
 }
@@ -1359,19 +1378,43 @@ int lscpm_scene_bin_name(const LscpmScene* s, int bin, char* buf, int buf_len) {
     return (int)name.size();
 }
 
-int lscpm_plan_create(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_batches, const LscpmSpectraDesc* spectra,
-                      LscpmPlan** out) {
-    if (!out) return fail(LSCPM_EINVAL, "out pointer is NULL");
-    *out = nullptr;
-    if (!s || !batches || n_batches < 1) return fail(LSCPM_EINVAL, "scene/batches missing");
-    CUDA_TRY(cudaSetDevice(s->device));
-    std::vector<float> sx, sc;
-    std::vector<unsigned short> sg;
+namespace {
+
+inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+int plan_layout(const LscpmBatchDesc* batches, int32_t n_batches, const LscpmSpectraDesc* spectra, PlanLayout& L) {
+    if (!batches || n_batches < 1) return fail(LSCPM_EINVAL, "scene/batches missing");
+    size_t knots = 0, n_spec = 0;
+    if (spectra && spectra->n_spectra > 0) {
+        n_spec = (size_t)spectra->n_spectra;
+        knots = (size_t)(spectra->begin[n_spec] - spectra->begin[0]);
+        if (spectra->begin[0] != 0) return fail(LSCPM_EINVAL, "spectra->begin must start at 0");
+    }
+    L.n_knots = knots; L.n_guide = n_spec * (SPEC_BUCKETS + 1);
+    L.off_batches = 0;
+    L.off_x = align16((size_t)n_batches * sizeof(DevBatch));
+    L.off_cdf = L.off_x + align16(std::max<size_t>(knots, 1) * sizeof(float));
+    L.off_guide = L.off_cdf + align16(std::max<size_t>(knots, 1) * sizeof(float));
+    L.bytes = L.off_guide + align16(std::max<size_t>(L.n_guide, 1) * sizeof(unsigned short));
+    return LSCPM_OK;
+}
+
+// lower batches and spectra into `image` (L.bytes bytes of host memory, pinned or not)
+int plan_fill(const LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_batches, const LscpmSpectraDesc* spectra,
+              const PlanLayout& L, unsigned char* image) {
+    DevBatch* lowered = reinterpret_cast<DevBatch*>(image + L.off_batches);
+    float* sx = reinterpret_cast<float*>(image + L.off_x);
+    float* sc = reinterpret_cast<float*>(image + L.off_cdf);
+    unsigned short* sg = reinterpret_cast<unsigned short*>(image + L.off_guide);
     std::vector<int> sb(1, 0);
     if (spectra && spectra->n_spectra > 0) {
+        sb.reserve((size_t)spectra->n_spectra + 1);
+        std::vector<double> cdf;
+        size_t w = 0, gw = 0;
         for (int i = 0; i < spectra->n_spectra; ++i) {
             const int lo = spectra->begin[i], n = spectra->begin[i + 1] - lo;
             if (n < 2) return fail(LSCPM_EINVAL, "spectrum needs at least two knots");
+            if (n > 65000) return fail(LSCPM_EUNSUPPORTED, "spectrum with more than 65000 knots");
             double total = 0;
             for (int k = 0; k < n; ++k) {
                 if (!(spectra->y[lo + k] >= 0)) return fail(LSCPM_EINVAL, "spectrum weights must be non-negative");
@@ -1379,33 +1422,84 @@ int lscpm_plan_create(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_ba
                 total += spectra->y[lo + k];
             }
             if (!(total > 0)) return fail(LSCPM_EINVAL, "spectrum is identically zero");
-            std::vector<double> cdf;
             cumulative_cdf(spectra->x + lo, spectra->y + lo, n, cdf);
-            if (n > 65000) return fail(LSCPM_EUNSUPPORTED, "spectrum with more than 65000 knots");
-            for (int k = 0; k < n; ++k) { sx.push_back((float)spectra->x[lo + k]); sc.push_back((float)cdf[k]); }
-            sb.push_back((int)sx.size());
+            for (int k = 0; k < n; ++k) { sx[w] = (float)spectra->x[lo + k]; sc[w] = (float)cdf[k]; ++w; }
+            sb.push_back((int)w);
             int j = 0;
             for (int b = 0; b <= SPEC_BUCKETS; ++b) {
                 const double level = (double)b / SPEC_BUCKETS;
                 while (j + 2 < n && cdf[j + 1] <= level) ++j;
-                sg.push_back((unsigned short)j);
+                sg[gw++] = (unsigned short)j;
             }
         }
     }
-    std::vector<DevBatch> lowered(n_batches);
     for (int b = 0; b < n_batches; ++b) {
         const int rc = lower_batch(s, batches + b, sb, lowered[b]);
         if (rc) return rc;
     }
+    return LSCPM_OK;
+}
+
+void plan_point(LscpmPlan* p, unsigned char* d_blob, const PlanLayout& L) {
+    p->d_blob = d_blob;
+    p->d_batches = reinterpret_cast<DevBatch*>(d_blob + L.off_batches);
+    p->d_spec_x = reinterpret_cast<float*>(d_blob + L.off_x);
+    p->d_spec_cdf = reinterpret_cast<float*>(d_blob + L.off_cdf);
+    p->d_spec_guide = reinterpret_cast<unsigned short*>(d_blob + L.off_guide);
+    p->h2d_bytes = L.bytes;
+}
+
+// the scene's scratch buffers, grown geometrically; caller holds scratch_mutex
+int scratch_reserve(LscpmScene* s, size_t host_bytes, size_t dev_bytes) {
+    if (!s->scratch_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->scratch_stream, cudaStreamNonBlocking));
+    if (host_bytes > s->h_scratch_bytes) {
+        if (s->h_scratch) cudaFreeHost(s->h_scratch);
+        s->h_scratch = nullptr; s->h_scratch_bytes = 0;
+        const size_t want = std::max<size_t>(host_bytes + host_bytes / 2, 64 * 1024);
+        CUDA_TRY(cudaMallocHost((void**)&s->h_scratch, want));
+        s->h_scratch_bytes = want;
+    }
+    if (dev_bytes > s->d_scratch_bytes) {
+        if (s->d_scratch) cudaFree(s->d_scratch);
+        s->d_scratch = nullptr; s->d_scratch_bytes = 0;
+        const size_t want = std::max<size_t>(dev_bytes + dev_bytes / 2, 64 * 1024);
+        CUDA_TRY(cudaMalloc((void**)&s->d_scratch, want));
+        s->d_scratch_bytes = want;
+    }
+    return LSCPM_OK;
+}
+
+}  // namespace
+
+// One device allocation and one host->device copy per plan: the lowered descriptors and the spectra are written straight
+// into the scene's pinned staging buffer and uploaded with a single cudaMemcpyAsync.
+int lscpm_plan_create(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_batches, const LscpmSpectraDesc* spectra,
+                      LscpmPlan** out) {
+    if (!out) return fail(LSCPM_EINVAL, "out pointer is NULL");
+    *out = nullptr;
+    if (!s || !batches || n_batches < 1) return fail(LSCPM_EINVAL, "scene/batches missing");
+    CUDA_TRY(cudaSetDevice(s->device));
+    PlanLayout L;
+    int rc = plan_layout(batches, n_batches, spectra, L);
+    if (rc) return rc;
     LscpmPlan* p = new (std::nothrow) LscpmPlan();
     if (!p) return fail(LSCPM_ENOMEM, "out of host memory");
     p->scene = s; p->n_batches = n_batches;
-    p->h2d_bytes = lowered.size() * sizeof(DevBatch) + (sx.size() + sc.size()) * sizeof(float) + sg.size() * sizeof(unsigned short);
-    int rc;
-    if ((rc = upload(lowered, &p->d_batches)) || (rc = upload(sx, &p->d_spec_x)) || (rc = upload(sc, &p->d_spec_cdf)) ||
-        (rc = upload(sg, &p->d_spec_guide))) {
-        lscpm_plan_destroy(p);
-        return rc;
+    unsigned char* d_blob = nullptr;
+    cudaError_t e = cudaMalloc((void**)&d_blob, L.bytes);
+    if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaMalloc plan"); }
+    plan_point(p, d_blob, L);
+    {
+        std::lock_guard<std::mutex> lock(s->scratch_mutex);
+        if ((rc = scratch_reserve(s, L.bytes, 0)) || (rc = plan_fill(s, batches, n_batches, spectra, L, s->h_scratch))) {
+            lscpm_plan_destroy(p);
+            return rc;
+        }
+        if ((e = cudaMemcpyAsync(d_blob, s->h_scratch, L.bytes, cudaMemcpyHostToDevice, s->scratch_stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(s->scratch_stream)) != cudaSuccess) {
+            lscpm_plan_destroy(p);
+            return cuda_fail(e, "plan upload");
+        }
     }
     *out = p;
     return LSCPM_OK;
@@ -1415,7 +1509,7 @@ uint64_t lscpm_plan_h2d_bytes(const LscpmPlan* p) { return p ? p->h2d_bytes : 0;
 
 int lscpm_plan_destroy(LscpmPlan* p) {
     if (!p) return LSCPM_OK;
-    cudaFree(p->d_batches); cudaFree(p->d_spec_x); cudaFree(p->d_spec_cdf); cudaFree(p->d_spec_guide);
+    if (p->owns_blob) cudaFree(p->d_blob);
     delete p;
     return LSCPM_OK;
 }
@@ -1495,19 +1589,32 @@ int lscpm_trace(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_batches,
     return LSCPM_OK;
 }
 
+// Host buffers in, host tallies out, no allocation per call: descriptors and spectra are lowered into the scene's pinned
+// staging buffer, one copy takes them to the scene's device scratch, the tally block behind them is zeroed, traced into
+// and copied back - all on the scene's own stream, one synchronisation at the end.
 int lscpm_trace_host(LscpmScene* s, const LscpmBatchDesc* batches, int32_t n_batches, const LscpmSpectraDesc* spectra,
                      uint64_t photon_begin, uint64_t photon_count, uint64_t seed, int64_t* tallies_host) {
     if (!s || !tallies_host) return fail(LSCPM_EINVAL, "scene/tallies missing");
     CUDA_TRY(cudaSetDevice(s->device));
-    const size_t n = (size_t)n_batches * (size_t)(s->dev.n_bins + LSCPM_N_COUNTERS);
-    int64_t* d = nullptr;
-    CUDA_TRY(cudaMalloc((void**)&d, n * sizeof(int64_t)));
-    cudaError_t e = cudaMemset(d, 0, n * sizeof(int64_t));
-    int rc = e == cudaSuccess ? lscpm_trace(s, batches, n_batches, spectra, photon_begin, photon_count, seed, d, nullptr)
-                              : cuda_fail(e, "cudaMemset");
-    if (!rc && (e = cudaMemcpy(tallies_host, d, n * sizeof(int64_t), cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "cudaMemcpy tallies");
-    cudaFree(d);
-    return rc;
+    PlanLayout L;
+    int rc = plan_layout(batches, n_batches, spectra, L);
+    if (rc) return rc;
+    const size_t tally_bytes = (size_t)n_batches * (size_t)(s->dev.n_bins + LSCPM_N_COUNTERS) * sizeof(int64_t);
+    std::lock_guard<std::mutex> lock(s->scratch_mutex);
+    if ((rc = scratch_reserve(s, std::max(L.bytes, tally_bytes), L.bytes + tally_bytes))) return rc;
+    if ((rc = plan_fill(s, batches, n_batches, spectra, L, s->h_scratch))) return rc;
+    LscpmPlan plan;
+    plan.scene = s; plan.n_batches = n_batches; plan.owns_blob = false;
+    plan_point(&plan, s->d_scratch, L);
+    int64_t* d_tallies = reinterpret_cast<int64_t*>(s->d_scratch + L.bytes);
+    CUDA_TRY(cudaMemcpyAsync(s->d_scratch, s->h_scratch, L.bytes, cudaMemcpyHostToDevice, s->scratch_stream));
+    CUDA_TRY(cudaMemsetAsync(d_tallies, 0, tally_bytes, s->scratch_stream));
+    if ((rc = lscpm_trace_plan(&plan, photon_begin, photon_count, seed, d_tallies, s->scratch_stream))) return rc;
+    // the staging buffer is free again once the upload has been consumed; stream order guarantees that here
+    CUDA_TRY(cudaMemcpyAsync(s->h_scratch, d_tallies, tally_bytes, cudaMemcpyDeviceToHost, s->scratch_stream));
+    CUDA_TRY(cudaStreamSynchronize(s->scratch_stream));
+    memcpy(tallies_host, s->h_scratch, tally_bytes);
+    return LSCPM_OK;
 }
 
 // ---- per-ray entry points ------------------------------------------------------------------------

@@ -1,6 +1,6 @@
 """Multi-GPU sharding of the hot path: one process per GPU, batches partitioned over ranks, and ONE
-collective — an all-reduce of the small integer tally block (NCCL over NVLink on GPUs, gloo in the CPU
-tests).  Photons are independent, so there is no data-path exchange; the reference's only parallelism
+collective on the small integer tally block — an all-gather when ranks own whole batches (disjoint rows), an
+all-reduce when they split photon ranges (NCCL over NVLink on GPUs, gloo in the CPU tests).  Photons are independent, so there is no data-path exchange; the reference's only parallelism
 is the same photon-level split over CPU processes (``scene.simulate(num_rays, workers)``, reference
 ``miniplant/simulation_runner.py:62``).
 
@@ -62,48 +62,82 @@ def all_reduce_tallies(tallies):
     return tallies
 
 
+def all_gather_rows(part, n_batches: int, rank: int, world: int):
+    """Rows of a round-robin partition (``shard_batches``) -> the full ``[n_batches, stride]`` block on every rank.
+
+    Every row has exactly one owner, so nothing needs adding: an all-gather moves half the bytes of the all-reduce it
+    replaces and does no arithmetic.  Ranks pad their share to ``ceil(n_batches / world)`` rows; rank r's i-th row is
+    batch ``r + i * world``."""
+    import torch
+    import torch.distributed as dist
+
+    per = -(-n_batches // world)
+    stride = part.shape[1]
+    padded = part
+    if part.shape[0] < per:
+        padded = torch.zeros((per, stride), dtype=part.dtype, device=part.device)
+        padded[:part.shape[0]] = part
+    if not (dist.is_available() and dist.is_initialized() and world > 1):
+        return padded[:n_batches].clone()
+    gathered = torch.empty((world, per, stride), dtype=part.dtype, device=part.device)
+    if dist.get_backend() == "nccl":
+        dist.all_gather_into_tensor(gathered.view(world * per, stride), padded.contiguous())
+    else:   # gloo (CPU tests)
+        dist.all_gather(list(gathered.unbind(0)), padded.contiguous())
+    return gathered.permute(1, 0, 2).reshape(per * world, stride)[:n_batches].contiguous()
+
+
 def trace_partitioned(n_batches: int, stride: int, photons_per_batch: int, trace_fn: Callable, rank: int, world: int,
                       by: str = "batch", device=None):
     """Run ``trace_fn(batch_indices, photon_begin, photon_count) -> int64 [len(batch_indices), stride]`` on
-    this rank's share and all-reduce into the full ``[n_batches, stride]`` block.
+    this rank's share and return the full ``[n_batches, stride]`` block on every rank.
 
-    ``by="batch"`` gives each rank whole batches (the drivers' thousands of time points);
-    ``by="photon"`` splits every batch's photon range (few, large batches)."""
+    ``by="batch"`` gives each rank whole batches (the drivers' thousands of time points): rows are disjoint, the
+    collective is an all-gather;  ``by="photon"`` splits every batch's photon range (few, large batches): rows add,
+    the collective is an all-reduce."""
     import torch
 
-    full = torch.zeros((n_batches, stride), dtype=torch.int64, device=device)
     if by == "batch":
         mine = shard_batches(n_batches, rank, world)
+        part = torch.zeros((0, stride), dtype=torch.int64, device=device)
         if len(mine):
-            part = trace_fn(mine, 0, int(photons_per_batch))
-            full[torch.as_tensor(mine, device=full.device)] = torch.as_tensor(part, device=full.device)
-    elif by == "photon":
+            part = torch.as_tensor(trace_fn(mine, 0, int(photons_per_batch)), device=device)
+        return all_gather_rows(part, n_batches, rank, world)
+    if by == "photon":
+        full = torch.zeros((n_batches, stride), dtype=torch.int64, device=device)
         begin, count = shard_photons(photons_per_batch, rank, world)
         if count:
             part = trace_fn(np.arange(n_batches, dtype=np.int64), begin, count)
             full += torch.as_tensor(part, device=full.device)
-    else:
-        raise ValueError("by must be 'batch' or 'photon'")
-    return all_reduce_tallies(full)
+        return all_reduce_tallies(full)
+    raise ValueError("by must be 'batch' or 'photon'")
 
 
-def trace_lights_distributed(arrays, lights: Sequence, photons_per_batch: int, seed: int, by: str = "batch"):
-    """CUDA tracing of ``lights`` sharded over the ranks of the initialised process group; every rank
-    returns the full reduced ``[n_batches, n_bins + N_COUNTERS]`` int64 tensor (on its GPU)."""
+def trace_lights_distributed(arrays, lights, photons_per_batch: int, seed: int, by: str = "batch"):
+    """CUDA tracing of ``lights`` (a sequence of ``LightArrays`` or a ``lights.BatchTable``) sharded over the ranks of
+    the initialised process group; every rank returns the full ``[n_batches, n_bins + N_COUNTERS]`` int64 tensor (on
+    its GPU).  ``seed`` must be the same on every rank (``miniplant.full_simulation.agreed_seed`` broadcasts one)."""
     import torch
     import torch.distributed as dist
 
     from . import backend
+    from .lights import BatchTable
 
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     device = torch.cuda.current_device()
     scene = backend.scene_handle(arrays, device)
+    table = isinstance(lights, BatchTable)
 
     def trace_fn(batch_indices, photon_begin, photon_count):
-        plan = backend.Plan(scene, [lights[int(b)] for b in batch_indices], [int(b) for b in batch_indices])
-        tallies = plan.new_tallies()
-        plan.trace_into(tallies, photon_count, seed, photon_begin)
+        with torch.cuda.device(device):
+            if table:
+                plan = backend.Plan(scene, lights.take(batch_indices))
+            else:
+                plan = backend.Plan(scene, [lights[int(b)] for b in batch_indices], [int(b) for b in batch_indices])
+            tallies = plan.new_tallies()
+            plan.trace_into(tallies, photon_count, seed, photon_begin)
+            torch.cuda.current_stream().synchronize()   # the plan's buffers must outlive the launch
         return tallies
 
     return trace_partitioned(len(lights), scene.stride, photons_per_batch, trace_fn, rank, world, by=by,

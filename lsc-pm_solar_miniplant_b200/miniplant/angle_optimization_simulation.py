@@ -12,7 +12,8 @@ from pathlib import Path
 import numpy as np
 
 from .. import lights as _lights
-from .full_simulation import trace_time_points
+from .full_simulation import is_rank_zero, trace_time_points, year_batches
+from ._csv import write_csv
 from .solar_data import solar_data_for_place_and_time
 from .utils import PhotonFactory  # noqa: F401
 
@@ -38,8 +39,7 @@ def evaluate_tilt_angle(tilt_angle: int, location, workers: int = None, time_res
     for stamp in solar_data.index[~valid]:
         print(f"skipping this point {stamp} due to low spectrum")
     rows = solar_data[valid]
-    batches = [_lights.direct_light(tilt_angle, r["apparent_elevation"], r["azimuth"], r["direct_spectrum"])
-               for _, r in rows.iterrows()]
+    batches = year_batches(tilt_angle, rows, diffuse=False) if len(rows) else []
     fractions = trace_time_points(tilt_angle, batches, RAYS_PER_SIMULATIONS, INCLUDE_DYE, seed, device, tracer)
     results.loc[valid, "simulation_direct"] = fractions
     results["direct_reacted"] = results["simulation_direct"] * results["direct_irradiance"]
@@ -50,9 +50,10 @@ def evaluate_tilt_angle(tilt_angle: int, location, workers: int = None, time_res
         if not INCLUDE_DYE:
             prefix += "_no_dye"
         target_file = Path(f"{prefix}_{np.abs(tilt_angle)}deg_results.csv")
-    target_file = Path(target_file)
-    target_file.parent.mkdir(parents=True, exist_ok=True)
-    results.to_csv(target_file, columns=("apparent_elevation", "azimuth", "simulation_direct", "direct_reacted"))
+    if is_rank_zero():
+        target_file = Path(target_file)
+        target_file.parent.mkdir(parents=True, exist_ok=True)
+        write_csv(results, target_file, columns=("apparent_elevation", "azimuth", "simulation_direct", "direct_reacted"))
     return results
 
 

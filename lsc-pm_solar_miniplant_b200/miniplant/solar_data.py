@@ -27,7 +27,9 @@ import pandas as pd
 
 from ..compat import pvlib_lite, pvtrace_namespace
 from ..workloads import SPECTRL2_SLICE_NM
-from .utils import spectral_distribution_to_photon_distribution
+from ..compat.pvtrace_api import LazyDistribution
+from ._csv import write_csv as _write_csv
+from .utils import irradiance_to_photon_flux, spectral_distribution_to_photon_distribution
 
 Distribution = pvtrace_namespace().Distribution
 
@@ -45,6 +47,12 @@ def _have_pvlib() -> bool:
         return not getattr(pvlib, "__lscpm_shim__", False)
     except Exception:
         return False
+
+
+def _is_rank_zero() -> bool:
+    import os
+
+    return int(os.environ.get("RANK", "0")) == 0
 
 
 def _photon_distribution(wavelengths, spectral_irradiance, integration_time):
@@ -86,29 +94,29 @@ def solar_data_for_place_and_time(site, tilt_angle: int, time_resolution: int = 
         poa_direct = spec["poa_direct"].T
         poa_sky = spec["poa_sky_diffuse"].T
 
-    direct_spectrum, diffuse_spectrum = [], []
-    direct_irr = np.full(len(solar_data), np.nan)
-    diffuse_irr = np.full(len(solar_data), np.nan)
-    for i in range(len(solar_data)):
-        # a negative ordinate (sun behind the plane) makes Distribution raise: the reference skips those rows (:93-104)
-        if np.any(poa_direct[i] < 0) or np.any(poa_sky[i] < 0) or not np.all(np.isfinite(poa_direct[i])):
-            direct_spectrum.append(None)
-            diffuse_spectrum.append(None)
-            continue
-        d = _photon_distribution(wavelengths, poa_direct[i], time_resolution)
-        s = _photon_distribution(wavelengths, poa_sky[i], time_resolution)
-        direct_spectrum.append(d)
-        diffuse_spectrum.append(s)
-        direct_irr[i] = np.trapezoid(d._y, d._x)
-        diffuse_irr[i] = np.trapezoid(s._y, s._x)
+    # All time points at once.  A negative ordinate (sun behind the plane) makes Distribution raise: the reference skips
+    # those rows (:93-104); they keep None / NaN here and fall out with the irradiance filter below.
+    poa_direct = np.asarray(poa_direct, dtype=float)
+    poa_sky = np.asarray(poa_sky, dtype=float)
+    ok = ~((poa_direct < 0).any(axis=1) | (poa_sky < 0).any(axis=1) | ~np.isfinite(poa_direct).all(axis=1))
+    wavelengths = np.asarray(wavelengths, dtype=float)
+    flux_direct = irradiance_to_photon_flux(poa_direct, wavelengths) * time_resolution     # utils.py:26-36, vectorised
+    flux_sky = irradiance_to_photon_flux(poa_sky, wavelengths) * time_resolution
+    direct_irr = np.where(ok, np.trapezoid(flux_direct, wavelengths, axis=1), np.nan)
+    diffuse_irr = np.where(ok, np.trapezoid(flux_sky, wavelengths, axis=1), np.nan)
+    direct_spectrum = np.empty(len(solar_data), dtype=object)
+    diffuse_spectrum = np.empty(len(solar_data), dtype=object)
+    for i in np.flatnonzero(ok):
+        direct_spectrum[i] = LazyDistribution(wavelengths, flux_direct[i])
+        diffuse_spectrum[i] = LazyDistribution(wavelengths, flux_sky[i])
     solar_data["direct_spectrum"] = direct_spectrum
     solar_data["diffuse_spectrum"] = diffuse_spectrum
     solar_data["direct_irradiance"] = direct_irr
     solar_data["diffuse_irradiance"] = diffuse_irr
     solar_data = solar_data[solar_data["direct_irradiance"] > 0].copy()
 
-    if write_csv:
-        solar_data.to_csv(f"Full_data_{site.name}.csv", columns=("apparent_zenith", "zenith", "apparent_elevation", "elevation",
+    if write_csv and _is_rank_zero():   # under torchrun every rank computes the table, one writes it
+        _write_csv(solar_data, f"Full_data_{site.name}.csv", columns=("apparent_zenith", "zenith", "apparent_elevation", "elevation",
                                                                  "azimuth", "airmass_relative", "aoi", "direct_irradiance",
                                                                  "diffuse_irradiance"))
     logger = logging.getLogger("pvtrace").getChild("miniplant")

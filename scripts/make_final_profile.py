@@ -20,10 +20,16 @@ tot = trace = 0.0
 for r in csv.reader(l for l in open(launches) if l.startswith('"')):
     if len(r) > 14 and r[12] == "gpu__time_duration.sum":
         t = float(r[14].replace(",", "")); tot += t
-        if "trace_kernel" in r[4] or "trace_sorted" in r[4]: trace += t
+        if "trace_kernel" in r[4] or "trace_sorted" in r[4] or "trace_pool" in r[4]: trace += t
 name = d[h.index("Kernel Name")] if "Kernel Name" in h else "trace_kernel"
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (source_digest: the sha256 bench.py checks before it reports these counters)
+head = subprocess.run(["git", "-C", ROOT, "rev-parse", "HEAD"], capture_output=True, text=True).stdout.strip()
+dirty = bool(subprocess.run(["git", "-C", ROOT, "status", "--porcelain", "--", "lsc-pm_solar_miniplant_b200/csrc", "include"],
+                            capture_output=True, text=True).stdout.strip())
 meta = {
     "kernel": name, "command": command,
+    "source_sha256": bench.source_digest(), "git_head": head + ("+uncommitted kernel sources" if dirty else ""),
     "photons_per_launch": 64000000,
     "gpu__time_duration_ms": g("gpu__time_duration.sum") * {"ms": 1, "us": 1e-3, "ns": 1e-6, "s": 1e3}[unit("gpu__time_duration.sum")],
     "dram__bytes_read.sum": g("dram__bytes_read.sum") * scale[unit("dram__bytes_read.sum")],

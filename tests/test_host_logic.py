@@ -183,3 +183,89 @@ def test_spectral_unit_conversion():
     assert irradiance_to_photon_flux(1.0, 500) == pytest.approx(500e-9 / (6.62607015e-34 * 299792458.0) / 6.02214076e23)
     d = spectral_distribution_to_photon_distribution(Distribution(np.array([400.0, 500.0]), np.array([1.0, 1.0])), 1800)
     assert d._y[1] / d._y[0] == pytest.approx(500 / 400)
+
+
+# ---- round 2: column-wise host stage ----------------------------------------------------------------------------------
+
+
+def test_fast_csv_is_byte_identical_to_pandas(tmp_path):
+    import pandas as pd
+    from lscpm_b200.miniplant._csv import write_csv
+
+    rng = np.random.default_rng(3)
+    for tz in ("Europe/Amsterdam", "Australia/Brisbane", "UTC", None):
+        index = pd.date_range("2020-03-28 22:00", periods=400, freq="1800s", tz=tz)      # spans a DST change
+        frame = pd.DataFrame({"apparent_elevation": rng.normal(30, 20, 400), "azimuth": rng.uniform(0, 360, 400),
+                              "simulation_direct": rng.integers(0, 121, 400) / 120.0, "count": rng.integers(0, 9, 400),
+                              "direct_reacted": rng.uniform(0, 1e-3, 400)}, index=index)
+        frame.iloc[5, 0] = np.nan
+        frame.iloc[7, 2] = 0.0
+        frame.iloc[9, 4] = 1e-320
+        cols = ("apparent_elevation", "azimuth", "simulation_direct", "count", "direct_reacted")
+        write_csv(frame, tmp_path / "fast.csv", cols)
+        frame.to_csv(tmp_path / "pandas.csv", columns=cols)
+        assert (tmp_path / "fast.csv").read_bytes() == (tmp_path / "pandas.csv").read_bytes(), tz
+    # anything the fast writer does not format itself goes through pandas
+    frame = pd.DataFrame({"a": ["x", "y"], "b": [1.0, 2.0]}, index=pd.RangeIndex(2))
+    write_csv(frame, tmp_path / "f.csv", ("a", "b"))
+    frame.to_csv(tmp_path / "p.csv", columns=("a", "b"))
+    assert (tmp_path / "f.csv").read_bytes() == (tmp_path / "p.csv").read_bytes()
+
+
+def test_batch_tables_equal_the_per_row_descriptors():
+    """lights.direct_batches / diffuse_batches (column-wise) against backend.batch_table over per-row LightArrays."""
+    from lscpm_b200 import _native as nat, backend, lights
+    from lscpm_b200.workloads import AM15_LIKE_W, SPECTRL2_SLICE_NM
+
+    assert nat.BATCH_DTYPE.itemsize == 176
+    rng = np.random.default_rng(5)
+    n = 37
+    elevation, azimuth = rng.uniform(1, 89, n), rng.uniform(60, 300, n)
+    flux = AM15_LIKE_W * SPECTRL2_SLICE_NM * rng.uniform(0.5, 1.5, (n, 1)) * rng.uniform(0.9, 1.1, (n, len(SPECTRL2_SLICE_NM)))
+    flux[11] = flux[3]      # a repeated spectrum is stored once
+    table = lights.BatchTable.concatenate([lights.direct_batches(-15.0, elevation, azimuth, flux=flux, x=SPECTRL2_SLICE_NM),
+                                           lights.diffuse_batches(-15.0, flux=flux[:5], x=SPECTRL2_SLICE_NM)])
+    rows = [lights.direct_light(-15.0, e, a, np.stack([SPECTRL2_SLICE_NM, f], axis=1)) for e, a, f in zip(elevation, azimuth, flux)]
+    rows += [lights.diffuse_light(-15.0, np.stack([SPECTRL2_SLICE_NM, f], axis=1)) for f in flux[:5]]
+    packed = backend.batch_table(rows)
+    assert len(table) == len(packed) == n + 5 and len(table.spectra) == n - 1 + 5
+    for field in ("light_kind", "batch_id", "wavelength_nm", "mask_half", "mask_pose", "direction", "back_off", "tilt_deg"):
+        assert np.array_equal(table.desc[field], packed.desc[field]), field
+    for i in range(len(table)):
+        assert np.array_equal(table.spectra[table.desc["spectrum"][i]], packed.spectra[packed.desc["spectrum"][i]])
+        light = table[i]
+        assert light.kind == rows[i].kind and np.array_equal(light.spectrum, rows[i].spectrum)
+        assert np.array_equal(light.direction, rows[i].direction) and np.array_equal(light.mask_pose, rows[i].mask_pose)
+    sub = table.take([40, 2, 7])
+    assert list(sub.desc["batch_id"]) == [40, 2, 7]
+    spectra = nat.PackedSpectra(table.spectra)
+    assert spectra.n == len(table.spectra) and spectra._begin[-1] == len(table.spectra) * len(SPECTRL2_SLICE_NM)
+
+
+def test_year_batches_column_wise_and_row_wise_agree():
+    import pandas as pd
+    from lscpm_b200 import backend, lights
+    from lscpm_b200.compat.pvtrace_api import Distribution
+    from lscpm_b200.miniplant.full_simulation import year_batches
+    from lscpm_b200.miniplant.solar_data import solar_data_from_positions
+
+    data = solar_data_from_positions([30.0, 45.0, 60.0], [150.0, 180.0, 210.0], 30, index=pd.RangeIndex(3))
+    fast = year_batches(30, data)
+    assert isinstance(fast, lights.BatchTable) and len(fast) == 6
+    data.at[1, "direct_spectrum"] = Distribution(np.array([360.0, 500.0, 690.0]), np.array([1.0, 2.0, 1.0]))   # other abscissae
+    slow = year_batches(30, data)
+    assert isinstance(slow, list) and len(slow) == 6
+    a, b = fast.desc, backend.batch_table(slow).desc
+    for field in ("light_kind", "batch_id", "mask_pose", "direction", "back_off", "tilt_deg"):
+        assert np.array_equal(a[field], b[field]), field
+
+
+def test_lazy_distribution_behaves_like_distribution():
+    from lscpm_b200.compat.pvtrace_api import Distribution, LazyDistribution
+    from lscpm_b200.workloads import am15_like_photon_spectrum
+
+    spec = am15_like_photon_spectrum()
+    a, b = Distribution(spec[:, 0], spec[:, 1]), LazyDistribution(spec[:, 0], spec[:, 1])
+    u = np.linspace(0, 1, 101)
+    assert np.array_equal(a.sample(u), b.sample(u)) and np.array_equal(a.lookup(spec[:, 0]), b.lookup(spec[:, 0]))
+    assert np.array_equal(a(500.0), b(500.0)) and isinstance(b, Distribution) and b.hist is False
