@@ -4,7 +4,7 @@ scenes outside the family (rejected loudly, never traced as something else)."""
 import numpy as np
 import pytest
 
-from helpers import assert_counts_agree, assert_tallies_agree, grouped, standard_scene
+from helpers import am15_like_photon_spectrum, assert_counts_agree, assert_tallies_agree, grouped, standard_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -186,3 +186,35 @@ def test_scenes_with_many_bins_share_the_kernel(built_library):
     other = backend.trace_lights(small, [small.light], n, seed=8, device=0)[0]
     again = backend.trace_lights(big, [big.light], n, seed=8, device=0)[0]
     assert first[:-2].sum() == n and other[:-2].sum() == n and np.array_equal(first, again)
+
+
+def test_plate_array_with_dense_channel_grid_one_plate_per_batch(native, built_library):
+    """BASELINE configs[4] in small: a 3 x 3 array of dense-grid plates (46 capillaries at 10 mm).  The plates of an array
+    are optically independent (photons are independent; the reference has no multi-plate scene), so every
+    plate is one batch with its own tilt, sun position, RNG stream and tally row; plates that share a tilt share a launch.
+    1e6 photons over the array, every plate's bins and pooled families against the oracle tracing the same plate."""
+    import c_oracle
+    from lscpm_b200 import backend, flatten, lights
+    from lscpm_b200.workloads import AM15_LIKE_W, SPECTRL2_SLICE_NM
+
+    photons = 111_112                                  # x 9 plates = 1e6
+    flux = (AM15_LIKE_W * SPECTRL2_SLICE_NM)[None, :].repeat(3, axis=0)
+    plate = 0
+    for row, tilt in enumerate((0.0, 20.0, 40.0)):     # one row of the array per tilt
+        scene = standard_scene(tilt=tilt, elevation=60, azimuth=180, spectrum=am15_like_photon_spectrum(), capillary_count=46, capillary_pitch=0.01)
+        arrays = flatten.flatten_scene(scene)
+        names = arrays.bin_names()
+        elevation = np.array([25.0, 50.0, 75.0]) + row
+        azimuth = np.array([120.0, 180.0, 235.0]) - 3 * row
+        table = lights.direct_batches(tilt, elevation, azimuth, flux=flux, x=SPECTRL2_SLICE_NM, first_batch_id=3 * row)
+        rows = backend.trace_lights(arrays, table, photons, seed=31, device=0)
+        assert rows.shape == (3, len(names) + 2) and np.all(rows[:, :len(names)].sum(axis=1) == photons)
+        oracle = c_oracle.COracle(native, native.PackedScene(arrays))
+        for i in range(3):
+            light = table[i]
+            batches, _ = backend.pack_batches([light], [plate])
+            ref = oracle.trace(batches[0], spectra=[light.spectrum], photon_count=photons, seed=900 + plate)
+            assert_tallies_agree(names, rows[i][:len(names)], ref[:len(names)], label=f"plate {plate} (tilt {tilt})",
+                                 resample=lambda i=i: backend.trace_lights(arrays, table, photons, seed=77, device=0)[i][:len(names)])
+            plate += 1
+    assert plate == 9

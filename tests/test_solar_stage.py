@@ -209,15 +209,18 @@ def test_oracle_against_the_reference_yearly_results():
             assert abs(z) < 4.0, (dye, column, z, p_ours.mean(), p_ref.mean())
 
 
-def test_experimental_conditions_script_window():
-    """reference experimental_comparison/simulate_experimental_conditions.py: the script's window, built with
-    ``Location.pytz.localize``, selects the six half-hour points of the committed result CSV."""
-    from miniplant.experimental_comparison import simulate_experimental_conditions as script
+def test_experimental_conditions_window():
+    """The 15 July 2020 15:00-17:30 window of the reference's 1e4-photon run (its experimental_comparison script builds it
+    with ``Location.pytz.localize``): the solar stage yields exactly the six half-hour points of the committed result CSV."""
+    import datetime
+
     from miniplant.locations import EINDHOVEN
     from miniplant.solar_data import solar_data_for_place_and_time
 
-    assert script.XP_START.utcoffset().total_seconds() == 7200 and script.target_file.name == "experimental_conditions_results.csv"
+    start = EINDHOVEN.pytz.localize(datetime.datetime(2020, 7, 15, 15, 0))
+    end = EINDHOVEN.pytz.localize(datetime.datetime(2020, 7, 15, 17, 30))
+    assert start.utcoffset().total_seconds() == 7200
     frame = solar_data_for_place_and_time(EINDHOVEN, 40, 1800, write_csv=False)
-    window = frame.loc[script.time_interval[0]: script.time_interval[1]]
+    window = frame.loc[start: end]
     exp = pd.read_csv(os.path.join(GOLDEN, "reference_experimental_conditions.csv"), index_col=0)
     assert [str(t) for t in window.index] == list(exp.index)
