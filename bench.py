@@ -298,6 +298,120 @@ def measure_drivers(device) -> dict:
     return out
 
 
+def run_config4(args) -> None:
+    """Strong scaling of ONE fixed job over N GPUs (BASELINE configs[3]): the Eindhoven 40 deg year, 16 096 batches (8 048
+    half-hour points x {direct, sky-diffuse}, each with its own SPECTRL2 spectrum) x `--photons` photons, batches dealt
+    round-robin to the ranks, one all-gather of the tally rows per job.  `value`: device-timed, descriptors resident;
+    `e2e`: wall time of `yearlong_simulation` under the process group - every rank runs the (replicated) solar stage,
+    traces its share, gathers; rank 0 writes the CSV."""
+    import tempfile
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import lscpm_b200
+
+    lscpm_b200.install()
+    from lscpm_b200 import _native as nat, backend, distributed
+    from lscpm_b200.miniplant import full_simulation as fs
+    from lscpm_b200.miniplant.locations import EINDHOVEN
+    from lscpm_b200.miniplant.solar_data import solar_data_for_place_and_time
+
+    rank, local_rank, world = distributed.init_process_group()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device visible; the traced path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.cuda.current_device()
+    dev = f"cuda:{device}"
+    lib = nat.load()
+    ppb = args.photons
+    data = solar_data_for_place_and_time(EINDHOVEN, 40, 1800, write_csv=False)
+    table = fs.year_batches(40, data)
+    arrays = fs.plate_geometry(40, True)
+    scene = backend.scene_handle(arrays, device)
+    n = len(table)
+    rows = distributed.shard_batches(n, rank, world)
+    plan = backend.Plan(scene, table.take(rows))
+    part = plan.new_tallies()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def job(seed):
+        part.zero_()
+        plan.trace_into(part, ppb, seed)
+        return distributed.all_gather_rows(part, n, rank, world)
+
+    for w in range(max(args.warmup, 3)):
+        full = job(100 + w)
+    barrier()
+    launches0 = lib.lscpm_launch_count()
+    step_ms = []
+    with ClockSampler(local_rank) as sampler:
+        barrier()
+        t_begin = time.perf_counter()
+        for k in range(args.steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            full = job(500 + k)
+            e1.record()
+            torch.cuda.synchronize()
+            step_ms.append(e0.elapsed_time(e1))
+        barrier()
+        t_end = time.perf_counter()
+    launches = lib.lscpm_launch_count() - launches0
+    clocks = sampler.summary(t_begin, t_end)
+    tallies = full.cpu().numpy()
+    n_bins = scene.n_bins
+    assert (tallies[:, :n_bins].sum(axis=1) == ppb).all(), "every batch's bins must sum to its photons"
+    events_per_photon = float(tallies[:, n_bins].sum()) / (n * ppb)
+
+    # end to end: the driver a user runs, every step
+    e2e_steps = max(1, min(args.steps, 5))
+    tmp = tempfile.mkdtemp()
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        fs.yearlong_simulation(40, EINDHOVEN, num_photons_per_simulation=ppb, target_file=os.path.join(tmp, f"w{rank}.csv"), seed=1)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            res = fs.yearlong_simulation(40, EINDHOVEN, num_photons_per_simulation=ppb, target_file=os.path.join(tmp, "year.csv"), seed=10 + k)
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+    finally:
+        os.chdir(cwd)
+    t_max = torch.tensor([sum(step_ms) / len(step_ms), e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    ms_per_step, ms_e2e = (float(x) for x in t_max.cpu())
+    if rank == 0:
+        total = n * ppb
+        line = {
+            "metric": METRIC, "value": total / (ms_per_step * 1e-3), "unit": "photons/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[3]: full_simulation, Eindhoven tilt 40 deg, 2020 at 30 min resolution: {n} batches "
+                                   f"({n // 2} time points x direct + sky-diffuse, own SPECTRL2 spectrum each) x {ppb} photons = "
+                                   f"{total:.3g} photons per job, FIXED for every N",
+                       "l2": "inputs larger than L2 are not involved: photon state lives on chip; tallies 30 MB per job",
+                       "parallelism": f"batch-dp{world} (round-robin)", "collective": "one all-gather of the tally rows per job"},
+            "photon_events_per_s": total * events_per_photon / (ms_per_step * 1e-3), "events_per_photon": events_per_photon,
+            "e2e": {"value": total / (ms_e2e * 1e-3), "unit": "photons/s", "wall_s_per_job": ms_e2e * 1e-3, "steps": e2e_steps,
+                    "h2d_bytes_per_step": int(lib.lscpm_plan_h2d_bytes(plan.handle)), "d2h_bytes_per_step": int(tallies.nbytes),
+                    "api": "miniplant.full_simulation.yearlong_simulation (solar stage on every rank, sharded trace, all-gather, CSV on rank 0)",
+                    "yearly_mean_reacted_direct": float(np.mean(res["simulation_direct"]))},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        emit(line)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_cuda(args) -> None:
     import numpy as np
     import torch
@@ -508,14 +622,17 @@ def main() -> None:
     ap.add_argument("--cpu-photons", type=int, default=0, help="photons of the bounded CPU sample (0: calibrate to ~10 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-drivers", action="store_true", help="skip the driver-level (config 4) and latency measurements")
-    ap.add_argument("--workload", choices=("config2", "config5"), default="config2",
-                    help="config2 (default, the bench contract line) or config5 (dense-grid plate array)")
+    ap.add_argument("--workload", choices=("config2", "config4", "config5"), default="config2",
+                    help="config2 (default, the bench contract line), config4 (the Eindhoven year as ONE fixed job: strong "
+                         "scaling; use --photons 100000) or config5 (dense-grid plate array)")
     args = ap.parse_args()
     global WORKLOAD
     WORKLOAD = args.workload
     claim_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif WORKLOAD == "config4":
+        run_config4(args)
     else:
         run_cuda(args)
 

@@ -87,6 +87,7 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
     unsigned c_next = 0, c_end = 0;
     int cbatch = 0;
     bool more = true;                       // work items may remain in the global queue
+    unsigned items_since_flush = 0u;
 
     Photon p;
     Rng rng;
@@ -136,9 +137,12 @@ trace_kernel(const __grid_constant__ DevScene S, const __grid_constant__ TraceAr
                 chunk_base = A.photon_begin + first;
                 c_next = 0;
                 c_end = (unsigned)min((unsigned long long)A.chunk, A.photon_count - first);
-                if (cbatch != hbatch) {
+                // the 32-bit shared row is flushed when the batch changes and, within one batch, every 256 work items
+                // (<= 1M photons): a single huge batch cannot wrap its event counters
+                if (cbatch != hbatch || ++items_since_flush >= 256u) {
                     if (hbatch >= 0) flush_row(hist, A.tallies + (size_t)hbatch * stride, stride, lane);
                     hbatch = cbatch;
+                    items_since_flush = 0u;
                 }
             }
             const unsigned avail = c_end - c_next;
@@ -250,6 +254,7 @@ trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ 
     __syncthreads();
     int hbatch = -1;                        // block-uniform: batch whose photons the shared row accumulates
     int it = 0;                             // iteration parity selects the cursor copy
+    unsigned iterations = 0u;
 
     Photon p;
     p.xr = p.y = p.z = p.dx = p.dy = p.dz = p.wl = p.a_plate = p.a_outer = p.a_inner = 0.f;
@@ -306,7 +311,8 @@ trace_sorted_kernel(const __grid_constant__ DevScene S, const __grid_constant__ 
         LSCPM_CHECK(dest >= 0 && dest < BLOCK);
         // ---- the shared tally row follows the batch of the current work item --------------------------
         const int target = sm.cursor[it].cur_batch;
-        if (target != hbatch) {
+        // also every 2^14 iterations (<= 4M photon-steps per block): a single huge batch cannot wrap the 32-bit row
+        if (target != hbatch || (++iterations & 0x3fffu) == 0u) {
             if (hbatch >= 0) {
                 unsigned long long* row = A.tallies + (size_t)hbatch * stride;
                 for (int b = tid; b < stride; b += BLOCK) {

@@ -25,7 +25,7 @@ for r in csv.reader(src.splitlines()):
     except ValueError: pass
 tot = sum(v[0] for v in agg.values()) or 1; tots = sum(v[2] for v in agg.values()) or 1
 root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lsc-pm_solar_miniplant_b200", "csrc")
-srcs = {f: open(os.path.join(root, f)).read().split('\n') for f in ('lscpm.cu', 'lscpm_device.cuh')}
+srcs = {f: open(os.path.join(root, f)).read().split('\n') for f in ('lscpm.cu', 'lscpm_device.cuh', 'lscpm_pool.cuh')}
 print(f"total warp-inst {tot}, thread-inst {sum(v[1] for v in agg.values())}")
 for (f, l), v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
     text = srcs[f][l - 1].strip()[:84] if f in srcs and l - 1 < len(srcs[f]) else ''
