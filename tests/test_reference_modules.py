@@ -255,6 +255,45 @@ def test_reference_shaped_pv_scene_returns_the_five_tuple(built_library):
     assert isinstance(out, tuple) and len(out) == 5 and out[3] > 0 and out[4] > 0 and 0.2 <= out[0] <= 0.4
 
 
+def _pvtrace_style_runner(scene, num_photons, workers):
+    """The pvtrace object API exactly as the reference's runner consumes it (reference simulation_runner.py:38-48,62-66),
+    written against the names ``compat.install()`` registers under ``pvtrace``: per ray ``scene.emit`` ->
+    ``photon_tracer.follow`` -> last event + ``next_hit`` of the last ray; or ``scene.simulate`` for ``workers > 1``."""
+    import collections
+
+    from pvtrace import Event, photon_tracer
+    from pvtrace.algorithm.photon_tracer import next_hit
+
+    pv_hits = collections.Counter()
+    if workers == 1:
+        finals = []
+        for ray in scene.emit(num_photons):
+            history = photon_tracer.follow(scene, ray)
+            rays, events = zip(*history)
+            finals.append(events[-1])
+            ahead = next_hit(scene, history[-1][0])
+            if ahead:
+                pv_hits[ahead[0].name] += 1
+    else:
+        finals = [photon[-1][1] for photon in scene.simulate(num_rays=num_photons, workers=workers)]
+    return collections.Counter(finals)[Event.REACT] / num_photons, pv_hits
+
+
+@pytest.mark.gpu
+def test_pvtrace_object_api_on_reference_shaped_scenes(built_library):
+    """What travels to the GPU box of the next test: the seam the reference's runner uses (emit / follow / next_hit /
+    simulate / Event.REACT), on scenes whose lights expose only what the reference's classes expose."""
+    bulk, _ = _pvtrace_style_runner(reference_shaped_scene("direct", 40, 50, 180, green_photons), 100_000, workers=2)
+    assert 0.22 <= bulk <= 0.38
+    per_ray, _ = _pvtrace_style_runner(reference_shaped_scene("direct", 40, 50, 180, green_photons), 600, workers=1)
+    assert abs(per_ray - bulk) < 4 * np.sqrt(bulk * (1 - bulk) / 600)
+    diffuse, _ = _pvtrace_style_runner(reference_shaped_scene("diffuse", 0, wavelength=green_photons), 100_000, workers=2)
+    assert 0.22 <= diffuse <= 0.38
+    scene = reference_shaped_scene("direct", 40, 50, 180, green_photons, add_bottom_PV=True, add_side_PV=True)
+    _, pv_hits = _pvtrace_style_runner(scene, 400, workers=1)
+    assert pv_hits["bottomPV"] > 0 and sum(pv_hits[f"sidePV{i}"] for i in range(1, 5)) > 0
+
+
 @pytest.mark.gpu
 def test_reference_runner_unmodified_through_the_backend(built_library, reference_modules):
     """INTEGRATION.md §3, literally: the reference's simulation_runner + scene_creator + utils, unmodified, traced by
