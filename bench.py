@@ -293,6 +293,20 @@ def measure_drivers(device) -> dict:
         run_direct_simulation(tilt_angle=40, solar_elevation=20 + (k % 50), solar_azimuth=180, num_photons=100, seed=k, device=device)
         laps.append(time.perf_counter() - t0)
     laps.sort()
+    import random
+
+    rng = random.Random(3)
+
+    def two_lines():
+        return rng.choice([555, 585])
+
+    run_direct_simulation(tilt_angle=0, solar_elevation=90, solar_spectrum_function=two_lines, num_photons=200, seed=1, device=device)
+    t0 = time.perf_counter()
+    run_direct_simulation(tilt_angle=0, solar_elevation=90, solar_spectrum_function=two_lines, num_photons=20_000, seed=2, device=device)
+    dt = time.perf_counter() - t0
+    out["host_emitted_light"] = {"call": "run_direct_simulation with an arbitrary wavelength callable: the rays are emitted by the scene's "
+                                         "own Python callables (scene.emit) and traced by follow_kernel, one thread per ray",
+                                 "photons": 20_000, "wall_s": dt, "photons_per_s": 20_000 / dt}
     out["latency"] = {"call": "run_direct_simulation(num_photons=100), a new sun position per call", "calls": len(laps),
                       "median_ms": 1e3 * laps[len(laps) // 2], "p90_ms": 1e3 * laps[int(0.9 * len(laps))]}
     return out

@@ -166,18 +166,23 @@ int lscpm_trace(LscpmScene* scene, const LscpmBatchDesc* batches, int32_t n_batc
                 const LscpmSpectraDesc* spectra, uint64_t photon_begin, uint64_t photon_count,
                 uint64_t seed, int64_t* tallies_dev, void* stream);
 
-/* Host-buffer convenience: zeroes a device tally block, launches, copies the rows back into
- * tallies_host[n_batches*(n_bins+LSCPM_N_COUNTERS)] and synchronises.  This is the call behind
- * _common_simulation_runner (reference miniplant/simulation_runner.py:65-66 reads count[REACT]/N). */
+/* Host buffers in, host tallies out: lowers the descriptors into the scene's pinned staging buffer, uploads them with
+ * one copy, zeroes a tally block in the scene's device scratch, launches, copies the rows back into
+ * tallies_host[n_batches*(n_bins+LSCPM_N_COUNTERS)] and synchronises (the scene's own stream; no allocation per call
+ * once the scratch has grown to the job's size; calls on one scene are serialised by a mutex).  This is the call behind
+ * _common_simulation_runner (reference miniplant/simulation_runner.py:65-66 reads count[REACT]/N) and behind the
+ * drivers' one launch per year (full_simulation.py:64-106). */
 int lscpm_trace_host(LscpmScene* scene, const LscpmBatchDesc* batches, int32_t n_batches,
                      const LscpmSpectraDesc* spectra, uint64_t photon_begin, uint64_t photon_count,
                      uint64_t seed, int64_t* tallies_host);
 
 /* ---- resident batch plans --------------------------------------------------------------------- */
 /* The drivers trace thousands of time points (reference miniplant/full_simulation.py:106 applies one
- * simulation per DataFrame row).  A plan lowers and uploads the batch descriptors and spectra once, so
- * that repeated launches (more photons, other seeds, other photon ranges) start from inputs already
- * resident in device memory.  lscpm_trace == plan_create + trace_plan + plan_destroy. */
+ * simulation per DataFrame row).  A plan lowers and uploads the batch descriptors and spectra once (ONE device
+ * allocation, ONE copy from pinned memory), so that repeated launches (more photons, other seeds, other photon
+ * ranges) start from inputs already resident in device memory.  lscpm_trace == plan_create + trace_plan +
+ * plan_destroy.  `batches` may be any contiguous LscpmBatchDesc[n] - the Python binding passes a structured
+ * NumPy array with this layout, filled column-wise. */
 typedef struct LscpmPlan LscpmPlan;
 int lscpm_plan_create(LscpmScene* scene, const LscpmBatchDesc* batches, int32_t n_batches,
                       const LscpmSpectraDesc* spectra, LscpmPlan** out);

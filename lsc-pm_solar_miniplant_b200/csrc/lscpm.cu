@@ -612,6 +612,13 @@ __global__ void follow_kernel(const __grid_constant__ DevScene S, const FollowIn
             FollowStep& s = steps[(size_t)i * max_steps + k];
             s.x = abs_x(S, p); s.y = p.y; s.z = p.z + S.zc; s.dx = p.dx; s.dy = p.dy; s.dz = p.dz; s.wl = p.wl;
             s.event = so.event; s.medium = so.medium; s.ch = so.ch; s.kind = so.kind; s.face = so.face;
+            if (ext && so.event == EV_ABSORB && so.medium == MED_AIR && so.ch > 0) {
+                // absorbed inside an opaque outside box (alpha ~1e10 m^-1: within 1e-10 m of its face).  The photon state
+                // keeps the face point; the RECORD is placed 1e-7 m inside, so that the reference's
+                // next_hit(scene, last_ray) (simulation_runner.py:45-53) starts inside the box it names - also for the side
+                // PVs, whose entry face coincides with the plate's edge face (1e-10 m is below FP32 resolution here)
+                s.x = fmaf(1e-7f, p.dx, s.x); s.y = fmaf(1e-7f, p.dy, s.y); s.z = fmaf(1e-7f, p.dz, s.z);
+            }
         }
         ++k;
     }
@@ -762,8 +769,12 @@ struct LscpmScene {
     unsigned short *d_tab_fwd = nullptr, *d_tab_inv = nullptr;
     int *d_abs_outer = nullptr, *d_abs_inner = nullptr, *d_exit_outer = nullptr, *d_exit_inner = nullptr;
     int axis_sign = 0;              // +1: the capillaries' local +z axis points along the plate's +y
-    unsigned long long* d_counters = nullptr;   // ring of work counters
+    unsigned long long* d_counters = nullptr;   // ring of work counters, one per launch in flight
     std::atomic<unsigned> next_counter{0};
+    // one event per ring slot, recorded behind the launch that used it: the launch that takes the slot over waits for it
+    // (device-side, cudaStreamWaitEvent), so a counter is never zeroed under a kernel that still reads it
+    cudaEvent_t counter_event[256] = {};
+    std::mutex counter_mutex;
     int n_sm = 0, blocks_per_sm = 0;
     int trace_block = TRACE_BLOCK_BIG;   // threads per block of the lane kernel
     size_t trace_smem = 0;
@@ -1104,10 +1115,22 @@ TraceKernel pool_kernel(const LscpmScene* s) {
     return s->flight ? trace_pool_kernel<true, POOL_A_WARPS, POOL_A_SLOTS> : trace_pool_kernel<false, POOL_A_WARPS, POOL_A_SLOTS>;
 }
 
-int pick_counter(LscpmScene* s, cudaStream_t stream, unsigned long long** out) {
+int pick_counter(LscpmScene* s, cudaStream_t stream, unsigned long long** out, unsigned* slot_out) {
     const unsigned slot = s->next_counter.fetch_add(1) % COUNTER_RING;
     *out = s->d_counters + slot;
+    *slot_out = slot;
+    {
+        std::lock_guard<std::mutex> lock(s->counter_mutex);
+        if (s->counter_event[slot]) CUDA_TRY(cudaStreamWaitEvent(stream, s->counter_event[slot], 0));
+        else CUDA_TRY(cudaEventCreateWithFlags(&s->counter_event[slot], cudaEventDisableTiming));
+    }
     CUDA_TRY(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), stream));
+    return LSCPM_OK;
+}
+
+int release_counter(LscpmScene* s, cudaStream_t stream, unsigned slot) {
+    std::lock_guard<std::mutex> lock(s->counter_mutex);
+    CUDA_TRY(cudaEventRecord(s->counter_event[slot], stream));
     return LSCPM_OK;
 }
 
@@ -1367,6 +1390,7 @@ int lscpm_scene_destroy(LscpmScene* s) {
     if (!s) return LSCPM_OK;
     cudaFree(s->d_tab_x); cudaFree(s->d_tab_y); cudaFree(s->d_tab_cdf); cudaFree(s->d_tab_fwd); cudaFree(s->d_tab_inv);
     cudaFree(s->d_abs_outer); cudaFree(s->d_abs_inner); cudaFree(s->d_exit_outer); cudaFree(s->d_exit_inner); cudaFree(s->d_counters);
+    for (cudaEvent_t ev : s->counter_event) if (ev) cudaEventDestroy(ev);
     if (s->h_scratch) cudaFreeHost(s->h_scratch);
     if (s->d_scratch) cudaFree(s->d_scratch);
     if (s->scratch_stream) cudaStreamDestroy(s->scratch_stream);
@@ -1459,7 +1483,8 @@ void plan_point(LscpmPlan* p, unsigned char* d_blob, const PlanLayout& L) {
 int scratch_reserve(LscpmScene* s, size_t host_bytes, size_t dev_bytes) {
     if (!s->scratch_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->scratch_stream, cudaStreamNonBlocking));
     if (host_bytes > s->h_scratch_bytes) {
-        if (s->h_scratch) cudaFreeHost(s->h_scratch);
+        for (cudaEvent_t ev : s->counter_event) if (ev) cudaEventDestroy(ev);
+    if (s->h_scratch) cudaFreeHost(s->h_scratch);
         s->h_scratch = nullptr; s->h_scratch_bytes = 0;
         const size_t want = std::max<size_t>(host_bytes + host_bytes / 2, 64 * 1024);
         CUDA_TRY(cudaMallocHost((void**)&s->h_scratch, want));
@@ -1548,7 +1573,8 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
     a.chunk = (unsigned)chunk;
     a.chunks_per_batch = (photon_count + chunk - 1) / chunk;
     a.n_chunks = a.chunks_per_batch * (unsigned long long)p->n_batches;
-    int rc = pick_counter(s, stream, &a.work_counter);
+    unsigned counter_slot = 0;
+    int rc = pick_counter(s, stream, &a.work_counter, &counter_slot);
     if (rc) return rc;
     if (sorted) {
         // a block drinks from two work items at a time; tiny launches need fewer blocks than the grid
@@ -1563,6 +1589,7 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
     }
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
+    if ((rc = release_counter(s, stream, counter_slot))) return rc;
 #ifdef SORT_TIMING
     if (sorted) {
         unsigned long long t[64];
