@@ -591,7 +591,7 @@ def run_cuda(args) -> None:
                              "active_lanes_per_warp_instruction": ncu["smsp__thread_inst_executed_per_inst_executed.ratio"],
                              "warp_instructions_per_launch": ncu["smsp__inst_executed.sum"],
                              "source": "profiles/r2_final_metrics.json", "git_head": ncu.get("git_head")},
-                         "kernel": "trace_pool_kernel" if os.environ.get("LSCPM_TRACE_KERNEL", "pool").startswith("pool") else "trace_kernel",
+                         "kernel": scene.kernel_name,
                          "ms_per_launch": ms_kernel,
                          "how": f"events/s/GPU x {I_EVT} lane-instr/event (SURVEY 8d) / (n_SM {n_sm} x 128 x {sm_clock:.0f} MHz sampled)"},
             "roofline_hbm": {"bound": "hbm", "achieved": events_per_s_gpu * BYTES_PER_EVENT / 1e9, "peak": peaks["hbm_gbs"],

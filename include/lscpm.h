@@ -148,6 +148,9 @@ int lscpm_scene_destroy(LscpmScene* scene);
 int lscpm_scene_n_bins(const LscpmScene* scene);
 /* Writes the NUL-terminated name of bin `bin` into buf (truncating); returns its full length. */
 int lscpm_scene_bin_name(const LscpmScene* scene, int bin, char* buf, int buf_len);
+/* Which trace kernel launches on this scene use (chosen at lscpm_scene_create from the scene family and shared-memory
+ * needs), as text for benchmark records: writes the NUL-terminated name, returns its length. */
+int lscpm_scene_kernel_name(const LscpmScene* scene, char* buf, int buf_len);
 /* Same layout computed from a description alone (no device needed). */
 int lscpm_desc_n_bins(const LscpmSceneDesc* desc);
 int lscpm_desc_bin_name(const LscpmSceneDesc* desc, int bin, char* buf, int buf_len);

@@ -202,6 +202,7 @@ _SIGNATURES = {
     "lscpm_scene_destroy": (C.c_int, [C.c_void_p]),
     "lscpm_scene_n_bins": (C.c_int, [C.c_void_p]),
     "lscpm_scene_bin_name": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_int]),
+    "lscpm_scene_kernel_name": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "lscpm_desc_n_bins": (C.c_int, [C.POINTER(SceneDesc)]),
     "lscpm_desc_bin_name": (C.c_int, [C.POINTER(SceneDesc), C.c_int, C.c_char_p, C.c_int]),
     "lscpm_trace": (C.c_int, [C.c_void_p, C.POINTER(BatchDesc), C.c_int32, C.POINTER(SpectraDesc), C.c_uint64,

@@ -64,6 +64,13 @@ class SceneHandle:
         self.stride = self.n_bins + nat.N_COUNTERS
         weakref.finalize(self, self.lib.lscpm_scene_destroy, handle)
 
+    @property
+    def kernel_name(self) -> str:
+        """The trace kernel launches on this scene use (``lscpm_scene_kernel_name``)."""
+        buf = C.create_string_buffer(256)
+        nat.check(self.lib, min(self.lib.lscpm_scene_kernel_name(self.handle, buf, 256), 0))
+        return buf.value.decode("utf8")
+
     def _bin_name(self, b: int) -> str:
         buf = C.create_string_buffer(256)
         n = self.lib.lscpm_scene_bin_name(self.handle, b, buf, 256)

@@ -783,8 +783,8 @@ struct LscpmScene {
     bool flight = false;                 // plate flights (scenes without outside boxes whose plate holds a luminophore)
     int sort_blocks_per_sm = 0;
     size_t sort_smem = 0;
-    int pool = 0;                        // pool kernel configuration: 0 off, 1 = 24 warps x 96 records, 2 = 32 warps x 64 records
-    size_t pool_smem = 0;
+    int pool = 0;                        // pool kernel configuration (PoolConfig), 0: lane / sorted kernel
+    int pool_small_plan = 0;             // configuration for launches whose plan fits the small L1 (0: same as `pool`)
     // scratch of the host-buffer entry points (lscpm_trace_host, plan staging): one pinned host buffer, one device
     // buffer and one stream per scene, grown on demand and reused, so a call costs no allocation
     std::mutex scratch_mutex;
@@ -1107,12 +1107,29 @@ TraceKernel sorted_kernel(const LscpmScene* s) {
     return s->flight ? trace_sorted_kernel<false, true, SORT_THREADS> : trace_sorted_kernel<false, false, SORT_THREADS>;
 }
 
-constexpr int POOL_A_WARPS = 24, POOL_A_SLOTS = 96, POOL_B_WARPS = 32, POOL_B_SLOTS = 64;
-int pool_warps(const LscpmScene* s) { return s->pool == 2 ? POOL_B_WARPS : POOL_A_WARPS; }
-int pool_slots(const LscpmScene* s) { return s->pool == 2 ? POOL_B_SLOTS : POOL_A_SLOTS; }
-TraceKernel pool_kernel(const LscpmScene* s) {
-    if (s->pool == 2) return s->flight ? trace_pool_kernel<true, POOL_B_WARPS, POOL_B_SLOTS> : trace_pool_kernel<false, POOL_B_WARPS, POOL_B_SLOTS>;
-    return s->flight ? trace_pool_kernel<true, POOL_A_WARPS, POOL_A_SLOTS> : trace_pool_kernel<false, POOL_A_WARPS, POOL_A_SLOTS>;
+// pool kernel configurations: records per warp decide the lanes per phase execution (120: 31.8 of 32, 96: 31, 80: 29,
+// 64: 26) and are limited by shared memory; what shared memory takes, the L1 loses (up to 196 KB leaves 60 KB of L1, more
+// leaves 28 KB).  Measured (one B200, ms per job; profiles/r2_pool_records_ab.txt):
+//                                              120 rec.   112     96      80     lanes (K2)
+//   config 2 (64 batches, one spectrum)          7.48     7.52    7.67    8.05   10.06
+//   config 4 (16 096 batches, 16 096 spectra)   197.8    198.7   195.1     -
+//   config 5 (dense grid: 702 counters per row)  (does not fit)   8.45    8.90   11.72
+// so: 96 records by default (fewer for scenes whose per-warp tally rows are very wide), 120 for launches whose batch
+// descriptors and spectra are small enough to live in the 28 KB L1 beside the scene tables.  The 28-warp x 80-record
+// configuration (72 registers) measured 7.94 ms on config 2: more warps do not buy back the lanes fewer records lose.
+constexpr int POOL_WARPS = 24, POOL_WARPS_WIDE = 32;
+constexpr size_t POOL_SMALL_PLAN_BYTES = 16 * 1024;
+enum PoolConfig { POOL_OFF = 0, POOL_96 = 1, POOL_WIDE_64 = 2, POOL_80 = 3, POOL_64 = 4, POOL_120 = 7 };
+int pool_warps(int cfg) { return cfg == POOL_WIDE_64 ? POOL_WARPS_WIDE : POOL_WARPS; }
+int pool_slots(int cfg) { return cfg == POOL_120 ? 120 : (cfg == POOL_96 ? 96 : (cfg == POOL_80 ? 80 : 64)); }
+TraceKernel pool_kernel(const LscpmScene* s, int cfg) {
+    switch (cfg) {
+        case POOL_120: return s->flight ? trace_pool_kernel<true, POOL_WARPS, 120> : trace_pool_kernel<false, POOL_WARPS, 120>;
+        case POOL_96: return s->flight ? trace_pool_kernel<true, POOL_WARPS, 96> : trace_pool_kernel<false, POOL_WARPS, 96>;
+        case POOL_80: return s->flight ? trace_pool_kernel<true, POOL_WARPS, 80> : trace_pool_kernel<false, POOL_WARPS, 80>;
+        case POOL_64: return s->flight ? trace_pool_kernel<true, POOL_WARPS, 64> : trace_pool_kernel<false, POOL_WARPS, 64>;
+        default: return s->flight ? trace_pool_kernel<true, POOL_WARPS_WIDE, 64> : trace_pool_kernel<false, POOL_WARPS_WIDE, 64>;
+    }
 }
 
 int pick_counter(LscpmScene* s, cudaStream_t stream, unsigned long long** out, unsigned* slot_out) {
@@ -1360,27 +1377,35 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
     }
     // The pool kernel (warp-private photon pools, lscpm_pool.cuh) is the default for scenes without outside boxes whose
     // plate re-emits: that is where photons live long enough for the phase lists to stay full.
-    // LSCPM_TRACE_KERNEL=pool|pool96|pool64 forces it (bit-identical tallies in every configuration).
-    s->pool = 0;
+    // LSCPM_TRACE_KERNEL=pool|pool96|pool80|pool64 forces it (bit-identical tallies in every configuration).
+    s->pool = POOL_OFF;
+    s->pool_small_plan = POOL_OFF;
     if (s->dev.n_ext == 0) {
-        if (s->flight) s->pool = 1;
-        if (which && (strcmp(which, "lanes") == 0 || strcmp(which, "sorted") == 0)) s->pool = 0;
-        if (which && (strcmp(which, "pool") == 0 || strcmp(which, "pool96") == 0)) s->pool = 1;
-        if (which && strcmp(which, "pool64") == 0) s->pool = 2;
-    }
-    if (s->pool) {
         const int stride = s->dev.n_bins + LSCPM_N_COUNTERS;
-        s->pool_smem = pool_smem_bytes(pool_warps(s), pool_slots(s), stride);
-        if (s->pool_smem > (size_t)prop.sharedMemPerBlockOptin) s->pool = 0;    // too many tally bins for the per-warp rows: lane kernel
-    }
-    if (s->pool) {
-        if ((e = cudaFuncSetAttribute(pool_kernel(s), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin)) != cudaSuccess)
-            return bail(cuda_fail(e, "cudaFuncSetAttribute (pool kernel)"));
-        int fit = 0;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, pool_kernel(s), pool_warps(s) * 32, s->pool_smem)) != cudaSuccess)
-            return bail(cuda_fail(e, "occupancy query (pool kernel)"));
-        if (fit < 1) s->pool = 0;
-        else s->sorted = false;
+        const size_t optin = (size_t)prop.sharedMemPerBlockOptin;
+        auto fits = [&](int cfg) { return pool_smem_bytes(pool_warps(cfg), pool_slots(cfg), stride) <= optin; };
+        const bool forced = which && strncmp(which, "pool", 4) == 0;
+        bool pinned = false;        // a configuration named in the environment is used for every launch
+        if (s->flight || forced) s->pool = POOL_96;
+        if (which && (strcmp(which, "lanes") == 0 || strcmp(which, "sorted") == 0)) s->pool = POOL_OFF;
+        if (which && strcmp(which, "pool120") == 0) { s->pool = POOL_120; pinned = true; }
+        if (which && strcmp(which, "pool96") == 0) { s->pool = POOL_96; pinned = true; }
+        if (which && strcmp(which, "pool80") == 0) { s->pool = POOL_80; pinned = true; }
+        if (which && strcmp(which, "pool64") == 0) { s->pool = POOL_WIDE_64; pinned = true; }
+        while (s->pool && !fits(s->pool))      // wide tally rows: fewer records, finally the lane kernel
+            s->pool = (s->pool == POOL_120) ? POOL_96 : (s->pool == POOL_96 ? POOL_80 : (s->pool == POOL_80 ? POOL_64 : POOL_OFF));
+        if (s->pool == POOL_96 && !pinned && fits(POOL_120)) s->pool_small_plan = POOL_120;
+        for (int cfg : {s->pool, s->pool_small_plan}) {
+            if (!cfg) continue;
+            if ((e = cudaFuncSetAttribute(pool_kernel(s, cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)) != cudaSuccess)
+                return bail(cuda_fail(e, "cudaFuncSetAttribute (pool kernel)"));
+            int fit = 0;
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, pool_kernel(s, cfg), pool_warps(cfg) * 32,
+                                                                   pool_smem_bytes(pool_warps(cfg), pool_slots(cfg), stride))) != cudaSuccess)
+                return bail(cuda_fail(e, "occupancy query (pool kernel)"));
+            if (fit < 1) { if (cfg == s->pool) s->pool = POOL_OFF; s->pool_small_plan = POOL_OFF; }
+        }
+        if (s->pool) s->sorted = false;
     }
     *out = s;
     return LSCPM_OK;
@@ -1399,6 +1424,22 @@ int lscpm_scene_destroy(LscpmScene* s) {
 }
 
 int lscpm_scene_n_bins(const LscpmScene* s) { return s ? s->dev.n_bins : fail(LSCPM_EINVAL, "scene is NULL"); }
+
+int lscpm_scene_kernel_name(const LscpmScene* s, char* buf, int buf_len) {
+    if (!s) return fail(LSCPM_EINVAL, "scene is NULL");
+    char text[160];
+    if (s->pool) {
+        snprintf(text, sizeof(text), "trace_pool_kernel<flight=%d, warps=%d, records=%d>%s", s->flight ? 1 : 0, pool_warps(s->pool),
+                 pool_slots(s->pool), s->pool_small_plan ? " (records=120 for plans <= 16 KB)" : "");
+    } else if (s->sorted) {
+        snprintf(text, sizeof(text), "trace_sorted_kernel<ext=%d, flight=%d, block=%d>%s", s->dev.n_ext > 0 ? 1 : 0, s->flight ? 1 : 0, SORT_THREADS,
+                 s->sorted_forced ? "" : " (trace_kernel for launches below 4 blocks' worth of photons per resident block)");
+    } else {
+        snprintf(text, sizeof(text), "trace_kernel<ext=%d, flight=%d, block=%d>", s->dev.n_ext > 0 ? 1 : 0, s->flight ? 1 : 0, s->trace_block);
+    }
+    if (buf && buf_len > 0) { strncpy(buf, text, (size_t)buf_len - 1); buf[buf_len - 1] = 0; }
+    return (int)strlen(text);
+}
 
 int lscpm_scene_bin_name(const LscpmScene* s, int bin, char* buf, int buf_len) {
     if (!s) return fail(LSCPM_EINVAL, "scene is NULL");
@@ -1561,9 +1602,10 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
     // launches too small to fill the sorted kernel's blocks a few times over go to the lane kernel
     const bool sorted = s->sorted && (s->sorted_forced || total >= 4ULL * (unsigned long long)(s->n_sm * s->sort_blocks_per_sm) * SORT_THREADS);
     const bool pool = !sorted && s->pool != 0;
+    const int pool_cfg = (pool && s->pool_small_plan && p->h2d_bytes <= POOL_SMALL_PLAN_BYTES) ? s->pool_small_plan : s->pool;
     const int per_sm = sorted ? s->sort_blocks_per_sm : (pool ? 1 : s->blocks_per_sm);
     const int grid = s->n_sm * per_sm;
-    const int lane_warps = pool ? pool_warps(s) : s->trace_block / 32;
+    const int lane_warps = pool ? pool_warps(pool_cfg) : s->trace_block / 32;
     // work items: claimed by a block (sorted kernel) or by a warp (lane / pool kernel); ~8 items per claimer, within a batch
     const unsigned long long claimers = sorted ? (unsigned long long)grid : (unsigned long long)grid * (unsigned long long)lane_warps;
     const unsigned long long lo = sorted ? (unsigned long long)SORT_THREADS : 32ULL, hi = sorted ? 16384ULL : 4096ULL;
@@ -1584,7 +1626,8 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
     } else {
         const unsigned long long warps = (unsigned long long)lane_warps;
         const int blocks = (int)std::min<unsigned long long>((unsigned long long)grid, (a.n_chunks + warps - 1) / warps);
-        if (pool) pool_kernel(s)<<<std::max(blocks, 1), lane_warps * 32, s->pool_smem, stream>>>(s->dev, a);
+        if (pool) pool_kernel(s, pool_cfg)<<<std::max(blocks, 1), lane_warps * 32,
+                                             pool_smem_bytes(lane_warps, pool_slots(pool_cfg), s->dev.n_bins + LSCPM_N_COUNTERS), stream>>>(s->dev, a);
         else lane_kernel(s)<<<std::max(blocks, 1), s->trace_block, s->trace_smem, stream>>>(s->dev, a);
     }
     g_launches.fetch_add(1);

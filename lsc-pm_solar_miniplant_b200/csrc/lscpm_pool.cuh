@@ -97,7 +97,7 @@ template <bool FLIGHT, int WARPS, int NSLOT>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_constant__ TraceArgs A) {
     using namespace lscpm;
-    static_assert(NSLOT % 16 == 0 && NSLOT <= 255, "slot numbers and list lengths travel as bytes");
+    static_assert(NSLOT % 8 == 0 && NSLOT <= 255, "slot numbers and list lengths travel as bytes");
     extern __shared__ uint4 pool_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lane_lt = (1u << lane) - 1u;

@@ -58,7 +58,7 @@ def test_sorted_kernel_is_bit_identical(label):
 POOL_CASES = sorted(k for k in CASES if not k.startswith("pv_"))   # scenes with outside boxes have no pool kernel
 
 
-@pytest.mark.parametrize("which", ["pool96", "pool64"])
+@pytest.mark.parametrize("which", ["pool120", "pool96", "pool80", "pool64"])
 @pytest.mark.parametrize("label", POOL_CASES)
 def test_pool_kernel_is_bit_identical(label, which):
     from lscpm_b200 import flatten
@@ -74,7 +74,7 @@ def test_pool_kernel_photon_offset_and_many_small_batches():
     from lscpm_b200 import flatten
     arrays = flatten.flatten_scene(standard_scene(tilt=20, elevation=50, spectrum=am15_like_photon_spectrum()))
     a, n_bins = _tallies(arrays, "lanes", 400, 37, seed=5, photon_begin=(1 << 33) + 12345)
-    for which in ("pool96", "pool64"):
+    for which in ("pool120", "pool96", "pool80", "pool64"):
         b, _ = _tallies(arrays, which, 400, 37, seed=5, photon_begin=(1 << 33) + 12345)
         assert (b[:, :n_bins].sum(axis=1) == 37).all()
         np.testing.assert_array_equal(a, b)
