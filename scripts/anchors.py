@@ -25,7 +25,7 @@ import lscpm_b200
 lscpm_b200.install()
 from helpers import binomial_z, frame_epoch, reference_counts
 from lscpm_b200 import lights
-from miniplant.full_simulation import trace_time_points, yearlong_simulation
+from miniplant.full_simulation import trace_time_points, year_batches, yearlong_simulation
 from miniplant.locations import LOCATIONS
 from miniplant.solar_data import solar_data_for_place_and_time
 
@@ -103,8 +103,7 @@ for key in sorted({name.split("|")[0] for name in SWEEP.files}):
     if site.name == "Townsville":
         tilt = -tilt                      # swept over range(0, -40, -5), file names carry |tilt|
     data = solar_data_for_place_and_time(site, tilt, 1800, write_csv=False)
-    batch = [lights.direct_light(tilt, r["apparent_elevation"], r["azimuth"], r["direct_spectrum"]) for _, r in data.iterrows()]
-    p = trace_time_points(tilt, batch, N, include_dye=dye, seed=3)
+    p = trace_time_points(tilt, year_batches(tilt, data, diffuse=False), N, include_dye=dye, seed=3)
     both = pd.DataFrame({"p": p, "irr": data["direct_irradiance"].values}, index=frame_epoch(data)).join(reference_counts(SWEEP, key), how="inner")
     z = binomial_z(both.direct.values, both.p.values, 100)
     sweep_z[dye].append(z)

@@ -127,7 +127,7 @@ def test_tilt_sweep_counts_against_the_reference_results(built_library):
                            ("Eindhoven_no_dye_90deg", 90, False)):
         data = solar_data_for_place_and_time(EINDHOVEN, tilt, 1800, write_csv=False)
         batch = [lights.direct_light(tilt, r["apparent_elevation"], r["azimuth"], r["direct_spectrum"]) for _, r in data.iterrows()]
-        p = trace_time_points(tilt, batch, 20000, include_dye=dye, seed=13)
+        p = trace_time_points(tilt, batch, 20000, include_dye=dye, seed=13)      # the per-row (list of LightArrays) form on purpose
         both = pd.DataFrame({"p": p}, index=frame_epoch(data)).join(reference_counts(gold, key), how="inner")
         assert len(both) >= len(gold[key + "|direct"]) - 2, key
         assert abs(binomial_z(both.direct.values, both.p.values, 100)) < 4.0, key
