@@ -21,12 +21,13 @@
 // coefficients are looked up from the wavelength when a flight needs them instead of travelling), at most 196 KB of
 // shared memory, and compact bookkeeping.
 //
-//   PH_FRESH  empty record: takes the next photon index of the warp's work item, generation draw, entry Fresnel test
+//   PH_FRESH  empty record: takes the next photon index of the warp's work item, generation draw, entry Fresnel test,
+//             and the photon's first flight (it is in registers and every lane wants the same thing)
 //   PH_PLATE  photon in the plastic (scenes with plate flights): step draw + plate_flight [+ absorption]
 //   PH_TUBE   photon in a tube wall / the mixture (every medium when the scene has no plate flights): step draw +
 //             compute_hit + free path + move [+ absorption]
 //   PH_SURF   photon on an interface: Fresnel test
-//   PH_EMIT   photon absorbed by the luminophore, to be re-emitted: emission draw
+//   PH_EMIT   photon absorbed by the luminophore, to be re-emitted: emission draw, and the flight that follows
 //
 // The phase code is the very device code of K2 / K2s (advance_hit, interact_*, source_*) fed with the same Philox words in
 // the same order, so the tallies are bit-identical to K2's for every scene, batch shape and photon offset
@@ -162,51 +163,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
         int tbin = -1, tbatch = 0;          // a photon that ended in this execution: tallied once, below
         unsigned tevents = 0u;
 
-        if (ph == PH_PLATE || ph == PH_TUBE) {
-            // ---- step draw, nearest interface, free path, move; absorption is settled here as well ---------------
-            if (act) {
-                const uint4 g0 = G[0 * NSLOT + slot], g1 = G[1 * NSLOT + slot], g2 = G[2 * NSLOT + slot];
-                uint4 g3 = G[3 * NSLOT + slot];
-                Photon p;
-                p.xr = __uint_as_float(g0.x); p.y = __uint_as_float(g0.y); p.z = __uint_as_float(g0.z);
-                p.kc = g0.w & 0xfff; p.medium = (g0.w >> 12) & 15; p.steps = g0.w >> 16;
-                p.dx = __uint_as_float(g1.x); p.dy = __uint_as_float(g1.y); p.dz = __uint_as_float(g1.z); p.wl = __uint_as_float(g1.w);
-                p.a_plate = p.a_outer = p.a_inner = 0.f; p.aux = 0;
-                Rng rng; rng.key = A.key; rng.p_lo = g2.x; rng.p_hi = g2.y; rng.batch = g2.w; rng.calls = g3.w;
-                unsigned n_events = g3.x;
-                const uint4 w = rng.next(A.rk);
-                Hit h; int cls, extra; float alpha;
-                int bin = advance_hit<true, FLIGHT, true, true>(S, p, w.x, h, cls, extra, alpha);
-                n_events += (unsigned)extra;
-                unsigned pend = 0u;
-                if (bin < 0) {
-                    if (cls == CLS_ABSORB) {
-                        n_events += 1u;
-                        int ev;
-                        bin = interact_absorb_alpha(S, p, h.container, alpha, u01(w.y), w.z, ev);
-                        if (bin < 0) {   // re-emitted by the luminophore: the emission table travels in the pending word
-                            n_events += 0x10000u;
-                            nph = PH_EMIT;
-                            pend = (unsigned)(p.aux >> 16) & 0xffu;
-                        }
-                    } else if (cls == CLS_CELL) {
-                        nph = fly_phase<FLIGHT>(p.medium);
-                    } else {
-                        nph = PH_SURF;
-                        pend = pack_pending(cls, h.kind, h.face, h.container, h.adj);
-                    }
-                }
-                if (bin >= 0) {
-                    tbin = bin; tbatch = (int)g2.z; tevents = n_events;
-                } else {
-                    G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
-                                                     (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
-                    if (FLIGHT) G[1 * NSLOT + slot].z = __float_as_uint(p.dz);    // a folded flight may end on a mirrored leg
-                    g3.x = n_events; g3.y = pend; g3.z = w.y; g3.w = rng.calls;
-                    G[3 * NSLOT + slot] = g3;
-                }
-            }
-        } else if (ph == PH_SURF) {
+        if (ph == PH_SURF) {
             // ---- Fresnel test on the interface the photon was moved to -----------------------------------------
             if (act) {
                 const uint4 g0 = G[0 * NSLOT + slot], g1 = G[1 * NSLOT + slot], g3 = G[3 * NSLOT + slot];
@@ -230,50 +187,95 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                 }
             }
         } else {
-            // ---- source: a new photon (PH_FRESH) or a re-emission (PH_EMIT) -------------------------------------
+            // ---- source (PH_FRESH: a new photon, PH_EMIT: a re-emission), then - in the SAME execution, with the photon
+            // ---- still in registers - its first flight; or the flight of a record waiting in PH_PLATE / PH_TUBE.
+            // A photon that has just been generated or re-emitted always flies next, and all lanes of a source execution
+            // do (but the 4 % reflected at first contact), so running the flight here costs no lanes and saves one phase
+            // execution per generation / emission: its bookkeeping and a whole record round trip through shared memory.
+            const bool is_source = ph == PH_FRESH || ph == PH_EMIT;      // warp-uniform
             const bool fresh = ph == PH_FRESH;
-            if (act) {
-                Photon p;
-                p.a_plate = p.a_outer = p.a_inner = 0.f;
-                Rng rng; rng.key = A.key;
-                int batch;
-                unsigned n_events = 0;
-                unsigned packed = 0u;
-                if (fresh) {
-                    const unsigned long long g = chunk_base + c_next + (unsigned)lane;
-                    batch = cbatch;
-                    rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32); rng.batch = A.batches[batch].batch_id; rng.calls = 0;
-                    p.xr = p.y = p.z = p.wl = 0.f; p.kc = p.medium = p.steps = p.aux = 0;
-                } else {
-                    const uint4 g2 = G[2 * NSLOT + slot], g3 = G[3 * NSLOT + slot];
-                    packed = G[0 * NSLOT + slot].w;
-                    p.medium = (packed >> 12) & 15;
-                    p.wl = __uint_as_float(G[1 * NSLOT + slot].w);
-                    p.aux = (int)(g3.y << 16);
-                    rng.p_lo = g2.x; rng.p_hi = g2.y; batch = (int)g2.z; rng.batch = g2.w; rng.calls = g3.w;
+            bool fly = act && !is_source;
+            Photon p;
+            p.a_plate = p.a_outer = p.a_inner = 0.f; p.aux = 0;
+            Rng rng; rng.key = A.key;
+            int batch = 0;
+            unsigned n_events = 0u;
+            if (is_source) {
+                if (act) {
+                    if (fresh) {
+                        const unsigned long long g = chunk_base + c_next + (unsigned)lane;
+                        batch = cbatch;
+                        rng.p_lo = (uint32_t)g; rng.p_hi = (uint32_t)(g >> 32); rng.batch = A.batches[batch].batch_id; rng.calls = 0;
+                        p.xr = p.y = p.z = p.wl = 0.f; p.kc = p.medium = p.steps = 0;
+                    } else {
+                        const uint4 g0 = G[0 * NSLOT + slot], g2 = G[2 * NSLOT + slot], g3 = G[3 * NSLOT + slot];
+                        p.xr = __uint_as_float(g0.x); p.y = __uint_as_float(g0.y); p.z = __uint_as_float(g0.z);
+                        p.kc = g0.w & 0xfff; p.medium = (g0.w >> 12) & 15; p.steps = g0.w >> 16;
+                        p.wl = __uint_as_float(G[1 * NSLOT + slot].w);
+                        p.aux = (int)(g3.y << 16);
+                        rng.p_lo = g2.x; rng.p_hi = g2.y; batch = (int)g2.z; rng.batch = g2.w; rng.calls = g3.w;
+                        n_events = g3.x;
+                    }
+                    const uint4 v = rng.next(A.rk);
+                    WavelengthDraw wd;
+                    int bin = -1;
+                    if (fresh) bin = source_fresh<false, true>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr, n_events);
+                    else source_emit(S, v, p, wd);
+                    source_wavelength(p, wd);
+                    if (bin >= 0) {   // reflected off the plate at first contact, or never touched it: the record stays empty
+                        tbin = bin; tbatch = batch; tevents = n_events;
+                    } else {
+                        fly = true;
+                    }
                 }
-                const uint4 v = rng.next(A.rk);
-                WavelengthDraw wd;
-                int bin = -1;
-                if (fresh) bin = source_fresh<false, true>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr, n_events);
-                else source_emit(S, v, p, wd);
-                source_wavelength(p, wd);
-                if (bin >= 0) {   // reflected off the plate at first contact, or never touched it: the record stays empty
+                if (fresh) c_next += (unsigned)n;
+            }
+            // ---- step draw, nearest interface, free path, move; absorption is settled here as well ---------------
+            if (fly) {
+                if (!is_source) {
+                    const uint4 g0 = G[0 * NSLOT + slot], g1 = G[1 * NSLOT + slot], g2 = G[2 * NSLOT + slot], g3 = G[3 * NSLOT + slot];
+                    p.xr = __uint_as_float(g0.x); p.y = __uint_as_float(g0.y); p.z = __uint_as_float(g0.z);
+                    p.kc = g0.w & 0xfff; p.medium = (g0.w >> 12) & 15; p.steps = g0.w >> 16;
+                    p.dx = __uint_as_float(g1.x); p.dy = __uint_as_float(g1.y); p.dz = __uint_as_float(g1.z); p.wl = __uint_as_float(g1.w);
+                    rng.p_lo = g2.x; rng.p_hi = g2.y; batch = (int)g2.z; rng.batch = g2.w; rng.calls = g3.w;
+                    n_events = g3.x;
+                }
+                const uint4 w = rng.next(A.rk);
+                Hit h; int cls, extra; float alpha;
+                int bin = advance_hit<true, FLIGHT, true, true>(S, p, w.x, h, cls, extra, alpha);
+                n_events += (unsigned)extra;
+                unsigned pend = 0u;
+                if (bin < 0) {
+                    if (cls == CLS_ABSORB) {
+                        n_events += 1u;
+                        int ev;
+                        bin = interact_absorb_alpha(S, p, h.container, alpha, u01(w.y), w.z, ev);
+                        if (bin < 0) {   // re-emitted by the luminophore: the emission table travels in the pending word
+                            n_events += 0x10000u;
+                            nph = PH_EMIT;
+                            pend = (unsigned)(p.aux >> 16) & 0xffu;
+                        }
+                    } else if (cls == CLS_CELL) {
+                        nph = fly_phase<FLIGHT>(p.medium);
+                    } else {
+                        nph = PH_SURF;
+                        pend = pack_pending(cls, h.kind, h.face, h.container, h.adj);
+                    }
+                }
+                if (bin >= 0) {
                     tbin = bin; tbatch = batch; tevents = n_events;
                 } else {
-                    nph = fly_phase<FLIGHT>(p.medium);
-                    if (fresh) {
-                        G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
-                                                         (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
-                        G[2 * NSLOT + slot] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.batch);
-                        G[3 * NSLOT + slot] = make_uint4(n_events, 0u, 0u, rng.calls);
-                    } else {
-                        G[3 * NSLOT + slot].w = rng.calls;
+                    G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
+                                                     (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
+                    if (is_source) {
+                        G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl));
+                        if (fresh) G[2 * NSLOT + slot] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.batch);
+                    } else if (FLIGHT) {
+                        G[1 * NSLOT + slot].z = __float_as_uint(p.dz);    // a folded flight may end on a mirrored leg
                     }
-                    G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl));
+                    G[3 * NSLOT + slot] = make_uint4(n_events, pend, w.y, rng.calls);
                 }
             }
-            if (fresh) c_next += (unsigned)n;
         }
         if (tbin >= 0) pool_tally(A.tallies, hist, S.n_bins, stride, hbatch, tbatch, tbin, tevents);
         pool_push<NSLOT>(lists, cnt, emit_len, act, nph, slot, lane_lt);
