@@ -231,6 +231,8 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                 if (fresh) c_next += (unsigned)n;
             }
             // ---- step draw, nearest interface, free path, move; absorption is settled here as well ---------------
+            bool keep = false;              // the photon lives on: its record is written back below, by all such lanes at once
+            unsigned pend = 0u, surf_word = 0u;
             if (fly) {
                 if (!is_source) {
                     const uint4 g0 = G[0 * NSLOT + slot], g1 = G[1 * NSLOT + slot], g2 = G[2 * NSLOT + slot], g3 = G[3 * NSLOT + slot];
@@ -241,10 +243,10 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                     n_events = g3.x;
                 }
                 const uint4 w = rng.next(A.rk);
+                surf_word = w.y;
                 Hit h; int cls, extra; float alpha;
                 int bin = advance_hit<true, FLIGHT, true, true>(S, p, w.x, h, cls, extra, alpha);
                 n_events += (unsigned)extra;
-                unsigned pend = 0u;
                 if (bin < 0) {
                     if (cls == CLS_ABSORB) {
                         n_events += 1u;
@@ -262,19 +264,22 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                         pend = pack_pending(cls, h.kind, h.face, h.container, h.adj);
                     }
                 }
-                if (bin >= 0) {
-                    tbin = bin; tbatch = batch; tevents = n_events;
-                } else {
-                    G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
-                                                     (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
-                    if (is_source) {
-                        G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl));
-                        if (fresh) G[2 * NSLOT + slot] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.batch);
-                    } else if (FLIGHT) {
-                        G[1 * NSLOT + slot].z = __float_as_uint(p.dz);    // a folded flight may end on a mirrored leg
-                    }
-                    G[3 * NSLOT + slot] = make_uint4(n_events, pend, w.y, rng.calls);
+                if (bin >= 0) { tbin = bin; tbatch = batch; tevents = n_events; }
+                else keep = true;
+            }
+            // the outcomes above diverge (absorbed | re-emitted | cell crossing | surface); without this convergence point the
+            // compiler duplicates the write-back into every one of them (profile of v4: the stores ran at 12.5 lanes)
+            __syncwarp();
+            if (keep) {
+                G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
+                                                 (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
+                if (is_source) {
+                    G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl));
+                    if (fresh) G[2 * NSLOT + slot] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.batch);
+                } else if (FLIGHT) {
+                    G[1 * NSLOT + slot].z = __float_as_uint(p.dz);    // a folded flight may end on a mirrored leg
                 }
+                G[3 * NSLOT + slot] = make_uint4(n_events, pend, surf_word, rng.calls);
             }
         }
         if (tbin >= 0) pool_tally(A.tallies, hist, S.n_bins, stride, hbatch, tbatch, tbin, tevents);
