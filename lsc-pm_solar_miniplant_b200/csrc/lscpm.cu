@@ -1109,19 +1109,20 @@ TraceKernel sorted_kernel(const LscpmScene* s) {
 
 // pool kernel configurations: records per warp decide the lanes per phase execution (120: 31.8 of 32, 96: 31, 80: 29,
 // 64: 26) and are limited by shared memory; what shared memory takes, the L1 loses (up to 196 KB leaves 60 KB of L1, more
-// leaves 28 KB).  Measured (one B200, ms per job; profiles/r2_pool_records_ab.txt):
-//                                              120 rec.   112     96      80     lanes (K2)
-//   config 2 (64 batches, one spectrum)          7.48     7.52    7.67    8.05   10.06
-//   config 4 (16 096 batches, 16 096 spectra)   197.8    198.7   195.1     -
-//   config 5 (dense grid: 702 counters per row)  (does not fit)   8.45    8.90   11.72
+// leaves 28 KB).  Measured (one B200, ms per job; profiles/r2_pool_records_ab.txt; end state of round 2):
+//                                              128 rec.   120      96
+//   config 2 (64 batches, one spectrum)          7.06     7.06    7.15     (K2: 10.0)
+//   config 4 (16 096 batches, 16 096 spectra)   189.4    189.4   183.7
+//   config 5 (dense grid: 702 counters per row)    (do not fit)   7.87     (K2: 11.7)
 // so: 96 records by default (fewer for scenes whose per-warp tally rows are very wide), 120 for launches whose batch
-// descriptors and spectra are small enough to live in the 28 KB L1 beside the scene tables.  The 28-warp x 80-record
-// configuration (72 registers) measured 7.94 ms on config 2: more warps do not buy back the lanes fewer records lose.
+// descriptors and spectra are small enough to live in the 28 KB L1 beside the scene tables.  With the five-phase version
+// of the kernel: 80 records 8.05 ms against 96 at 7.67 on config 2, and a 28-warp x 80-record configuration (72 registers)
+// 7.94 ms: more warps do not buy back the lanes fewer records lose.
 constexpr int POOL_WARPS = 24, POOL_WARPS_WIDE = 32;
 constexpr size_t POOL_SMALL_PLAN_BYTES = 16 * 1024;
 enum PoolConfig { POOL_OFF = 0, POOL_96 = 1, POOL_WIDE_64 = 2, POOL_80 = 3, POOL_64 = 4, POOL_120 = 7 };
 int pool_warps(int cfg) { return cfg == POOL_WIDE_64 ? POOL_WARPS_WIDE : POOL_WARPS; }
-int pool_slots(int cfg) { return cfg == POOL_120 ? 120 : (cfg == POOL_96 ? 96 : (cfg == POOL_80 ? 80 : 64)); }
+int pool_slots(int cfg) { return (cfg == POOL_120 ? 120 : (cfg == POOL_96 ? 96 : (cfg == POOL_80 ? 80 : 64))); }
 TraceKernel pool_kernel(const LscpmScene* s, int cfg) {
     switch (cfg) {
         case POOL_120: return s->flight ? trace_pool_kernel<true, POOL_WARPS, 120> : trace_pool_kernel<false, POOL_WARPS, 120>;

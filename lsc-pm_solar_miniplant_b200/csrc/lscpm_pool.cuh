@@ -11,7 +11,7 @@
 // lanes in the same code), stores what the phase changed and pushes each record onto the list of its next phase.  No
 // barrier, no atomics on the lists (one warp, warp-uniform counters), no hand-over between warps: what made the block-level
 // regrouping experiments of round 1 lose (K2s: the block waits for its slowest warp; page queues: queue management cost as
-// much as the photon work) does not exist here.  Cost: four 16-byte shared-memory loads / two or three stores per phase
+// much as the photon work) does not exist here.  Cost: four 16-byte shared-memory loads / three stores per phase
 // execution and ~50 instructions of list bookkeeping (one packed counter word, one MATCH + one REDUX per push).
 //
 // What the first version's profile asked for (profiles/r2_pool_v1_*): it executed 25 % fewer warp instructions than K2 at
@@ -23,10 +23,11 @@
 //
 //   PH_FRESH  empty record: takes the next photon index of the warp's work item, generation draw, entry Fresnel test,
 //             and the photon's first flight (it is in registers and every lane wants the same thing)
-//   PH_PLATE  photon in the plastic (scenes with plate flights): step draw + plate_flight [+ absorption]
+//   PH_PLATE  photon in the plastic (scenes with plate flights): step draw + plate_flight, then the interaction the
+//             flight ends in - absorption (component pick, quantum yield) or the Fresnel test on the interface reached
 //   PH_TUBE   photon in a tube wall / the mixture (every medium when the scene has no plate flights): step draw +
-//             compute_hit + free path + move [+ absorption]
-//   PH_SURF   photon on an interface: Fresnel test
+//             compute_hit + free path + move, then the interaction as above
+//   (PH_SURF  a Fresnel-test phase of its own existed up to v4; the test now runs inside the flight's execution)
 //   PH_EMIT   photon absorbed by the luminophore, to be re-emitted: emission draw, and the flight that follows
 //
 // The phase code is the very device code of K2 / K2s (advance_hit, interact_*, source_*) fed with the same Philox words in
@@ -37,14 +38,13 @@
 
 namespace lscpm {
 
-constexpr int PH_FRESH = 0, PH_PLATE = 1, PH_TUBE = 2, PH_SURF = 3, PH_EMIT = 4, N_PH = 5;
+constexpr int PH_FRESH = 0, PH_PLATE = 1, PH_TUBE = 2, PH_EMIT = 3, N_PH = 4;
 
 // record = 4 x uint4 (SoA over the slots of a warp):
 //   G0: xr, y, z, kc | medium << 12 | steps << 16
 //   G1: dx, dy, dz, wl
 //   G2: photon index lo, hi, batch (index into the plan), batch id (Philox counter word)
-//   G3: event counters, pending interaction (PH_SURF) / emission table (PH_EMIT), raw Philox word for the pending
-//       interaction, Philox call counter
+//   G3: event counters, emission table of a pending re-emission (PH_EMIT), unused, Philox call counter
 constexpr int POOL_GROUPS = 4;
 
 __host__ __device__ constexpr int pool_list_u4(int nslot) { return (N_PH * nslot + 15) / 16; }
@@ -55,22 +55,19 @@ __host__ __device__ constexpr size_t pool_smem_bytes(int warps, int nslot, int s
 template <bool FLIGHT>
 __device__ __forceinline__ int fly_phase(int medium) { return (FLIGHT && medium == MED_PLATE) ? PH_PLATE : PH_TUBE; }
 
-// List lengths, warp-uniform, packed into ONE word: phases 0..3 in its bytes (NSLOT <= 255).  Between two phase
-// executions every record is in exactly one list, so the fifth length (PH_EMIT) is NSLOT minus the byte sum.
-__device__ __forceinline__ unsigned pool_byte_sum(unsigned a) { return __vsadu4(a, 0u); }
-
+// List lengths, warp-uniform, packed into ONE word: phase k in byte k (NSLOT <= 255).
+//
 // Push the records the active lanes hold onto the lists of their next phases: lanes with the same target find each other
 // with one MATCH and rank themselves inside the group; the group leaders' sizes are summed into the packed counters with
-// one REDUX - independent of how many different targets there are.  `emit_len`: current length of the PH_EMIT list.
+// one REDUX - independent of how many different targets there are.
 template <int NSLOT>
-__device__ __forceinline__ void pool_push(unsigned char* __restrict__ lists, unsigned& cnt, unsigned emit_len, bool act, int nph, int slot,
-                                          unsigned lane_lt) {
+__device__ __forceinline__ void pool_push(unsigned char* __restrict__ lists, unsigned& cnt, bool act, int nph, int slot, unsigned lane_lt) {
     const unsigned grp = __match_any_sync(0xffffffffu, act ? nph : 7);   // idle lanes form a group of their own that is not counted
     const int rank = __popc(grp & lane_lt);
     const unsigned shift = 8u * (unsigned)nph;
-    const unsigned base = nph < 4 ? (cnt >> shift) & 0xffu : emit_len;
+    const unsigned base = (cnt >> shift) & 0xffu;
     if (act) lists[nph * NSLOT + (int)base + rank] = (unsigned char)slot;
-    const unsigned contrib = (act && rank == 0 && nph < 4) ? (unsigned)__popc(grp) << shift : 0u;
+    const unsigned contrib = (act && rank == 0) ? (unsigned)__popc(grp) << shift : 0u;
     cnt += __reduce_add_sync(0xffffffffu, contrib);
 }
 
@@ -123,10 +120,9 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
         // ---- the fullest list whose phase can run: max over (length << 3 | phase) ---------------------------------
         const unsigned fresh_len = (c_next < c_end || more) ? (cnt & 0xffu) : 0u;
         unsigned key = fresh_len << 3;
-        key = max(key, (__byte_perm(cnt, 0u, 0x4441) << 3) | 1u);
-        key = max(key, (__byte_perm(cnt, 0u, 0x4442) << 3) | 2u);
-        key = max(key, ((cnt >> 24) << 3) | 3u);
-        key = max(key, (((unsigned)NSLOT - pool_byte_sum(cnt)) << 3) | 4u);
+        key = max(key, (__byte_perm(cnt, 0u, 0x4441) << 3) | (unsigned)PH_PLATE);
+        key = max(key, (__byte_perm(cnt, 0u, 0x4442) << 3) | (unsigned)PH_TUBE);
+        key = max(key, ((cnt >> 24) << 3) | (unsigned)PH_EMIT);
         const int best = (int)(key >> 3);
         if (best == 0) break;
         const int ph = (int)(key & 7u);
@@ -157,36 +153,12 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
         int slot = 0;
         if (act) slot = lists[ph * NSLOT + best - n + lane];
         LSCPM_CHECK(slot >= 0 && slot < NSLOT);
-        cnt -= ph < 4 ? (unsigned)n << (8 * ph) : 0u;
-        const unsigned emit_len = (unsigned)(NSLOT - n) - pool_byte_sum(cnt);
+        cnt -= (unsigned)n << (8 * ph);
         int nph = PH_FRESH;
         int tbin = -1, tbatch = 0;          // a photon that ended in this execution: tallied once, below
         unsigned tevents = 0u;
 
-        if (ph == PH_SURF) {
-            // ---- Fresnel test on the interface the photon was moved to -----------------------------------------
-            if (act) {
-                const uint4 g0 = G[0 * NSLOT + slot], g1 = G[1 * NSLOT + slot], g3 = G[3 * NSLOT + slot];
-                Photon p;
-                p.xr = __uint_as_float(g0.x); p.y = __uint_as_float(g0.y); p.z = __uint_as_float(g0.z);
-                p.kc = g0.w & 0xfff; p.medium = (g0.w >> 12) & 15; p.steps = g0.w >> 16;
-                p.dx = __uint_as_float(g1.x); p.dy = __uint_as_float(g1.y); p.dz = __uint_as_float(g1.z);
-                p.wl = 0.f; p.a_plate = p.a_outer = p.a_inner = 0.f; p.aux = 0;
-                const unsigned n_events = g3.x + 1u;
-                int ev;
-                const int bin = interact_surface<false>(S, p, pending_kind(g3.y), pending_face(g3.y), pending_container(g3.y),
-                                                        pending_adj(g3.y), u01(g3.z), ev);
-                if (bin >= 0) {
-                    tbin = bin; tbatch = (int)G[2 * NSLOT + slot].z; tevents = n_events;
-                } else {
-                    nph = fly_phase<FLIGHT>(p.medium);
-                    G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
-                                                     (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
-                    G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), g1.w);
-                    G[3 * NSLOT + slot].x = n_events;
-                }
-            }
-        } else {
+        {
             // ---- source (PH_FRESH: a new photon, PH_EMIT: a re-emission), then - in the SAME execution, with the photon
             // ---- still in registers - its first flight; or the flight of a record waiting in PH_PLATE / PH_TUBE.
             // A photon that has just been generated or re-emitted always flies next, and all lanes of a source execution
@@ -232,7 +204,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
             }
             // ---- step draw, nearest interface, free path, move; absorption is settled here as well ---------------
             bool keep = false;              // the photon lives on: its record is written back below, by all such lanes at once
-            unsigned pend = 0u, surf_word = 0u;
+            unsigned pend = 0u;             // emission table of a pending re-emission
             if (fly) {
                 if (!is_source) {
                     const uint4 g0 = G[0 * NSLOT + slot], g1 = G[1 * NSLOT + slot], g2 = G[2 * NSLOT + slot], g3 = G[3 * NSLOT + slot];
@@ -243,7 +215,6 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                     n_events = g3.x;
                 }
                 const uint4 w = rng.next(A.rk);
-                surf_word = w.y;
                 Hit h; int cls, extra; float alpha;
                 int bin = advance_hit<true, FLIGHT, true, true>(S, p, w.x, h, cls, extra, alpha);
                 n_events += (unsigned)extra;
@@ -260,8 +231,13 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                     } else if (cls == CLS_CELL) {
                         nph = fly_phase<FLIGHT>(p.medium);
                     } else {
-                        nph = PH_SURF;
-                        pend = pack_pending(cls, h.kind, h.face, h.container, h.adj);
+                        // Fresnel test on the interface the photon was moved to, in the same execution: about half of a
+                        // flight's lanes are here, and a phase of its own would cost them more in bookkeeping and record
+                        // traffic than the idle lanes cost here
+                        n_events += 1u;
+                        int ev;
+                        bin = interact_surface<false>(S, p, h.kind, h.face, h.container, h.adj, u01(w.y), ev);
+                        if (bin < 0) nph = fly_phase<FLIGHT>(p.medium);
                     }
                 }
                 if (bin >= 0) { tbin = bin; tbatch = batch; tevents = n_events; }
@@ -273,17 +249,13 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
             if (keep) {
                 G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
                                                  (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
-                if (is_source) {
-                    G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl));
-                    if (fresh) G[2 * NSLOT + slot] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.batch);
-                } else if (FLIGHT) {
-                    G[1 * NSLOT + slot].z = __float_as_uint(p.dz);    // a folded flight may end on a mirrored leg
-                }
-                G[3 * NSLOT + slot] = make_uint4(n_events, pend, surf_word, rng.calls);
+                G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl));
+                if (fresh) G[2 * NSLOT + slot] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.batch);
+                G[3 * NSLOT + slot] = make_uint4(n_events, pend, 0u, rng.calls);
             }
         }
         if (tbin >= 0) pool_tally(A.tallies, hist, S.n_bins, stride, hbatch, tbatch, tbin, tevents);
-        pool_push<NSLOT>(lists, cnt, emit_len, act, nph, slot, lane_lt);
+        pool_push<NSLOT>(lists, cnt, act, nph, slot, lane_lt);
         __syncwarp();   // records and lists written by one lane are read by another in a later iteration
     }
     if (hbatch >= 0) flush_row(hist, A.tallies + (size_t)hbatch * stride, stride, lane);

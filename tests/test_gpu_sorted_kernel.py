@@ -87,10 +87,16 @@ def test_default_kernel_of_the_standard_scene_is_the_pool_kernel_and_agrees_with
     a, n_bins = _tallies(arrays, "lanes", 4, 250_000, seed=99)
     assert "LSCPM_TRACE_KERNEL" not in os.environ
     scene = backend.SceneHandle(arrays, 0)
+    assert scene.kernel_name.startswith("trace_pool_kernel<flight=1, warps=24, records=96>"), scene.kernel_name
     plan = backend.Plan(scene, [arrays.light] * 4, list(range(10, 14)))
     tallies = plan.new_tallies()
     plan.trace_into(tallies, 250_000, 99)
     np.testing.assert_array_equal(a, tallies.cpu().numpy())
+    # scenes the pool kernel is not chosen for: no luminophore in the plate (lane kernel), outside boxes (block-sorted)
+    no_dye = backend.SceneHandle(flatten.flatten_scene(standard_scene(include_dye=False)), 0)
+    assert no_dye.kernel_name.startswith("trace_kernel<ext=0, flight=0"), no_dye.kernel_name
+    pv = backend.SceneHandle(flatten.flatten_scene(standard_scene(add_bottom_PV=True)), 0)
+    assert pv.kernel_name.startswith("trace_sorted_kernel<ext=1"), pv.kernel_name
 
 
 def test_sorted_kernel_photon_offset_and_many_small_batches():
