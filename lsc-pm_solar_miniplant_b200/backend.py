@@ -62,7 +62,9 @@ class SceneHandle:
         self.n_bins = self.lib.lscpm_scene_n_bins(handle)
         self.bin_names = [self._bin_name(b) for b in range(self.n_bins)]
         self.stride = self.n_bins + nat.N_COUNTERS
-        weakref.finalize(self, self.lib.lscpm_scene_destroy, handle)
+        # released when the handle is collected; at interpreter exit the process teardown reclaims device memory,
+        # streams and events anyway, and CUDA calls made while other libraries unwind are not worth the risk
+        weakref.finalize(self, self.lib.lscpm_scene_destroy, handle).atexit = False
 
     @property
     def kernel_name(self) -> str:
@@ -174,7 +176,7 @@ class Plan:
         nat.check(scene.lib, scene.lib.lscpm_plan_create(scene.handle, self._batches, self.n_batches,
                                                          C.byref(self._spectra.desc), C.byref(handle)))
         self.handle = handle
-        weakref.finalize(self, scene.lib.lscpm_plan_destroy, handle)
+        weakref.finalize(self, scene.lib.lscpm_plan_destroy, handle).atexit = False
 
     def new_tallies(self):
         torch = _torch()

@@ -1525,8 +1525,7 @@ void plan_point(LscpmPlan* p, unsigned char* d_blob, const PlanLayout& L) {
 int scratch_reserve(LscpmScene* s, size_t host_bytes, size_t dev_bytes) {
     if (!s->scratch_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->scratch_stream, cudaStreamNonBlocking));
     if (host_bytes > s->h_scratch_bytes) {
-        for (cudaEvent_t ev : s->counter_event) if (ev) cudaEventDestroy(ev);
-    if (s->h_scratch) cudaFreeHost(s->h_scratch);
+        if (s->h_scratch) cudaFreeHost(s->h_scratch);
         s->h_scratch = nullptr; s->h_scratch_bytes = 0;
         const size_t want = std::max<size_t>(host_bytes + host_bytes / 2, 64 * 1024);
         CUDA_TRY(cudaMallocHost((void**)&s->h_scratch, want));
