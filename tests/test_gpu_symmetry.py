@@ -1,0 +1,84 @@
+"""Oracle-free properties of the traced path (GPU): the scene's mirror symmetries.
+
+The plate, its 16 capillaries (parallel to y, equally spaced in x, symmetric about x = 0) and the light masks are mirror
+symmetric in x and in y.  A light that is itself symmetric must therefore give tallies that are symmetric — whatever the
+restatement of pvtrace's bookkeeping is, so these checks do not depend on ``oracle/``:
+
+* normal incidence (tilt 0, sun at zenith): channel k and channel 15 - k react equally often, the -x and +x (and the -y and
+  +y) edge faces leak equally;
+* a sun at azimuth 180 + d against one at 180 - d (reference ``scene_creator.py:288-304``: the sun vector's y component
+  changes sign): every x-resolved tally agrees between the two runs, and the -y / +y faces (and the capillaries' two end
+  caps) swap roles.
+
+Two-sample binomial bands at 4 sigma on 2e7 photons per run (sigma of a per-channel reacted fraction: 3e-5)."""
+import numpy as np
+import pytest
+
+from helpers import am15_like_photon_spectrum, bins_outside_band, standard_scene
+
+pytestmark = pytest.mark.gpu
+
+N = 20_000_000
+
+
+def _trace(seed, **scene_kwargs):
+    from lscpm_b200 import backend, flatten
+
+    arrays = flatten.flatten_scene(standard_scene(**scene_kwargs))
+    names = arrays.bin_names()
+    row = backend.trace_lights(arrays, [arrays.light], N, seed=seed, device=0)[0]
+    assert row[:len(names)].sum() == N
+    return names, dict(zip(names, (int(c) for c in row[:len(names)])))
+
+
+def _mirror_x(name: str) -> str:
+    """The bin that a reflection x -> -x maps `name` onto: channel k <-> 15 - k, plate face -x <-> +x."""
+    parts = name.split("/")
+    if len(parts) >= 2 and "_" in parts[1] and parts[1].rsplit("_", 1)[1].isdigit():
+        stem, k = parts[1].rsplit("_", 1)
+        parts[1] = f"{stem}_{15 - int(k)}"
+    elif len(parts) == 3 and parts[2] in ("-x", "+x"):
+        parts[2] = "+x" if parts[2] == "-x" else "-x"
+    return "/".join(parts)
+
+
+def _mirror_y(name: str) -> str:
+    """y -> -y: plate face -y <-> +y; a capillary's two end caps swap."""
+    parts = name.split("/")
+    swap = {"-y": "+y", "+y": "-y", "-cap": "+cap", "+cap": "-cap"}
+    if len(parts) == 3 and parts[2] in swap:
+        parts[2] = swap[parts[2]]
+    return "/".join(parts)
+
+
+def _assert_mirrored(names, a, b, mirror, label):
+    mirrored = [mirror(n) for n in names]
+    assert sorted(mirrored) == sorted(names), "the mirror map must permute the bins"
+    bad = bins_outside_band(names, [a[n] for n in names], [b[m] for m in mirrored], z=4.0)
+    assert not bad, f"{label}: {bad}"
+    react = [n for n in names if n.startswith("react/")]
+    assert len(react) == 16 and sum(a[n] for n in react) > 0.15 * N
+
+
+def test_normal_incidence_is_mirror_symmetric_in_x_and_y(built_library):
+    names, a = _trace(101, tilt=0, elevation=90, azimuth=180, spectrum=am15_like_photon_spectrum())
+    _, b = _trace(202, tilt=0, elevation=90, azimuth=180, spectrum=am15_like_photon_spectrum())
+    _assert_mirrored(names, a, b, _mirror_x, "x mirror, independent run")
+    _assert_mirrored(names, a, b, _mirror_y, "y mirror, independent run")
+    # and within ONE run the mirrored halves agree (counts of disjoint bins of one multinomial: same band, conservatively)
+    left = sum(a[f"react/Reaction_mixture_{k}/0"] for k in range(8)) if "react/Reaction_mixture_0/0" in a else None
+    if left is not None:
+        right = sum(a[f"react/Reaction_mixture_{k}/0"] for k in range(8, 16))
+        assert abs(left - right) < 4.0 * np.sqrt(left + right)
+
+
+def test_mirrored_sun_azimuths_give_y_mirrored_tallies(built_library):
+    kw = dict(tilt=30, elevation=35, spectrum=am15_like_photon_spectrum())
+    names, east = _trace(303, azimuth=180 - 40, **kw)
+    _, west = _trace(404, azimuth=180 + 40, **kw)
+    _assert_mirrored(names, east, west, _mirror_y, "sun at 140 deg against 220 deg")
+    # the beam comes in obliquely in y: the face it heads for must see more light than the face behind it
+    lit, shaded = "exit/LSC-PM Reactor 47x47 cm^2/+y", "exit/LSC-PM Reactor 47x47 cm^2/-y"
+    if lit in east:
+        assert east[lit] != east[shaded]
+        assert (east[lit] > east[shaded]) == (west[shaded] > west[lit])
