@@ -82,3 +82,61 @@ def test_mirrored_sun_azimuths_give_y_mirrored_tallies(built_library):
     if lit in east:
         assert east[lit] != east[shaded]
         assert (east[lit] > east[shaded]) == (west[shaded] > west[lit])
+
+
+# ---- an analytic known answer through the whole traced path: the absorbing slab -----------------------------------------
+
+
+def _slab_scene(alpha, n_plate=1.48, thickness=0.008):
+    """A bare plate (no dye, no capillaries) of the LSC-PM family: one constant absorber."""
+    from lscpm_b200.compat import pvtrace_api as pv
+    from lscpm_b200.miniplant.utils import LightPosition, VectorInverter
+    from lscpm_b200.workloads import ConstantWavelength
+
+    world = pv.Node(name="World (air)", geometry=pv.Sphere(radius=10.0, material=pv.Material(refractive_index=1.0)))
+    sun = pv.spherical_to_cart(0.0, 0.0)
+    light = pv.Node(name="Solar Light", light=pv.Light(wavelength=ConstantWavelength(555.0), direction=VectorInverter(sun),
+                                                       position=LightPosition(tilt_angle=0.0)), parent=world)
+    light.translate(sun)
+    plate = pv.Node(name="plate", geometry=pv.Box(size=(0.47, 0.47, thickness), material=pv.Material(
+        refractive_index=n_plate, components=[pv.Absorber(coefficient=alpha)])), parent=world)
+    plate.translate((0, 0, -0.5 * thickness))
+    return pv.Scene(world)
+
+
+@pytest.mark.parametrize("elevation", [90.0, 50.0, 25.0])
+def test_absorbing_slab_matches_the_closed_form(elevation, built_library):
+    """Unpolarised Fresnel reflectivity R at both faces (the same by reciprocity), single-pass survival s = exp(-alpha d /
+    cos t): reflected at entry R; out of the bottom (1-R)^2 s / (1 - R^2 s^2); out of the top after entering
+    (1-R)^2 R s^2 / (1 - R^2 s^2); absorbed: the rest.  No restatement involved - Snell, Fresnel, Beer-Lambert and the
+    geometric series.  The light mask is shrunk to the middle of the plate so that no bounce sequence reaches an edge."""
+    from lscpm_b200 import backend, flatten, lights
+
+    alpha, n, d = 20.0, 1.48, 0.008
+    arrays = flatten.flatten_scene(_slab_scene(alpha, n, d), with_light=False)
+    names = arrays.bin_names()
+    table = lights.direct_batches(0.0, [elevation], [180.0], wavelength_nm=555.0)
+    table.desc["mask_half"] = 0.1
+    photons = 20_000_000
+    row = backend.trace_lights(arrays, table, photons, seed=2026, device=0)[0]
+    got = dict(zip(names, (int(c) for c in row[:len(names)])))
+    assert sum(got.values()) == photons
+
+    ti = np.radians(90.0 - elevation)
+    tt = np.arcsin(np.sin(ti) / n)
+    ci, ct = np.cos(ti), np.cos(tt)
+    rs = (ci - n * ct) / (ci + n * ct)
+    rp = (ct - n * ci) / (ct + n * ci)
+    R = 0.5 * (rs * rs + rp * rp)
+    s = np.exp(-alpha * d / ct)
+    geo = 1.0 - R * R * s * s
+    expect = {"exit/entry_reflect": R, "exit/plate/-z": (1 - R) ** 2 * s / geo, "exit/plate/+z": (1 - R) ** 2 * R * s * s / geo}
+    expect["absorb/plate/0"] = 1.0 - sum(expect.values())
+    for name, p in expect.items():
+        sigma = np.sqrt(p * (1 - p) / photons)
+        assert abs(got[name] / photons - p) < 4.5 * sigma + 2e-6, (name, got[name] / photons, p, sigma)
+    assert sum(got[k] for k in expect) == photons, {k: v for k, v in got.items() if v and k not in expect}
+    # interaction events per photon: the entry, then one per face visit or absorption - expected number of those per
+    # photon that entered: sum over passes k of (R s)^k = 1 / (1 - R s)
+    events = row[len(names)] / photons
+    assert abs(events - (1.0 + (1.0 - R) / (1.0 - R * s))) < 2e-3
