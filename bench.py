@@ -533,11 +533,12 @@ def run_cuda(args) -> None:
 
     # ---- end to end through the public API: host descriptors in, host tallies out, every step --------
     e2e_steps = max(1, args.steps)
-    backend.trace_lights(arrays, lights, ppb, seed=1, device=device, batch_ids=my_ids)
+    host_table = backend.batch_table(lights, my_ids)      # LscpmBatchDesc[nb] + spectra in host memory: the API's input format
+    backend.trace_lights(arrays, host_table, ppb, seed=1, device=device)
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        host = backend.trace_lights(arrays, lights, ppb, seed=7000 + k, device=device, batch_ids=my_ids)
+        host = backend.trace_lights(arrays, host_table, ppb, seed=7000 + k, device=device)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     h2d_bytes = int(lib.lscpm_plan_h2d_bytes(plan.handle))
@@ -577,7 +578,8 @@ def run_cuda(args) -> None:
             "reacted_fraction": reacted_fraction,
             "e2e": {"value": photons_per_step / (ms_e2e * 1e-3), "unit": "photons/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
-                    "api": "lscpm_b200.backend.trace_lights -> lscpm_trace_host (host descriptors lowered + H2D, launch, D2H of the tallies)"},
+                    "api": "lscpm_b200.backend.trace_lights(BatchTable) -> lscpm_trace_host: host LscpmBatchDesc[] + spectra lowered and copied H2D, "
+                           "launch, D2H of the tallies, every step"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "kernel_ms": {"slowest_rank_mean": ms_kernel, "fastest_rank_mean": ms_kernel_fastest,
