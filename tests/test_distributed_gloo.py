@@ -65,9 +65,9 @@ def _worker(rank, world, port, n_batches, ppb, by, out_dir):
     torch.distributed.destroy_process_group()
 
 
-@pytest.mark.parametrize("by", ["batch", "photon"])
-def test_world_size_2_gloo(by, tmp_path):
-    n_batches, ppb, world = 5, 601, 2
+@pytest.mark.parametrize("by,n_batches", [("batch", 5), ("photon", 5), ("batch", 1)])   # 1 batch: rank 1 owns nothing
+def test_world_size_2_gloo(by, n_batches, tmp_path):
+    ppb, world = 601, 2
     mp.spawn(_worker, args=(world, _free_port(), n_batches, ppb, by, str(tmp_path)), nprocs=world, join=True)
     trace_fn, stride = _oracle_trace_fn(n_batches)
     whole = trace_fn(np.arange(n_batches), 0, ppb).numpy()
