@@ -140,3 +140,77 @@ def test_absorbing_slab_matches_the_closed_form(elevation, built_library):
     # photon that entered: sum over passes k of (R s)^k = 1 / (1 - R s)
     events = row[len(names)] / photons
     assert abs(events - (1.0 + (1.0 - R) / (1.0 - R * s))) < 2e-3
+
+
+# ---- an analytic known answer for the capillary lattice: index-matched black tubes -------------------------------------------
+
+
+def _black_tube_scene(with_idle_dye, n_plate=1.48, n_tubes=16, pitch=0.03, r_outer=0.0015875):
+    """Non-absorbing plate holding index-matched, totally absorbing tubes (no Fresnel event and no refraction at their
+    surface).  `with_idle_dye` adds a luminophore that absorbs nothing, which selects the plate-flight kernels."""
+    from lscpm_b200.compat import pvtrace_api as pv
+    from lscpm_b200.miniplant.utils import LightPosition, VectorInverter
+    from lscpm_b200.workloads import ConstantWavelength
+
+    world = pv.Node(name="World (air)", geometry=pv.Sphere(radius=10.0, material=pv.Material(refractive_index=1.0)))
+    sun = pv.spherical_to_cart(0.0, 0.0)
+    light = pv.Node(name="Solar Light", light=pv.Light(wavelength=ConstantWavelength(555.0), direction=VectorInverter(sun),
+                                                       position=LightPosition(tilt_angle=0.0)), parent=world)
+    light.translate(sun)
+    components = [pv.Absorber(coefficient=0.0)]
+    if with_idle_dye:
+        grid = np.linspace(300.0, 800.0, 51)
+        components.append(pv.Luminophore(coefficient=np.stack([grid, np.zeros_like(grid)], axis=1),
+                                         emission=np.stack([grid, np.exp(-((grid - 620.0) / 30.0) ** 2)], axis=1),
+                                         quantum_yield=0.95, phase_function=pv.isotropic))
+    plate = pv.Node(name="plate", geometry=pv.Box(size=(0.47, 0.47, 0.008), material=pv.Material(
+        refractive_index=n_plate, components=components)), parent=world)
+    tube_geom = pv.Cylinder(length=0.47, radius=r_outer, material=pv.Material(
+        refractive_index=n_plate, components=[pv.Absorber(coefficient=1e7)]))
+    x0 = -0.5 * pitch * (n_tubes - 1)
+    for k in range(n_tubes):
+        tube = pv.Node(name=f"tube_{k}", geometry=tube_geom, parent=plate)
+        tube.rotate(np.radians(90), (1, 0, 0))
+        tube.translate((x0 + pitch * k, 0, 0))
+    plate.translate((0, 0, -0.004))
+    return pv.Scene(world)
+
+
+@pytest.mark.parametrize("with_idle_dye", [False, True])
+@pytest.mark.parametrize("elevation,azimuth", [(90.0, 180.0), (40.0, 90.0), (60.0, 270.0)])
+def test_black_tubes_shadow_their_geometric_cross_section(elevation, azimuth, with_idle_dye, built_library):
+    """Rays that travel in planes x = const (sun at zenith, or due east / west of the plate: no x component) keep their x:
+    such a ray is absorbed iff it enters within r_o of a tube axis, on its first way down - the ones reflected at the
+    bottom face retrace an x that missed.  With h = 16 * 2 r_o / 0.47 and the Fresnel reflectivity R of the faces:
+    tubes (1-R) h, entry reflection R, bottom (1-R)^2 (1-h) / (1-R^2), top (1-R)^2 (1-h) R / (1-R^2); every tube the same
+    share.  Both geometry code paths: cell march (no luminophore) and plate flights (a luminophore that absorbs nothing)."""
+    from lscpm_b200 import backend, flatten, lights
+
+    n, r_o, width = 1.48, 0.0015875, 0.47
+    arrays = flatten.flatten_scene(_black_tube_scene(with_idle_dye), with_light=False)
+    names = arrays.bin_names()
+    table = lights.direct_batches(0.0, [elevation], [azimuth], wavelength_nm=555.0)
+    table.desc["mask_half"] = (0.235, 0.05)          # the whole width in x; the middle in y, away from the tube ends
+    photons = 20_000_000
+    row = backend.trace_lights(arrays, table, photons, seed=777, device=0)[0]
+    got = dict(zip(names, (int(c) for c in row[:len(names)])))
+    assert sum(got.values()) == photons
+    handle = backend.scene_handle(arrays, 0)
+    assert ("flight=1" in handle.kernel_name) == with_idle_dye, handle.kernel_name
+
+    ti = np.radians(90.0 - elevation)
+    tt = np.arcsin(np.sin(ti) / n)
+    ci, ct = np.cos(ti), np.cos(tt)
+    R = 0.5 * (((ci - n * ct) / (ci + n * ct)) ** 2 + ((ct - n * ci) / (ct + n * ci)) ** 2)
+    h = 16 * 2 * r_o / width
+    expect = {"tubes": (1 - R) * h, "exit/entry_reflect": R, "exit/plate/-z": (1 - R) ** 2 * (1 - h) / (1 - R * R),
+              "exit/plate/+z": (1 - R) ** 2 * (1 - h) * R / (1 - R * R)}
+    tubes = np.array([got[f"absorb/tube_{k}/0"] for k in range(16)])
+    measured = dict(got, tubes=int(tubes.sum()))
+    assert abs(sum(expect.values()) - 1.0) < 1e-12
+    for name, p in expect.items():
+        sigma = np.sqrt(p * (1 - p) / photons)
+        assert abs(measured[name] / photons - p) < 4.5 * sigma + 2e-6, (name, measured[name] / photons, p, sigma)
+    assert sum(measured[k] for k in expect) == photons, {k: v for k, v in got.items() if v and not k.startswith("absorb/tube") and k not in expect}
+    share = tubes.sum() / 16.0
+    assert np.all(np.abs(tubes - share) < 4.5 * np.sqrt(share)), tubes
