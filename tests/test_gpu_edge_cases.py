@@ -218,3 +218,26 @@ def test_plate_array_with_dense_channel_grid_one_plate_per_batch(native, built_l
                                  resample=lambda i=i: backend.trace_lights(arrays, table, photons, seed=77, device=0)[i][:len(names)])
             plate += 1
     assert plate == 9
+
+
+def test_bare_plate_folded_flights_at_high_statistics(native, built_library):
+    """The plate without capillaries has no coincident faces and no adjacency question: for it the generic oracle is a
+    plain box billiard with Fresnel faces, while the GPU folds every run of total internal reflections into one plate
+    flight.  2e7 photons (most of the re-emitted light is trapped and walks to the edges): every bin within 4.5 sigma, no
+    re-draw, and the events per photon - which count every folded reflection - to 1.5e-3 (3.5 sigma)."""
+    from helpers import bins_outside_band
+    from lscpm_b200 import backend, flatten
+
+    arrays = flatten.flatten_scene(_custom_scene(n_channels=0, pitch=0.03, tilt=10.0))
+    handle = backend.scene_handle(arrays, 0)
+    assert "flight=1" in handle.kernel_name
+    n = 20_000_000
+    names = arrays.bin_names()
+    row = backend.trace_lights(arrays, [arrays.light], n, seed=61, device=0)[0]
+    ref = _oracle_row(arrays, native, n, seed=62)
+    assert row[:len(names)].sum() == n
+    assert not bins_outside_band(names, row[:len(names)], ref[:len(names)], z=4.5)
+    edges = sum(int(c) for name, c in zip(names, row) if name.startswith("exit/plate/") and name[-2:] in ("-x", "+x", "-y", "+y"))
+    assert edges > 0.15 * n                                 # the case is about trapped light (18.6 % leaves through the edges)
+    # events per photon have a long tail (trapped photons bounce up to 1000 times): sigma of the two-sample ratio ~4e-4
+    assert abs(row[len(names)] / ref[len(names)] - 1.0) < 1.5e-3, (row[len(names)] / n, ref[len(names)] / n)
