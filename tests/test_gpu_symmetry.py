@@ -214,3 +214,52 @@ def test_black_tubes_shadow_their_geometric_cross_section(elevation, azimuth, wi
     assert sum(measured[k] for k in expect) == photons, {k: v for k, v in got.items() if v and not k.startswith("absorb/tube") and k not in expect}
     share = tubes.sum() / 16.0
     assert np.all(np.abs(tubes - share) < 4.5 * np.sqrt(share)), tubes
+
+
+# ---- two geometry code paths against each other: folded plate flights vs explicit bounces ----------------------------------
+
+
+def _scene_handle_with_env(arrays, **env):
+    import os
+
+    from lscpm_b200 import backend
+
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return backend.SceneHandle(arrays, 0)       # the choice of kernel and geometry is made at scene creation
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("case", [dict(tilt=0, elevation=90, spectrum=am15_like_photon_spectrum()),
+                                  dict(tilt=35, elevation=30, azimuth=150, wavelength=585.0)])
+def test_folded_flights_agree_with_explicit_bounces(case, built_library):
+    """The default path takes a photon in the plastic straight to its next real event through the unfolded lattice of
+    capillary images (plate_flight, pool kernel); with LSCPM_PLATE_FLIGHTS=0 the lane kernel marches cell by cell and
+    makes every total internal reflection an iteration of its own.  Different geometry code, different draws per photon,
+    same physics: every bin within 4.5 sigma at 2e7 photons, the events per photon (which count the folded reflections) to
+    1.5e-3."""
+    import torch
+
+    from lscpm_b200 import backend, flatten
+
+    arrays = flatten.flatten_scene(standard_scene(**case))
+    names = arrays.bin_names()
+    rows = {}
+    for label, env in (("flights", {}), ("bounces", dict(LSCPM_PLATE_FLIGHTS=0, LSCPM_TRACE_KERNEL="lanes"))):
+        scene = _scene_handle_with_env(arrays, **env)
+        assert ("flight=1" in scene.kernel_name) == (label == "flights"), scene.kernel_name
+        plan = backend.Plan(scene, [arrays.light] * 4, list(range(4)))
+        tallies = plan.new_tallies()
+        plan.trace_into(tallies, N // 4, seed=11 if label == "flights" else 12)
+        torch.cuda.synchronize()
+        rows[label] = tallies.sum(dim=0).cpu().numpy()
+    a, b = rows["flights"], rows["bounces"]
+    assert a[:len(names)].sum() == b[:len(names)].sum() == N
+    assert not bins_outside_band(names, a[:len(names)], b[:len(names)], z=4.5)
+    assert abs(a[len(names)] / b[len(names)] - 1.0) < 1.5e-3, (a[len(names)] / N, b[len(names)] / N)
