@@ -1124,13 +1124,23 @@ enum PoolConfig { POOL_OFF = 0, POOL_96 = 1, POOL_WIDE_64 = 2, POOL_80 = 3, POOL
 int pool_warps(int cfg) { return cfg == POOL_WIDE_64 ? POOL_WARPS_WIDE : POOL_WARPS; }
 int pool_slots(int cfg) { return (cfg == POOL_120 ? 120 : (cfg == POOL_96 ? 96 : (cfg == POOL_80 ? 80 : 64))); }
 TraceKernel pool_kernel(const LscpmScene* s, int cfg) {
-    switch (cfg) {
-        case POOL_120: return s->flight ? trace_pool_kernel<true, POOL_WARPS, 120> : trace_pool_kernel<false, POOL_WARPS, 120>;
-        case POOL_96: return s->flight ? trace_pool_kernel<true, POOL_WARPS, 96> : trace_pool_kernel<false, POOL_WARPS, 96>;
-        case POOL_80: return s->flight ? trace_pool_kernel<true, POOL_WARPS, 80> : trace_pool_kernel<false, POOL_WARPS, 80>;
-        case POOL_64: return s->flight ? trace_pool_kernel<true, POOL_WARPS, 64> : trace_pool_kernel<false, POOL_WARPS, 64>;
-        default: return s->flight ? trace_pool_kernel<true, POOL_WARPS_WIDE, 64> : trace_pool_kernel<false, POOL_WARPS_WIDE, 64>;
+    if (s->dev.n_ext > 0) {   // scenes with outside boxes: five-group records, no plate flights
+        switch (cfg) {
+            case POOL_96: return trace_pool_kernel<true, false, POOL_WARPS, 96>;
+            case POOL_80: return trace_pool_kernel<true, false, POOL_WARPS, 80>;
+            default: return trace_pool_kernel<true, false, POOL_WARPS, 64>;
+        }
     }
+    switch (cfg) {
+        case POOL_120: return s->flight ? trace_pool_kernel<false, true, POOL_WARPS, 120> : trace_pool_kernel<false, false, POOL_WARPS, 120>;
+        case POOL_96: return s->flight ? trace_pool_kernel<false, true, POOL_WARPS, 96> : trace_pool_kernel<false, false, POOL_WARPS, 96>;
+        case POOL_80: return s->flight ? trace_pool_kernel<false, true, POOL_WARPS, 80> : trace_pool_kernel<false, false, POOL_WARPS, 80>;
+        case POOL_64: return s->flight ? trace_pool_kernel<false, true, POOL_WARPS, 64> : trace_pool_kernel<false, false, POOL_WARPS, 64>;
+        default: return s->flight ? trace_pool_kernel<false, true, POOL_WARPS_WIDE, 64> : trace_pool_kernel<false, false, POOL_WARPS_WIDE, 64>;
+    }
+}
+size_t pool_smem(const LscpmScene* s, int cfg) {
+    return pool_smem_bytes(pool_warps(cfg), pool_slots(cfg), s->dev.n_bins + LSCPM_N_COUNTERS, s->dev.n_ext > 0);
 }
 
 int pick_counter(LscpmScene* s, cudaStream_t stream, unsigned long long** out, unsigned* slot_out) {
@@ -1381,28 +1391,27 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
     // LSCPM_TRACE_KERNEL=pool|pool96|pool80|pool64 forces it (bit-identical tallies in every configuration).
     s->pool = POOL_OFF;
     s->pool_small_plan = POOL_OFF;
-    if (s->dev.n_ext == 0) {
-        const int stride = s->dev.n_bins + LSCPM_N_COUNTERS;
+    {
+        const bool ext = s->dev.n_ext > 0;
         const size_t optin = (size_t)prop.sharedMemPerBlockOptin;
-        auto fits = [&](int cfg) { return pool_smem_bytes(pool_warps(cfg), pool_slots(cfg), stride) <= optin; };
+        auto fits = [&](int cfg) { return pool_smem(s, cfg) <= optin; };
         const bool forced = which && strncmp(which, "pool", 4) == 0;
         bool pinned = false;        // a configuration named in the environment is used for every launch
-        if (s->flight || forced) s->pool = POOL_96;
+        if (s->flight || forced || ext) s->pool = POOL_96;
         if (which && (strcmp(which, "lanes") == 0 || strcmp(which, "sorted") == 0)) s->pool = POOL_OFF;
-        if (which && strcmp(which, "pool120") == 0) { s->pool = POOL_120; pinned = true; }
+        if (which && strcmp(which, "pool120") == 0) { s->pool = ext ? POOL_96 : POOL_120; pinned = true; }
         if (which && strcmp(which, "pool96") == 0) { s->pool = POOL_96; pinned = true; }
         if (which && strcmp(which, "pool80") == 0) { s->pool = POOL_80; pinned = true; }
-        if (which && strcmp(which, "pool64") == 0) { s->pool = POOL_WIDE_64; pinned = true; }
-        while (s->pool && !fits(s->pool))      // wide tally rows: fewer records, finally the lane kernel
+        if (which && strcmp(which, "pool64") == 0) { s->pool = ext ? POOL_64 : POOL_WIDE_64; pinned = true; }
+        while (s->pool && !fits(s->pool))      // wide tally rows: fewer records, finally the lane / sorted kernel
             s->pool = (s->pool == POOL_120) ? POOL_96 : (s->pool == POOL_96 ? POOL_80 : (s->pool == POOL_80 ? POOL_64 : POOL_OFF));
-        if (s->pool == POOL_96 && !pinned && fits(POOL_120)) s->pool_small_plan = POOL_120;
+        if (s->pool == POOL_96 && !pinned && !ext && fits(POOL_120)) s->pool_small_plan = POOL_120;
         for (int cfg : {s->pool, s->pool_small_plan}) {
             if (!cfg) continue;
             if ((e = cudaFuncSetAttribute(pool_kernel(s, cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)) != cudaSuccess)
                 return bail(cuda_fail(e, "cudaFuncSetAttribute (pool kernel)"));
             int fit = 0;
-            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, pool_kernel(s, cfg), pool_warps(cfg) * 32,
-                                                                   pool_smem_bytes(pool_warps(cfg), pool_slots(cfg), stride))) != cudaSuccess)
+            if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, pool_kernel(s, cfg), pool_warps(cfg) * 32, pool_smem(s, cfg))) != cudaSuccess)
                 return bail(cuda_fail(e, "occupancy query (pool kernel)"));
             if (fit < 1) { if (cfg == s->pool) s->pool = POOL_OFF; s->pool_small_plan = POOL_OFF; }
         }
@@ -1430,8 +1439,8 @@ int lscpm_scene_kernel_name(const LscpmScene* s, char* buf, int buf_len) {
     if (!s) return fail(LSCPM_EINVAL, "scene is NULL");
     char text[160];
     if (s->pool) {
-        snprintf(text, sizeof(text), "trace_pool_kernel<flight=%d, warps=%d, records=%d>%s", s->flight ? 1 : 0, pool_warps(s->pool),
-                 pool_slots(s->pool), s->pool_small_plan ? " (records=120 for plans <= 16 KB)" : "");
+        snprintf(text, sizeof(text), "trace_pool_kernel<ext=%d, flight=%d, warps=%d, records=%d>%s", s->dev.n_ext > 0 ? 1 : 0,
+                 s->flight ? 1 : 0, pool_warps(s->pool), pool_slots(s->pool), s->pool_small_plan ? " (records=120 for plans <= 16 KB)" : "");
     } else if (s->sorted) {
         snprintf(text, sizeof(text), "trace_sorted_kernel<ext=%d, flight=%d, block=%d>%s", s->dev.n_ext > 0 ? 1 : 0, s->flight ? 1 : 0, SORT_THREADS,
                  s->sorted_forced ? "" : " (trace_kernel for launches below 4 blocks' worth of photons per resident block)");
@@ -1626,8 +1635,7 @@ int lscpm_trace_plan(LscpmPlan* p, uint64_t photon_begin, uint64_t photon_count,
     } else {
         const unsigned long long warps = (unsigned long long)lane_warps;
         const int blocks = (int)std::min<unsigned long long>((unsigned long long)grid, (a.n_chunks + warps - 1) / warps);
-        if (pool) pool_kernel(s, pool_cfg)<<<std::max(blocks, 1), lane_warps * 32,
-                                             pool_smem_bytes(lane_warps, pool_slots(pool_cfg), s->dev.n_bins + LSCPM_N_COUNTERS), stream>>>(s->dev, a);
+        if (pool) pool_kernel(s, pool_cfg)<<<std::max(blocks, 1), lane_warps * 32, pool_smem(s, pool_cfg), stream>>>(s->dev, a);
         else lane_kernel(s)<<<std::max(blocks, 1), s->trace_block, s->trace_smem, stream>>>(s->dev, a);
     }
     g_launches.fetch_add(1);

@@ -32,28 +32,38 @@
 //
 // The phase code is the very device code of K2 / K2s (advance_hit, interact_*, source_*) fed with the same Philox words in
 // the same order, so the tallies are bit-identical to K2's for every scene, batch shape and photon offset
-// (tests/test_gpu_sorted_kernel.py covers all three kernels).  Scenes with outside boxes stay on K2s / K2.
+// (tests/test_gpu_sorted_kernel.py covers all three kernels).
+//
+// EXT (scenes with boxes outside the plate - the photovoltaic variants): the air around the plate is a medium with geometry
+// of its own (outside_step).  Such scenes have no plate flights, so the PH_PLATE list serves as PH_OUT - photons travelling
+// outside the plate - and the record grows by a fifth uint4 for the surface bookkeeping word (`aux`) that the EXIT
+// classification of these scenes needs.
 #pragma once
 #include "lscpm_device.cuh"
 
 namespace lscpm {
 
 constexpr int PH_FRESH = 0, PH_PLATE = 1, PH_TUBE = 2, PH_EMIT = 3, N_PH = 4;
+constexpr int PH_OUT = PH_PLATE;          // scenes with outside boxes have no plate flights: the list holds the photons in the air
 
 // record = 4 x uint4 (SoA over the slots of a warp):
 //   G0: xr, y, z, kc | medium << 12 | steps << 16
 //   G1: dx, dy, dz, wl
 //   G2: photon index lo, hi, batch (index into the plan), batch id (Philox counter word)
 //   G3: event counters, emission table of a pending re-emission (PH_EMIT), unused, Philox call counter
-constexpr int POOL_GROUPS = 4;
+//   G4 (scenes with outside boxes only): aux (surface bookkeeping of the EXIT classification, emission table), unused x 3
+__host__ __device__ constexpr int pool_groups(bool ext) { return ext ? 5 : 4; }
 
 __host__ __device__ constexpr int pool_list_u4(int nslot) { return (N_PH * nslot + 15) / 16; }
-__host__ __device__ constexpr size_t pool_smem_bytes(int warps, int nslot, int stride) {
-    return (size_t)warps * (size_t)(POOL_GROUPS * nslot + pool_list_u4(nslot) + (stride + 3) / 4) * 16u;
+__host__ __device__ constexpr size_t pool_smem_bytes(int warps, int nslot, int stride, bool ext = false) {
+    return (size_t)warps * (size_t)(pool_groups(ext) * nslot + pool_list_u4(nslot) + (stride + 3) / 4) * 16u;
 }
 
-template <bool FLIGHT>
-__device__ __forceinline__ int fly_phase(int medium) { return (FLIGHT && medium == MED_PLATE) ? PH_PLATE : PH_TUBE; }
+template <bool FLIGHT, bool EXT = false>
+__device__ __forceinline__ int fly_phase(int medium) {
+    if (EXT) return medium == MED_OUT ? PH_OUT : PH_TUBE;
+    return (FLIGHT && medium == MED_PLATE) ? PH_PLATE : PH_TUBE;
+}
 
 // List lengths, warp-uniform, packed into ONE word: phase k in byte k (NSLOT <= 255).
 //
@@ -91,11 +101,13 @@ __device__ __forceinline__ void pool_tally(unsigned long long* __restrict__ tall
 // The kernel itself is compiled inside lscpm.cu, after TraceArgs / flush_row (this header is not stand-alone).
 #ifdef LSCPM_POOL_KERNEL_BODY
 
-template <bool FLIGHT, int WARPS, int NSLOT>
+template <bool EXT, bool FLIGHT, int WARPS, int NSLOT>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_constant__ TraceArgs A) {
     using namespace lscpm;
     static_assert(NSLOT % 8 == 0 && NSLOT <= 255, "slot numbers and list lengths travel as bytes");
+    static_assert(!(EXT && FLIGHT), "plate flights assume air beyond the z faces");
+    constexpr int POOL_GROUPS = pool_groups(EXT);
     extern __shared__ uint4 pool_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lane_lt = (1u << lane) - 1u;
@@ -184,14 +196,14 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                         p.xr = __uint_as_float(g0.x); p.y = __uint_as_float(g0.y); p.z = __uint_as_float(g0.z);
                         p.kc = g0.w & 0xfff; p.medium = (g0.w >> 12) & 15; p.steps = g0.w >> 16;
                         p.wl = __uint_as_float(G[1 * NSLOT + slot].w);
-                        p.aux = (int)(g3.y << 16);
+                        p.aux = EXT ? (int)G[4 * NSLOT + slot].x : (int)(g3.y << 16);    // carries the emission table (bits 16-23)
                         rng.p_lo = g2.x; rng.p_hi = g2.y; batch = (int)g2.z; rng.batch = g2.w; rng.calls = g3.w;
                         n_events = g3.x;
                     }
                     const uint4 v = rng.next(A.rk);
                     WavelengthDraw wd;
                     int bin = -1;
-                    if (fresh) bin = source_fresh<false, true>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr, n_events);
+                    if (fresh) bin = source_fresh<EXT, true>(S, A.batches[batch], A.spec_x, A.spec_cdf, A.spec_guide, rng, v, p, wd, nullptr, n_events);
                     else source_emit(S, v, p, wd);
                     source_wavelength(p, wd);
                     if (bin >= 0) {   // reflected off the plate at first contact, or never touched it: the record stays empty
@@ -201,6 +213,24 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                     }
                 }
                 if (fresh) c_next += (unsigned)n;
+            }
+            // A new photon of a scene with outside boxes may start in the air, on a plate face or inside the plate.  When
+            // every lane's photon starts in the air (the reference's lights do: they sit 1 m up-beam of the plate), the first
+            // step in the air follows right here; otherwise there is no common next step and the photons wait in the lists
+            // of their media.
+            bool fresh_outside = false;
+            if (EXT && fresh) {
+                fresh_outside = __all_sync(FULL_MASK, !fly || p.medium == MED_OUT);
+                if (!fresh_outside && fly) {
+                    nph = fly_phase<FLIGHT, EXT>(p.medium);
+                    G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
+                                                     (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
+                    G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl));
+                    G[2 * NSLOT + slot] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.batch);
+                    G[3 * NSLOT + slot] = make_uint4(n_events, 0u, 0u, rng.calls);
+                    G[4 * NSLOT + slot].x = (unsigned)p.aux;
+                    fly = false;
+                }
             }
             // ---- step draw, nearest interface, free path, move; absorption is settled here as well ---------------
             bool keep = false;              // the photon lives on: its record is written back below, by all such lanes at once
@@ -213,12 +243,28 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                     p.dx = __uint_as_float(g1.x); p.dy = __uint_as_float(g1.y); p.dz = __uint_as_float(g1.z); p.wl = __uint_as_float(g1.w);
                     rng.p_lo = g2.x; rng.p_hi = g2.y; batch = (int)g2.z; rng.batch = g2.w; rng.calls = g3.w;
                     n_events = g3.x;
+                    if (EXT) p.aux = (int)G[4 * NSLOT + slot].x;
                 }
                 const uint4 w = rng.next(A.rk);
-                Hit h; int cls, extra; float alpha;
-                int bin = advance_hit<true, FLIGHT, true, true>(S, p, w.x, h, cls, extra, alpha);
-                n_events += (unsigned)extra;
-                if (bin < 0) {
+                Hit h; int cls = CLS_CELL, extra = 0; float alpha = 0.f;
+                int bin = -1;
+                const bool outside = EXT && (ph == PH_OUT || fresh_outside);   // warp-uniform: only photons in the air
+                if (outside) {
+                    // one follow() iteration in the air around the plate: next hit among the plate and the outside boxes
+                    OutState q;
+                    q.x = abs_x(S, p); q.y = p.y; q.z = p.z + S.zc; q.dx = p.dx; q.dy = p.dy; q.dz = p.dz; q.aux = p.aux; q.steps = p.steps;
+                    const OutResult r = outside_step(S, q, u01(w.y));
+                    p.dx = r.dx; p.dy = r.dy; p.dz = r.dz; p.aux = r.aux; p.steps = r.steps;
+                    if (counts_as_event(r.event)) n_events += 1u + (unsigned)r.extra;
+                    if (r.entered) { p.y = r.y; locate_in_plate(S, p, r.x, r.z); }
+                    else { p.kc = 0; p.xr = r.x - axis_x(S, 0); p.y = r.y; p.z = r.z - S.zc; }
+                    bin = r.bin;
+                    if (bin < 0) nph = fly_phase<FLIGHT, EXT>(p.medium);
+                } else {
+                    bin = advance_hit<true, FLIGHT, true, true>(S, p, w.x, h, cls, extra, alpha);
+                    n_events += (unsigned)extra;
+                }
+                if (bin < 0 && !outside) {
                     if (cls == CLS_ABSORB) {
                         n_events += 1u;
                         int ev;
@@ -229,15 +275,15 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                             pend = (unsigned)(p.aux >> 16) & 0xffu;
                         }
                     } else if (cls == CLS_CELL) {
-                        nph = fly_phase<FLIGHT>(p.medium);
+                        nph = fly_phase<FLIGHT, EXT>(p.medium);
                     } else {
                         // Fresnel test on the interface the photon was moved to, in the same execution: about half of a
                         // flight's lanes are here, and a phase of its own would cost them more in bookkeeping and record
                         // traffic than the idle lanes cost here
                         n_events += 1u;
                         int ev;
-                        bin = interact_surface<false>(S, p, h.kind, h.face, h.container, h.adj, u01(w.y), ev);
-                        if (bin < 0) nph = fly_phase<FLIGHT>(p.medium);
+                        bin = interact_surface<EXT>(S, p, h.kind, h.face, h.container, h.adj, u01(w.y), ev);
+                        if (bin < 0) nph = fly_phase<FLIGHT, EXT>(p.medium);
                     }
                 }
                 if (bin >= 0) { tbin = bin; tbatch = batch; tevents = n_events; }
@@ -252,6 +298,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                 G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl));
                 if (fresh) G[2 * NSLOT + slot] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.batch);
                 G[3 * NSLOT + slot] = make_uint4(n_events, pend, 0u, rng.calls);
+                if (EXT) G[4 * NSLOT + slot].x = (unsigned)p.aux;
             }
         }
         if (tbin >= 0) pool_tally(A.tallies, hist, S.n_bins, stride, hbatch, tbatch, tbin, tevents);

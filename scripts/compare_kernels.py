@@ -20,6 +20,7 @@ CASES = {
     "diffuse": dict(tilt=30, diffuse=True, spectrum=am15_like_photon_spectrum()),
     "no_dye": dict(tilt=0, elevation=90, spectrum=am15_like_photon_spectrum(), include_dye=False),
     "pv_both": dict(tilt=0, elevation=60, spectrum=am15_like_photon_spectrum(), add_bottom_PV=True, add_side_PV=True),
+    "pv_bottom_tilted": dict(tilt=40, elevation=50, wavelength=555.0, add_bottom_PV=True),
 }
 
 
@@ -37,7 +38,7 @@ def timed(plan, tallies, ppb, seed):
 for label, kw in CASES.items():
     arrays = flatten.flatten_scene(standard_scene(**kw))
     out = {}
-    variants = ("lanes", "sorted") if "pv" in label else ("lanes", "sorted", "pool96", "pool64")
+    variants = ("lanes", "sorted", "pool96", "pool64")
     for which in variants:
         scene = handle(arrays, which)
         for nb, ppb in ((3, 70_001), (64, 1_000_000)):

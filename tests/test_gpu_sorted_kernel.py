@@ -55,7 +55,7 @@ def test_sorted_kernel_is_bit_identical(label):
         np.testing.assert_array_equal(a, b, err_msg=f"{label} batches={n_batches} photons={photons}")
 
 
-POOL_CASES = sorted(k for k in CASES if not k.startswith("pv_"))   # scenes with outside boxes have no pool kernel
+POOL_CASES = sorted(CASES)   # scenes with outside boxes included: their pool kernel carries a fifth record group
 
 
 @pytest.mark.parametrize("which", ["pool120", "pool96", "pool80", "pool64"])
@@ -87,16 +87,16 @@ def test_default_kernel_of_the_standard_scene_is_the_pool_kernel_and_agrees_with
     a, n_bins = _tallies(arrays, "lanes", 4, 250_000, seed=99)
     assert "LSCPM_TRACE_KERNEL" not in os.environ
     scene = backend.SceneHandle(arrays, 0)
-    assert scene.kernel_name.startswith("trace_pool_kernel<flight=1, warps=24, records=96>"), scene.kernel_name
+    assert scene.kernel_name.startswith("trace_pool_kernel<ext=0, flight=1, warps=24, records=96>"), scene.kernel_name
     plan = backend.Plan(scene, [arrays.light] * 4, list(range(10, 14)))
     tallies = plan.new_tallies()
     plan.trace_into(tallies, 250_000, 99)
     np.testing.assert_array_equal(a, tallies.cpu().numpy())
-    # scenes the pool kernel is not chosen for: no luminophore in the plate (lane kernel), outside boxes (block-sorted)
+    # a plate without luminophore stays on the lane kernel; scenes with outside boxes use the pool kernel with five-group records
     no_dye = backend.SceneHandle(flatten.flatten_scene(standard_scene(include_dye=False)), 0)
     assert no_dye.kernel_name.startswith("trace_kernel<ext=0, flight=0"), no_dye.kernel_name
     pv = backend.SceneHandle(flatten.flatten_scene(standard_scene(add_bottom_PV=True)), 0)
-    assert pv.kernel_name.startswith("trace_sorted_kernel<ext=1"), pv.kernel_name
+    assert pv.kernel_name.startswith("trace_pool_kernel<ext=1, flight=0"), pv.kernel_name
 
 
 def test_sorted_kernel_photon_offset_and_many_small_batches():
