@@ -780,7 +780,7 @@ struct LscpmScene {
     size_t trace_smem = 0;
     bool sorted = false;                 // block-sorted kernel or the lane-per-photon kernel
     bool sorted_forced = false;
-    bool flight = false;                 // plate flights (scenes without outside boxes whose plate holds a luminophore)
+    bool flight = false;                 // plate flights (plate holds a luminophore, no outside box shares one of its z faces)
     int sort_blocks_per_sm = 0;
     size_t sort_smem = 0;
     int pool = 0;                        // pool kernel configuration (PoolConfig), 0: lane / sorted kernel
@@ -1096,14 +1096,14 @@ int lower_batch(const LscpmScene* s, const LscpmBatchDesc* b, const std::vector<
 typedef void (*TraceKernel)(const DevScene, const TraceArgs);
 TraceKernel lane_kernel(const LscpmScene* s) {
     if (s->trace_block == TRACE_BLOCK_BIG) {
-        if (s->dev.n_ext > 0) return trace_kernel<true, false, TRACE_BLOCK_BIG>;
+        if (s->dev.n_ext > 0) return s->flight ? trace_kernel<true, true, TRACE_BLOCK_BIG> : trace_kernel<true, false, TRACE_BLOCK_BIG>;
         return s->flight ? trace_kernel<false, true, TRACE_BLOCK_BIG> : trace_kernel<false, false, TRACE_BLOCK_BIG>;
     }
-    if (s->dev.n_ext > 0) return trace_kernel<true, false, TRACE_BLOCK_SMALL>;
+    if (s->dev.n_ext > 0) return s->flight ? trace_kernel<true, true, TRACE_BLOCK_SMALL> : trace_kernel<true, false, TRACE_BLOCK_SMALL>;
     return s->flight ? trace_kernel<false, true, TRACE_BLOCK_SMALL> : trace_kernel<false, false, TRACE_BLOCK_SMALL>;
 }
 TraceKernel sorted_kernel(const LscpmScene* s) {
-    if (s->dev.n_ext > 0) return trace_sorted_kernel<true, false, SORT_THREADS>;
+    if (s->dev.n_ext > 0) return s->flight ? trace_sorted_kernel<true, true, SORT_THREADS> : trace_sorted_kernel<true, false, SORT_THREADS>;
     return s->flight ? trace_sorted_kernel<false, true, SORT_THREADS> : trace_sorted_kernel<false, false, SORT_THREADS>;
 }
 
@@ -1124,11 +1124,12 @@ enum PoolConfig { POOL_OFF = 0, POOL_96 = 1, POOL_WIDE_64 = 2, POOL_80 = 3, POOL
 int pool_warps(int cfg) { return cfg == POOL_WIDE_64 ? POOL_WARPS_WIDE : POOL_WARPS; }
 int pool_slots(int cfg) { return (cfg == POOL_120 ? 120 : (cfg == POOL_96 ? 96 : (cfg == POOL_80 ? 80 : 64))); }
 TraceKernel pool_kernel(const LscpmScene* s, int cfg) {
-    if (s->dev.n_ext > 0) {   // scenes with outside boxes: five-group records, no plate flights
+    if (s->dev.n_ext > 0) {   // scenes with outside boxes: the air phase in the plate flights' list slot, or in a fifth list
         switch (cfg) {
-            case POOL_96: return trace_pool_kernel<true, false, POOL_WARPS, 96>;
-            case POOL_80: return trace_pool_kernel<true, false, POOL_WARPS, 80>;
-            default: return trace_pool_kernel<true, false, POOL_WARPS, 64>;
+            case POOL_120: return s->flight ? trace_pool_kernel<true, true, POOL_WARPS, 120> : trace_pool_kernel<true, false, POOL_WARPS, 120>;
+            case POOL_96: return s->flight ? trace_pool_kernel<true, true, POOL_WARPS, 96> : trace_pool_kernel<true, false, POOL_WARPS, 96>;
+            case POOL_80: return s->flight ? trace_pool_kernel<true, true, POOL_WARPS, 80> : trace_pool_kernel<true, false, POOL_WARPS, 80>;
+            default: return s->flight ? trace_pool_kernel<true, true, POOL_WARPS, 64> : trace_pool_kernel<true, false, POOL_WARPS, 64>;
         }
     }
     switch (cfg) {
@@ -1140,7 +1141,7 @@ TraceKernel pool_kernel(const LscpmScene* s, int cfg) {
     }
 }
 size_t pool_smem(const LscpmScene* s, int cfg) {
-    return pool_smem_bytes(pool_warps(cfg), pool_slots(cfg), s->dev.n_bins + LSCPM_N_COUNTERS, s->dev.n_ext > 0);
+    return pool_smem_bytes(pool_warps(cfg), pool_slots(cfg), s->dev.n_bins + LSCPM_N_COUNTERS, pool_lists(s->dev.n_ext > 0, s->flight));
 }
 
 int pick_counter(LscpmScene* s, cudaStream_t stream, unsigned long long** out, unsigned* slot_out) {
@@ -1346,11 +1347,14 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
     // plate flights pay where light is trapped in the plastic, i.e. when the plate's material re-emits; a plate without a
     // luminophore (the reference's include_dye=False) is crossed once and is faster with the plain cell march.
     // LSCPM_PLATE_FLIGHTS=0|1 overrides (diagnostics; tallies agree statistically, not bit for bit).
+    // A flight folds the reflections at the z faces with the test against the world's medium: an outside box that shares
+    // one of those faces (none of the reference's does: the bottom cells hang 17 mm below the plate) rules flights out.
+    const bool flights_valid = s->dev.ext_touch[4] == 0u && s->dev.ext_touch[5] == 0u;
     s->flight = false;
-    if (s->dev.n_ext == 0)
+    if (flights_valid)
         for (int c = 0; c < s->dev.med[MED_PLATE].n_comp; ++c)
             if (s->dev.med[MED_PLATE].comp[c].kind == COMP_LUMINOPHORE) s->flight = true;
-    if (const char* f = getenv("LSCPM_PLATE_FLIGHTS")) s->flight = s->dev.n_ext == 0 && f[0] == '1';
+    if (const char* f = getenv("LSCPM_PLATE_FLIGHTS")) s->flight = flights_valid && f[0] == '1';
 #ifdef LSCPM_DIAG
     s->dev.diag_emit = getenv("LSCPM_DIAG_EMIT") ? atoi(getenv("LSCPM_DIAG_EMIT")) : 0;
 #endif
@@ -1386,8 +1390,8 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
             return bail(cuda_fail(e, "occupancy query (sorted kernel)"));
         if (s->sort_blocks_per_sm < 1) return bail(fail(LSCPM_ECUDA, "sorted trace kernel does not fit on an SM"));
     }
-    // The pool kernel (warp-private photon pools, lscpm_pool.cuh) is the default for scenes without outside boxes whose
-    // plate re-emits: that is where photons live long enough for the phase lists to stay full.
+    // The pool kernel (warp-private photon pools, lscpm_pool.cuh) is the default for scenes whose plate re-emits - that is
+    // where photons live long enough for the phase lists to stay full - and for every scene with outside boxes.
     // LSCPM_TRACE_KERNEL=pool|pool96|pool80|pool64 forces it (bit-identical tallies in every configuration).
     s->pool = POOL_OFF;
     s->pool_small_plan = POOL_OFF;
@@ -1399,13 +1403,13 @@ int lscpm_scene_create(const LscpmSceneDesc* desc, int device, LscpmScene** out)
         bool pinned = false;        // a configuration named in the environment is used for every launch
         if (s->flight || forced || ext) s->pool = POOL_96;
         if (which && (strcmp(which, "lanes") == 0 || strcmp(which, "sorted") == 0)) s->pool = POOL_OFF;
-        if (which && strcmp(which, "pool120") == 0) { s->pool = ext ? POOL_96 : POOL_120; pinned = true; }
+        if (which && strcmp(which, "pool120") == 0) { s->pool = POOL_120; pinned = true; }
         if (which && strcmp(which, "pool96") == 0) { s->pool = POOL_96; pinned = true; }
         if (which && strcmp(which, "pool80") == 0) { s->pool = POOL_80; pinned = true; }
         if (which && strcmp(which, "pool64") == 0) { s->pool = ext ? POOL_64 : POOL_WIDE_64; pinned = true; }
         while (s->pool && !fits(s->pool))      // wide tally rows: fewer records, finally the lane / sorted kernel
             s->pool = (s->pool == POOL_120) ? POOL_96 : (s->pool == POOL_96 ? POOL_80 : (s->pool == POOL_80 ? POOL_64 : POOL_OFF));
-        if (s->pool == POOL_96 && !pinned && !ext && fits(POOL_120)) s->pool_small_plan = POOL_120;
+        if (s->pool == POOL_96 && !pinned && fits(POOL_120)) s->pool_small_plan = POOL_120;
         for (int cfg : {s->pool, s->pool_small_plan}) {
             if (!cfg) continue;
             if ((e = cudaFuncSetAttribute(pool_kernel(s, cfg), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)optin)) != cudaSuccess)

@@ -817,6 +817,12 @@ __device__ __forceinline__ int note_surface(int aux, bool air_reflection, int no
     return aux;
 }
 
+// the reflections a plate flight folded in: each one is a surface interaction inside the plate (nothing recorded)
+__device__ __forceinline__ int note_folded(int aux, int bounces) {
+    const int n_surface = (aux >> 9) & 3;
+    return (aux & ~(3 << 9)) | (min(n_surface + bounces, 2) << 9);
+}
+
 // One follow() iteration of a photon travelling in the air around the plate: next hit among the plate and the outside
 // boxes (container = world, adjacent = hit), Fresnel test; an outside box that is entered absorbs at once (alpha ~1e10).
 __device__ __noinline__ OutResult outside_step(const DevScene& S, OutState q, float u_surf) {
@@ -1055,7 +1061,8 @@ __device__ __forceinline__ void plate_flight(const DevScene& S, Photon& p, const
 // `extra` counts the reflections folded into a plate flight.
 // BRANCH_ENTRY: skip the geometry for a photon still waiting for its entry Fresnel test (pays when whole warps are in
 // that state - the sorted kernel; the lane kernel computes and overrides, which costs no branch).
-// FLIGHT: plate flights (scenes without outside boxes); FOLD: fold total internal reflections into them.
+// FLIGHT: plate flights (the host enables them only when no outside box shares a z face of the plate: the fold's test
+// is against the world's medium); FOLD: fold total internal reflections into them.
 // LAZY (pool kernel): the photon record carries no attenuation coefficients; the container's is looked up from the
 // wavelength here (same function, same value as refresh_alphas stored) and handed back in `alpha` for the absorption.
 template <bool BRANCH_ENTRY, bool FLIGHT, bool FOLD, bool LAZY = false>
@@ -1116,10 +1123,10 @@ __device__ __forceinline__ int advance_hit(const DevScene& S, Photon& p, const u
 // the sorted kernel's form: the result packed into the pending word that travels with the photon record
 template <bool EXT, bool FLIGHT>
 __device__ __forceinline__ int advance(const DevScene& S, Photon& p, const uint32_t w_x, unsigned& pend, unsigned& n_events) {
-    static_assert(!(EXT && FLIGHT), "plate flights assume air beyond the z faces");
     if (EXT && p.medium == MED_OUT) { pend = CLS_OUT; return -1; }
     Hit h; int cls, extra;
     const int killed = advance_hit<true, FLIGHT, true>(S, p, w_x, h, cls, extra);
+    if (EXT && FLIGHT) p.aux = note_folded(p.aux, extra);
     n_events += (unsigned)extra;
     pend = pack_pending(cls, h.kind, h.face, h.container, h.adj);
     return killed;
@@ -1214,7 +1221,6 @@ __device__ __forceinline__ int interact_surface(const DevScene& S, Photon& p, in
 // one whole iteration: advance, then the interaction it names
 template <bool EXT, bool FLIGHT, bool FOLD = true>
 __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const uint4 w, StepOut& out) {
-    static_assert(!(EXT && FLIGHT), "plate flights assume air beyond the z faces");
     out.extra = 0;
     if (EXT && p.medium == MED_OUT) {
         OutState q;
@@ -1229,6 +1235,7 @@ __device__ __forceinline__ int photon_step(const DevScene& S, Photon& p, const u
     out.ch = p.kc;
     Hit h; int cls;
     const int killed = advance_hit<false, FLIGHT, FOLD>(S, p, w.x, h, cls, out.extra);
+    if (EXT && FLIGHT) p.aux = note_folded(p.aux, out.extra);
     out.medium = h.container; out.kind = h.kind; out.face = h.kind == SURF_CAP ? (h.face & 7) : h.face;
     if (killed >= 0) { out.event = EV_KILL; return killed; }
     if (cls == CLS_ABSORB) {

@@ -35,33 +35,37 @@
 // (tests/test_gpu_sorted_kernel.py covers all three kernels).
 //
 // EXT (scenes with boxes outside the plate - the photovoltaic variants): the air around the plate is a medium with geometry
-// of its own (outside_step).  Such scenes have no plate flights, so the PH_PLATE list serves as PH_OUT - photons travelling
-// outside the plate - and the record grows by a fifth uint4 for the surface bookkeeping word (`aux`) that the EXIT
-// classification of these scenes needs.
+// of its own (outside_step), and photons travelling in it wait in a list of their own: the PH_PLATE list when the scene has
+// no plate flights, a fifth list (PH_AIR, its length in a second counter word) when it has.  The surface bookkeeping
+// word (`aux`) that the EXIT classification of these scenes needs travels in the record's spare word (G3.z).
 #pragma once
 #include "lscpm_device.cuh"
 
 namespace lscpm {
 
 constexpr int PH_FRESH = 0, PH_PLATE = 1, PH_TUBE = 2, PH_EMIT = 3, N_PH = 4;
-constexpr int PH_OUT = PH_PLATE;          // scenes with outside boxes have no plate flights: the list holds the photons in the air
+// photons in the air around the plate (scenes with outside boxes): the plate flights' list when the scene has none, a
+// fifth list with a counter of its own otherwise
+constexpr int PH_AIR = 4;
+__host__ __device__ constexpr int pool_out_phase(bool flight) { return flight ? PH_AIR : PH_PLATE; }
+__host__ __device__ constexpr int pool_lists(bool ext, bool flight) { return (ext && flight) ? 5 : N_PH; }
 
 // record = 4 x uint4 (SoA over the slots of a warp):
 //   G0: xr, y, z, kc | medium << 12 | steps << 16
 //   G1: dx, dy, dz, wl
 //   G2: photon index lo, hi, batch (index into the plan), batch id (Philox counter word)
-//   G3: event counters, emission table of a pending re-emission (PH_EMIT), unused, Philox call counter
-//   G4 (scenes with outside boxes only): aux (surface bookkeeping of the EXIT classification, emission table), unused x 3
-__host__ __device__ constexpr int pool_groups(bool ext) { return ext ? 5 : 4; }
+//   G3: event counters, emission table of a pending re-emission (PH_EMIT), aux (scenes with outside boxes only: surface
+//       bookkeeping of the EXIT classification; it carries the emission table itself there), Philox call counter
+constexpr int POOL_GROUPS = 4;
 
-__host__ __device__ constexpr int pool_list_u4(int nslot) { return (N_PH * nslot + 15) / 16; }
-__host__ __device__ constexpr size_t pool_smem_bytes(int warps, int nslot, int stride, bool ext = false) {
-    return (size_t)warps * (size_t)(pool_groups(ext) * nslot + pool_list_u4(nslot) + (stride + 3) / 4) * 16u;
+__host__ __device__ constexpr int pool_list_u4(int nslot, int n_lists = N_PH) { return (n_lists * nslot + 15) / 16; }
+__host__ __device__ constexpr size_t pool_smem_bytes(int warps, int nslot, int stride, int n_lists = N_PH) {
+    return (size_t)warps * (size_t)(POOL_GROUPS * nslot + pool_list_u4(nslot, n_lists) + (stride + 3) / 4) * 16u;
 }
 
 template <bool FLIGHT, bool EXT = false>
 __device__ __forceinline__ int fly_phase(int medium) {
-    if (EXT) return medium == MED_OUT ? PH_OUT : PH_TUBE;
+    if (EXT && medium == MED_OUT) return pool_out_phase(FLIGHT);
     return (FLIGHT && medium == MED_PLATE) ? PH_PLATE : PH_TUBE;
 }
 
@@ -70,15 +74,18 @@ __device__ __forceinline__ int fly_phase(int medium) {
 // Push the records the active lanes hold onto the lists of their next phases: lanes with the same target find each other
 // with one MATCH and rank themselves inside the group; the group leaders' sizes are summed into the packed counters with
 // one REDUX - independent of how many different targets there are.
-template <int NSLOT>
-__device__ __forceinline__ void pool_push(unsigned char* __restrict__ lists, unsigned& cnt, bool act, int nph, int slot, unsigned lane_lt) {
+// FIVE: the fifth list (PH_AIR) has its length in `cnt_air`; its group is counted with one ballot.
+template <int NSLOT, bool FIVE>
+__device__ __forceinline__ void pool_push(unsigned char* __restrict__ lists, unsigned& cnt, unsigned& cnt_air, bool act, int nph, int slot, unsigned lane_lt) {
     const unsigned grp = __match_any_sync(0xffffffffu, act ? nph : 7);   // idle lanes form a group of their own that is not counted
     const int rank = __popc(grp & lane_lt);
-    const unsigned shift = 8u * (unsigned)nph;
-    const unsigned base = (cnt >> shift) & 0xffu;
+    const bool air = FIVE && nph == PH_AIR;
+    const unsigned shift = air ? 0u : 8u * (unsigned)nph;
+    const unsigned base = air ? cnt_air : ((cnt >> shift) & 0xffu);
     if (act) lists[nph * NSLOT + (int)base + rank] = (unsigned char)slot;
-    const unsigned contrib = (act && rank == 0) ? (unsigned)__popc(grp) << shift : 0u;
+    const unsigned contrib = (act && rank == 0 && !air) ? (unsigned)__popc(grp) << shift : 0u;
     cnt += __reduce_add_sync(0xffffffffu, contrib);
+    if (FIVE) cnt_air += (unsigned)__popc(__ballot_sync(0xffffffffu, act && air));
 }
 
 __device__ __forceinline__ void pool_tally(unsigned long long* __restrict__ tallies, unsigned int* hist, int n_bins, int stride,
@@ -106,21 +113,22 @@ __global__ void __launch_bounds__(WARPS * 32, 1)
 trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_constant__ TraceArgs A) {
     using namespace lscpm;
     static_assert(NSLOT % 8 == 0 && NSLOT <= 255, "slot numbers and list lengths travel as bytes");
-    static_assert(!(EXT && FLIGHT), "plate flights assume air beyond the z faces");
-    constexpr int POOL_GROUPS = pool_groups(EXT);
+    constexpr bool FIVE = EXT && FLIGHT;
+    constexpr int N_LISTS = pool_lists(EXT, FLIGHT), PH_OUT = pool_out_phase(FLIGHT);
     extern __shared__ uint4 pool_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lane_lt = (1u << lane) - 1u;
     const int stride = S.n_bins + LSCPM_N_COUNTERS;
-    const int per_warp = POOL_GROUPS * NSLOT + pool_list_u4(NSLOT) + (stride + 3) / 4;
+    const int per_warp = POOL_GROUPS * NSLOT + pool_list_u4(NSLOT, N_LISTS) + (stride + 3) / 4;
     uint4* G = pool_smem + (size_t)warp * per_warp;
     unsigned char* lists = reinterpret_cast<unsigned char*>(G + POOL_GROUPS * NSLOT);
-    unsigned int* hist = reinterpret_cast<unsigned int*>(G + POOL_GROUPS * NSLOT + pool_list_u4(NSLOT));
+    unsigned int* hist = reinterpret_cast<unsigned int*>(G + POOL_GROUPS * NSLOT + pool_list_u4(NSLOT, N_LISTS));
     for (int b = lane; b < stride; b += 32) hist[b] = 0u;
     for (int i = lane; i < NSLOT; i += 32) lists[PH_FRESH * NSLOT + i] = (unsigned char)i;
     __syncwarp();
 
     unsigned cnt = (unsigned)NSLOT;         // packed list lengths: every record starts empty (PH_FRESH = byte 0)
+    unsigned cnt_air = 0u;                  // length of the fifth list (FIVE)
     int hbatch = -1;                        // batch whose photons the shared row accumulates
     unsigned long long chunk_base = 0;      // work item: photons chunk_base + [c_next, c_end) of batch `cbatch` are unclaimed
     unsigned c_next = 0, c_end = 0;
@@ -135,6 +143,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
         key = max(key, (__byte_perm(cnt, 0u, 0x4441) << 3) | (unsigned)PH_PLATE);
         key = max(key, (__byte_perm(cnt, 0u, 0x4442) << 3) | (unsigned)PH_TUBE);
         key = max(key, ((cnt >> 24) << 3) | (unsigned)PH_EMIT);
+        if (FIVE) key = max(key, (cnt_air << 3) | (unsigned)PH_AIR);
         const int best = (int)(key >> 3);
         if (best == 0) break;
         const int ph = (int)(key & 7u);
@@ -165,7 +174,8 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
         int slot = 0;
         if (act) slot = lists[ph * NSLOT + best - n + lane];
         LSCPM_CHECK(slot >= 0 && slot < NSLOT);
-        cnt -= (unsigned)n << (8 * ph);
+        if (FIVE && ph == PH_AIR) cnt_air -= (unsigned)n;
+        else cnt -= (unsigned)n << (8 * ph);
         int nph = PH_FRESH;
         int tbin = -1, tbatch = 0;          // a photon that ended in this execution: tallied once, below
         unsigned tevents = 0u;
@@ -196,7 +206,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                         p.xr = __uint_as_float(g0.x); p.y = __uint_as_float(g0.y); p.z = __uint_as_float(g0.z);
                         p.kc = g0.w & 0xfff; p.medium = (g0.w >> 12) & 15; p.steps = g0.w >> 16;
                         p.wl = __uint_as_float(G[1 * NSLOT + slot].w);
-                        p.aux = EXT ? (int)G[4 * NSLOT + slot].x : (int)(g3.y << 16);    // carries the emission table (bits 16-23)
+                        p.aux = EXT ? (int)g3.z : (int)(g3.y << 16);    // carries the emission table (bits 16-23)
                         rng.p_lo = g2.x; rng.p_hi = g2.y; batch = (int)g2.z; rng.batch = g2.w; rng.calls = g3.w;
                         n_events = g3.x;
                     }
@@ -227,8 +237,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                                                      (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
                     G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl));
                     G[2 * NSLOT + slot] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.batch);
-                    G[3 * NSLOT + slot] = make_uint4(n_events, 0u, 0u, rng.calls);
-                    G[4 * NSLOT + slot].x = (unsigned)p.aux;
+                    G[3 * NSLOT + slot] = make_uint4(n_events, 0u, (unsigned)p.aux, rng.calls);
                     fly = false;
                 }
             }
@@ -243,7 +252,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                     p.dx = __uint_as_float(g1.x); p.dy = __uint_as_float(g1.y); p.dz = __uint_as_float(g1.z); p.wl = __uint_as_float(g1.w);
                     rng.p_lo = g2.x; rng.p_hi = g2.y; batch = (int)g2.z; rng.batch = g2.w; rng.calls = g3.w;
                     n_events = g3.x;
-                    if (EXT) p.aux = (int)G[4 * NSLOT + slot].x;
+                    if (EXT) p.aux = (int)g3.z;
                 }
                 const uint4 w = rng.next(A.rk);
                 Hit h; int cls = CLS_CELL, extra = 0; float alpha = 0.f;
@@ -262,6 +271,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                     if (bin < 0) nph = fly_phase<FLIGHT, EXT>(p.medium);
                 } else {
                     bin = advance_hit<true, FLIGHT, true, true>(S, p, w.x, h, cls, extra, alpha);
+                    if (FIVE) p.aux = note_folded(p.aux, extra);
                     n_events += (unsigned)extra;
                 }
                 if (bin < 0 && !outside) {
@@ -297,12 +307,11 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                                                  (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
                 G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl));
                 if (fresh) G[2 * NSLOT + slot] = make_uint4(rng.p_lo, rng.p_hi, (unsigned)batch, rng.batch);
-                G[3 * NSLOT + slot] = make_uint4(n_events, pend, 0u, rng.calls);
-                if (EXT) G[4 * NSLOT + slot].x = (unsigned)p.aux;
+                G[3 * NSLOT + slot] = make_uint4(n_events, pend, EXT ? (unsigned)p.aux : 0u, rng.calls);
             }
         }
         if (tbin >= 0) pool_tally(A.tallies, hist, S.n_bins, stride, hbatch, tbatch, tbin, tevents);
-        pool_push<NSLOT>(lists, cnt, act, nph, slot, lane_lt);
+        pool_push<NSLOT, FIVE>(lists, cnt, cnt_air, act, nph, slot, lane_lt);
         __syncwarp();   // records and lists written by one lane are read by another in a later iteration
     }
     if (hbatch >= 0) flush_row(hist, A.tallies + (size_t)hbatch * stride, stride, lane);

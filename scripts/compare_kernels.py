@@ -1,4 +1,6 @@
-"""Scratch A/B of the two trace kernels (lane-per-photon vs block-sorted): tallies with the same seed and timing.
+"""A/B of the trace kernels (lane-per-photon, block-sorted, pool configurations): tallies with the same seed and timing.
+
+    python scripts/compare_kernels.py [case ...]      # default: all cases
 
 The photon's fate depends only on (seed, batch id, photon index), so the two kernels must produce the same tallies up
 to a handful of photons whose path flips on a last-bit difference in instruction contraction.
@@ -35,10 +37,13 @@ def timed(plan, tallies, ppb, seed):
     return e0.elapsed_time(e1)
 
 
+ONLY = sys.argv[1:]
 for label, kw in CASES.items():
+    if ONLY and label not in ONLY:
+        continue
     arrays = flatten.flatten_scene(standard_scene(**kw))
     out = {}
-    variants = ("lanes", "sorted", "pool96", "pool64")
+    variants = ("lanes", "sorted", "pool120", "pool96", "pool64")
     for which in variants:
         scene = handle(arrays, which)
         for nb, ppb in ((3, 70_001), (64, 1_000_000)):

@@ -42,6 +42,38 @@ def test_pv_tallies_match_oracle(case, native, built_library):
         assert sum(c for name, c in zip(names, row) if "PV" in name and name.startswith("absorb/")) > 0.05 * n
 
 
+def test_box_on_a_z_face_rules_plate_flights_out(native, built_library):
+    """Plate flights fold the reflections at the z faces with the test against the world's medium; the library enables
+    them for scenes with outside boxes only when no box shares one of those faces.  The reference's bottom cells hang
+    centimetres below the plate (flights on); pushed up against the plate they are optically coupled to it (n = 3.4 beyond the
+    face: no total internal reflection there) and the cell march must run - tallies against the oracle either way."""
+    from lscpm_b200 import backend, flatten
+
+    arrays = flatten.flatten_scene(standard_scene(tilt=0, elevation=90, wavelength=585.0, add_bottom_PV=True))
+    assert "flight=1" in backend.SceneHandle(arrays, 0).kernel_name
+    i = arrays.node_name.index("bottomPV")
+    plate = int(arrays.node_parent[i])
+    # poses are world poses; the plate is level (tilt 0), so only z matters
+    touching = arrays.node_pose[plate, 11] - (arrays.node_size[plate, 2] + arrays.node_size[i, 2]) / 2
+    assert arrays.node_pose[i, 11] < touching - 0.01            # as built: an air gap of centimetres
+    arrays.node_pose[i, 11] = touching                          # top face of the cells = bottom face of the plate
+    scene = backend.SceneHandle(arrays, 0)
+    assert scene.kernel_name.startswith("trace_pool_kernel<ext=1, flight=0"), scene.kernel_name
+    n = 300_000
+    row = backend.trace_lights(arrays, [arrays.light], n, seed=3, device=0)[0]
+    batches, _ = backend.pack_batches([arrays.light])
+    ref = _oracle(arrays, native).trace(batches[0], photon_count=n, seed=4)
+    names = arrays.bin_names()
+    nb = len(names)
+    assert row[:nb].sum() == n and ref[:nb].sum() == n
+    assert_tallies_agree(names, row[:nb], ref[:nb], label="coupled cells", resample=lambda: backend.trace_lights(
+        arrays, [arrays.light], n, seed=5, device=0)[0][:nb])
+    assert abs(row[nb] - ref[nb]) / ref[nb] < 0.01
+    # the coupled cells drain the trapped light: several times the share the hanging cells see
+    coupled = sum(c for name, c in zip(names, row) if name.startswith("absorb/bottomPV"))
+    assert coupled > 0.3 * n, coupled / n
+
+
 def test_pv_probe_matches_oracle(native, built_library):
     import pvtrace_oracle as po
     from lscpm_b200 import backend, flatten

@@ -55,7 +55,7 @@ def test_sorted_kernel_is_bit_identical(label):
         np.testing.assert_array_equal(a, b, err_msg=f"{label} batches={n_batches} photons={photons}")
 
 
-POOL_CASES = sorted(CASES)   # scenes with outside boxes included: their pool kernel carries a fifth record group
+POOL_CASES = sorted(CASES)   # scenes with outside boxes included: their pool kernel has an air phase and carries `aux` in the record
 
 
 @pytest.mark.parametrize("which", ["pool120", "pool96", "pool80", "pool64"])
@@ -92,11 +92,11 @@ def test_default_kernel_of_the_standard_scene_is_the_pool_kernel_and_agrees_with
     tallies = plan.new_tallies()
     plan.trace_into(tallies, 250_000, 99)
     np.testing.assert_array_equal(a, tallies.cpu().numpy())
-    # a plate without luminophore stays on the lane kernel; scenes with outside boxes use the pool kernel with five-group records
+    # a plate without luminophore stays on the lane kernel; scenes with outside boxes use the pool kernel too (plate flights included: no box shares a z face)
     no_dye = backend.SceneHandle(flatten.flatten_scene(standard_scene(include_dye=False)), 0)
     assert no_dye.kernel_name.startswith("trace_kernel<ext=0, flight=0"), no_dye.kernel_name
     pv = backend.SceneHandle(flatten.flatten_scene(standard_scene(add_bottom_PV=True)), 0)
-    assert pv.kernel_name.startswith("trace_pool_kernel<ext=1, flight=0"), pv.kernel_name
+    assert pv.kernel_name.startswith("trace_pool_kernel<ext=1, flight=1"), pv.kernel_name
 
 
 def test_sorted_kernel_photon_offset_and_many_small_batches():

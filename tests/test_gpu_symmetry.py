@@ -237,7 +237,8 @@ def _scene_handle_with_env(arrays, **env):
 
 
 @pytest.mark.parametrize("case", [dict(tilt=0, elevation=90, spectrum=am15_like_photon_spectrum()),
-                                  dict(tilt=35, elevation=30, azimuth=150, wavelength=585.0)])
+                                  dict(tilt=35, elevation=30, azimuth=150, wavelength=585.0),
+                                  dict(tilt=0, elevation=60, spectrum=am15_like_photon_spectrum(), add_bottom_PV=True, add_side_PV=True)])
 def test_folded_flights_agree_with_explicit_bounces(case, built_library):
     """The default path takes a photon in the plastic straight to its next real event through the unfolded lattice of
     capillary images (plate_flight, pool kernel); with LSCPM_PLATE_FLIGHTS=0 the lane kernel marches cell by cell and
