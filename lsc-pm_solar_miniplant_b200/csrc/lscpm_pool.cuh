@@ -244,6 +244,7 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
             // ---- step draw, nearest interface, free path, move; absorption is settled here as well ---------------
             bool keep = false;              // the photon lives on: its record is written back below, by all such lanes at once
             unsigned pend = 0u;             // emission table of a pending re-emission
+            bool emitted = false;
             if (fly) {
                 if (!is_source) {
                     const uint4 g0 = G[0 * NSLOT + slot], g1 = G[1 * NSLOT + slot], g2 = G[2 * NSLOT + slot], g3 = G[3 * NSLOT + slot];
@@ -268,7 +269,6 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                     if (r.entered) { p.y = r.y; locate_in_plate(S, p, r.x, r.z); }
                     else { p.kc = 0; p.xr = r.x - axis_x(S, 0); p.y = r.y; p.z = r.z - S.zc; }
                     bin = r.bin;
-                    if (bin < 0) nph = fly_phase<FLIGHT, EXT>(p.medium);
                 } else {
                     bin = advance_hit<true, FLIGHT, true, true>(S, p, w.x, h, cls, extra, alpha);
                     if (FIVE) p.aux = note_folded(p.aux, extra);
@@ -281,19 +281,16 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
                         bin = interact_absorb_alpha(S, p, h.container, alpha, u01(w.y), w.z, ev);
                         if (bin < 0) {   // re-emitted by the luminophore: the emission table travels in the pending word
                             n_events += 0x10000u;
-                            nph = PH_EMIT;
+                            emitted = true;
                             pend = (unsigned)(p.aux >> 16) & 0xffu;
                         }
-                    } else if (cls == CLS_CELL) {
-                        nph = fly_phase<FLIGHT, EXT>(p.medium);
-                    } else {
+                    } else if (cls != CLS_CELL) {
                         // Fresnel test on the interface the photon was moved to, in the same execution: about half of a
                         // flight's lanes are here, and a phase of its own would cost them more in bookkeeping and record
                         // traffic than the idle lanes cost here
                         n_events += 1u;
                         int ev;
                         bin = interact_surface<EXT>(S, p, h.kind, h.face, h.container, h.adj, u01(w.y), ev);
-                        if (bin < 0) nph = fly_phase<FLIGHT, EXT>(p.medium);
                     }
                 }
                 if (bin >= 0) { tbin = bin; tbatch = batch; tevents = n_events; }
@@ -303,6 +300,8 @@ trace_pool_kernel(const __grid_constant__ lscpm::DevScene S, const __grid_consta
             // compiler duplicates the write-back into every one of them (profile of v4: the stores ran at 12.5 lanes)
             __syncwarp();
             if (keep) {
+                // the next phase is chosen here, once, by all surviving lanes (in the branches above it ran at 6 lanes)
+                nph = emitted ? PH_EMIT : fly_phase<FLIGHT, EXT>(p.medium);
                 G[0 * NSLOT + slot] = make_uint4(__float_as_uint(p.xr), __float_as_uint(p.y), __float_as_uint(p.z),
                                                  (unsigned)p.kc | ((unsigned)p.medium << 12) | ((unsigned)p.steps << 16));
                 G[1 * NSLOT + slot] = make_uint4(__float_as_uint(p.dx), __float_as_uint(p.dy), __float_as_uint(p.dz), __float_as_uint(p.wl));
