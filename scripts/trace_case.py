@@ -22,6 +22,7 @@ CASES = {
     "no_dye": dict(tilt=0, elevation=90, spectrum=am15_like_photon_spectrum(), include_dye=False),
     "pv_both": dict(tilt=0, elevation=60, spectrum=am15_like_photon_spectrum(), add_bottom_PV=True, add_side_PV=True),
     "pv_bottom_tilted": dict(tilt=40, elevation=50, wavelength=555.0, add_bottom_PV=True),
+    "pv_no_dye": dict(tilt=10, elevation=60, spectrum=am15_like_photon_spectrum(), include_dye=False, add_bottom_PV=True, add_side_PV=True),
 }
 
 label = sys.argv[1] if len(sys.argv) > 1 else "am15"
