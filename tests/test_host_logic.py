@@ -269,3 +269,21 @@ def test_lazy_distribution_behaves_like_distribution():
     u = np.linspace(0, 1, 101)
     assert np.array_equal(a.sample(u), b.sample(u)) and np.array_equal(a.lookup(spec[:, 0]), b.lookup(spec[:, 0]))
     assert np.array_equal(a(500.0), b(500.0)) and isinstance(b, Distribution) and b.hist is False
+
+
+def test_committed_ncu_summary_belongs_to_these_kernel_sources():
+    """bench.py replays the counters of profiles/r2_final_metrics.json in its roofline object only when the summary was
+    captured from the sources the library is built from.  This pins that the committed pair is
+    consistent: whoever edits a kernel re-captures the profile (scripts/run_final_profile_r2.sh, make_final_profile.py)."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_digest", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    metrics, reason = bench.committed_profile()
+    assert metrics is not None, reason
+    assert metrics["source_sha256"] == bench.source_digest()
+    assert metrics["kernel"].startswith("void trace_pool_kernel<0, 1, 24, 120>")
+    assert metrics["photons_per_launch"] == 64_000_000
