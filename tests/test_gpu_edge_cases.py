@@ -63,7 +63,7 @@ def test_photon_indices_beyond_32_bits(built_library):
 
 
 def _custom_scene(n_channels, pitch, with_inner=True, r_outer=0.0015875, r_inner=0.00079375, tilt=0.0, wavelength=585.0,
-                  plate=(0.47, 0.47, 0.008)):
+                  plate=(0.47, 0.47, 0.008), cells=False):
     """A member of the LSC-PM family built with the same object API the reference uses."""
     from lscpm_b200.compat import pvtrace_api as pv
     from lscpm_b200.miniplant import scene_creator as sc
@@ -80,6 +80,11 @@ def _custom_scene(n_channels, pitch, with_inner=True, r_outer=0.0015875, r_inner
                          quantum_yield=0.95, phase_function=pv.isotropic)
     reactor = pv.Node(name="plate", geometry=pv.Box(size=plate, material=pv.Material(
         refractive_index=1.48, components=[pv.Absorber(coefficient=0.1), dye])), parent=world)
+    if cells:   # photovoltaic absorbers as the reference places them: one under the plate behind an air gap, one strip on an edge
+        opaque = pv.Material(refractive_index=3.4, components=[pv.Absorber(coefficient=1e10)])
+        pv.Node(name="bottomPV", geometry=pv.Box(size=plate, material=opaque), parent=reactor).translate((0, 0, -0.025))
+        pv.Node(name="sidePV1", geometry=pv.Box(size=(plate[0], 0.01, plate[2]), material=opaque),
+                parent=reactor).translate((0, 0.5 * plate[1] + 0.005, 0))
     mix = pv.Reactor(np.array(spectra["mb_abs"]))
     tube_geom = pv.Cylinder(length=plate[1], radius=r_outer, material=pv.Material(refractive_index=1.34, components=[pv.Absorber(coefficient=0.1)]))
     x0 = -0.5 * pitch * (n_channels - 1)
@@ -101,11 +106,16 @@ def _custom_scene(n_channels, pitch, with_inner=True, r_outer=0.0015875, r_inner
     ("single_capillary", dict(n_channels=1, pitch=0.03)),
     ("dense_grid_46_channels", dict(n_channels=46, pitch=0.01, wavelength=555.0)),
     ("fat_tubes_tilted", dict(n_channels=8, pitch=0.05, r_outer=0.003, r_inner=0.002, tilt=25.0)),
+    # outside boxes with plate flights (pool kernel, fifth list) on family members other than the reference's plate
+    ("bare_plate_with_cells", dict(n_channels=0, pitch=0.03, tilt=15.0, cells=True)),
+    ("dense_grid_with_cells", dict(n_channels=46, pitch=0.01, wavelength=555.0, cells=True)),
 ])
 def test_scene_family_variants_match_oracle(label, kw, native, built_library):
     from lscpm_b200 import backend, flatten
 
     arrays = flatten.flatten_scene(_custom_scene(**kw))
+    if kw.get("cells"):
+        assert backend.scene_handle(arrays, 0).kernel_name.startswith("trace_pool_kernel<ext=1, flight=1"), backend.scene_handle(arrays, 0).kernel_name
     n = 200_000
     row = backend.trace_lights(arrays, [arrays.light], n, seed=21, device=0)[0]
     ref = _oracle_row(arrays, native, n)
